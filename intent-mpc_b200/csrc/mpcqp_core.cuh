@@ -1,0 +1,983 @@
+// mpcqp_core.cuh — one-warp-per-QP ADMM solver for the stage-structured MPC QP of
+// trajPlanner::mpcPlanner::solveTraj (reference: trajectory_planner/include/trajectory_planner/
+// mpcPlanner.cpp:375-541; QP layout mpcPlanner.cpp:932-1146), reproducing the iterate sequence of the
+// OSQP 0.6.2 solver the reference calls through OsqpEigen::Solver (constants:
+// third_party/osqp/constants.h:59-118, step structure: third_party/osqp/auxil.h:21-154).
+//
+// This is NOT a port of OSQP/QDLDL.  Differences that matter:
+//   * lane = horizon stage.  All per-stage data (x_k,u_k, the 21+R constraint rows of stage k, the
+//     factor blocks of stage k) live in one shared-memory column [slot][stage], so every per-row /
+//     per-variable step of ADMM is a conflict-free lane-parallel loop and neighbour-stage coupling
+//     (dynamics rows) is a read of column k±1.
+//   * The iteration runs in UN-scaled coordinates: xh = D x, zh = E^-1 z, uh = E^-1 (y/rho).  Ruiz
+//     equilibration (scaling.h: scale_data) then only enters through Rh_i = rho_i E_i^2 and
+//     sigma/D_j^2, the constraint matrix keeps its exact constants (+-1, ts, ts^2/2, obstacle
+//     gradients) and is never stored.  This is algebraically the same iteration as OSQP's
+//     (DESIGN.md §3 derives it); only rounding differs.
+//   * The KKT solve of update_xz_tilde (auxil.h:67) is done on the reduced SPD system
+//     (c P + sigma D^-2 + A' Rh A) xt = rhs.  Slack states, accelerations and slack inputs are "leaf"
+//     variables that are eliminated in closed form, leaving a 6x6 block-tridiagonal system in
+//     (p_k, v_k) that is factored by a twisted (two-ended) block LDL' and solved by 12 lanes with
+//     warp shuffles.
+//
+// The same source compiles for the host when MPCQP_HOST_EMUL is defined: lane loops become plain
+// loops over all stages.  That build exists only for tests/ (logic checks without a GPU); the
+// shipped library contains no host solve path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(MPCQP_HOST_EMUL)
+#define MQ_DEV 1
+#define MQ_HD __device__ __forceinline__
+#define MQ_NOINL __device__ __noinline__
+#else
+#define MQ_DEV 0
+#define MQ_HD inline
+#define MQ_NOINL inline
+#endif
+
+namespace mpcqp {
+
+// third_party/osqp/constants.h:59-118
+constexpr double kRhoMin = 1e-06, kRhoMax = 1e06, kRhoEqOverIneq = 1e03, kRhoTol = 1e-04;
+constexpr double kMinScaling = 1e-04, kMaxScaling = 1e+04, kInfty = 1e30;
+constexpr double kOsqpNan = 2143289344.0;  // constants.h:95-97: (c_float)0x7fc00000UL is this NUMBER
+enum Status : int {                         // constants.h:18-30
+  kDualInfInacc = 4, kPrimInfInacc = 3, kSolvedInacc = 2, kSolved = 1, kMaxIter = -2,
+  kPrimInf = -3, kDualInf = -4, kNonCvx = -7, kUnsolved = -10
+};
+
+constexpr int NX = 8, NU = 5, NV = 13;      // mpcPlanner.h:42-43
+constexpr int NBR = 21;                     // dynamics (8) + box (13) rows per stage; obstacle rows follow
+
+struct Shape {              // batch-uniform problem shape, passed by value
+  int NS;                   // stages = horizon (N+1)
+  int R;                    // obstacle rows per stage (numObs)
+  int n, m;
+  double a_pv, b_pa, b_va;  // dynamics coefficients as the reference inserts them (float-rounded, MP.cpp:1003,1014)
+  double blo[NV], bhi[NV];  // box bounds on (x_k, u_k), stage-uniform (MP.cpp:904-921)
+};
+
+struct Settings {           // third_party/osqp/types.h:139-176 (subset that affects the iterates)
+  double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
+  int max_iter, scaling, adaptive_rho, adaptive_rho_interval, check_termination, warm_start;
+};
+
+struct Batch {              // device pointers
+  const double* pd;             // [NS*13] diagonal of P per stage variable (batch-uniform)
+  const unsigned char* slack;   // [(NS-1)*R] 0: row uses slack input 3 (dynamic), 1: slack input 4 (static)
+  const double* q;              // [B][n]   linear cost, reference variable order
+  const double* x0;             // [B][8]   stage-0 equality right-hand side is -x0
+  const double* g;              // [B][NS-1][R][3] obstacle-row gradients
+  const double* low;            // [B][NS-1][R]    obstacle-row lower bounds (upper = +inf)
+  const double* warm_x;         // [B][n] or nullptr
+  double* x;                    // [B][n]
+  double* y;                    // [B][m] or nullptr
+  int* status; int* iter; int* rho_updates;
+  double* obj; double* pri_res; double* dua_res;
+  double* ws;                   // per-warp scratch, ws_doubles(shape) each
+  int B;
+};
+
+struct Lay {  // shared-memory slot map; element (slot, k) is at sm[slot*NS + k]
+  int NS, R, MK;
+  int oX, oZ, oU, oRH, oSD, oCQ, oG3, oLO, oB, oW, oTD, oMA, oSI, oGG, oDSI, oESD, oDGI, oFS, oDAI, oCV, nslots;
+  MQ_HD void init(int NS_, int R_) {
+    NS = NS_; R = R_; MK = NBR + R_;
+    int o = 0;
+    oX = o; o += NV; oZ = o; o += MK; oU = o; o += MK; oRH = o; o += MK; oSD = o; o += NV; oCQ = o; o += NV;
+    oG3 = o; o += 3 * R; oLO = o; o += R; oB = o; o += NV; oW = o; o += NV; oTD = o; o += 8; oMA = o; o += 3;
+    oSI = o; o += 36; oGG = o; o += 36; oDSI = o; o += 2; oESD = o; o += 2; oDGI = o; o += 2; oFS = o; o += 6;
+    oDAI = o; o += 3; oCV = o; o += 12;
+    nslots = o;
+  }
+};
+inline int smem_doubles(int NS, int R) { Lay L; L.init(NS, R); return L.nslots * NS; }
+inline int ws_doubles(int NS, int R) { return (2 * (NBR + R) + 2 * NV) * NS; }
+
+#if MQ_DEV
+#define MQ_FOR_STAGES(k) for (int k = lane; k < NS; k += 32)
+#define MQ_SYNC() __syncwarp()
+#else
+#define MQ_FOR_STAGES(k) for (int k = 0; k < NS; ++k)
+#define MQ_SYNC() ((void)0)
+#endif
+
+MQ_HD double limit_scaling(double v) { v = v < kMinScaling ? 1.0 : v; return v > kMaxScaling ? kMaxScaling : v; }
+
+// In-place inverse of a symmetric positive definite 6x6 (Gauss-Jordan, no pivoting).
+MQ_HD void inv6(double* a) {
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    double piv = 1.0 / a[p * 6 + p];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) if (j != p) a[p * 6 + j] *= piv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) if (i != p) {
+      double f = a[i * 6 + p];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) if (j != p) a[i * 6 + j] -= f * a[p * 6 + j];
+      a[i * 6 + p] = -f * piv;
+    }
+    a[p * 6 + p] = piv;
+  }
+}
+
+struct Qp {
+  double* sm; Lay L; Shape sh; Settings st; int NS, N, R, MK, lane;
+  const double* pd; const unsigned char* slack; const double* x0p;
+  double *wsE, *wsD, *wsDY, *wsDX;
+  double c, cinv, rho, nq, nq_s;                 // cost scaling, current rho, |q|_inf norms (unscaled / scaled)
+  double pri_res, dua_res, obj, nAx, nZ, nPx, nAty, pri_s, dua_s, nAx_s, nZ_s, nPx_s, nAty_s;
+  int status, info_iter, rho_updates;
+
+#define X_(j, k) sm[(L.oX + (j)) * NS + (k)]
+#define Z_(i, k) sm[(L.oZ + (i)) * NS + (k)]
+#define U_(i, k) sm[(L.oU + (i)) * NS + (k)]
+#define RH_(i, k) sm[(L.oRH + (i)) * NS + (k)]
+#define SD_(j, k) sm[(L.oSD + (j)) * NS + (k)]
+#define CQ_(j, k) sm[(L.oCQ + (j)) * NS + (k)]
+#define G3_(i, k) sm[(L.oG3 + (i)) * NS + (k)]
+#define LO_(o, k) sm[(L.oLO + (o)) * NS + (k)]
+#define B_(j, k) sm[(L.oB + (j)) * NS + (k)]
+#define W_(j, k) sm[(L.oW + (j)) * NS + (k)]
+#define TD_(r, k) sm[(L.oTD + (r)) * NS + (k)]
+#define MA_(c, k) sm[(L.oMA + (c)) * NS + (k)]
+#define SI_(e, k) sm[(L.oSI + (e)) * NS + (k)]
+#define GG_(e, k) sm[(L.oGG + (e)) * NS + (k)]
+#define DSI_(t, k) sm[(L.oDSI + (t)) * NS + (k)]
+#define ESD_(t, k) sm[(L.oESD + (t)) * NS + (k)]
+#define DGI_(t, k) sm[(L.oDGI + (t)) * NS + (k)]
+#define FS_(e, k) sm[(L.oFS + (e)) * NS + (k)]
+#define DAI_(c, k) sm[(L.oDAI + (c)) * NS + (k)]
+#define CV_(e, k) sm[(L.oCV + (e)) * NS + (k)]
+#define PK_(chain, e) sm[(L.oB + (e)) * NS + (NS / 2) + (chain)]
+#define WSE_(i, k) wsE[(i) * NS + (k)]
+#define WSD_(j, k) wsD[(j) * NS + (k)]
+#define WSDY_(i, k) wsDY[(i) * NS + (k)]
+#define WSDX_(j, k) wsDX[(j) * NS + (k)]
+#define SLK_(o, k) ((int)slack[(k) * R + (o)])
+
+  MQ_HD int nrows(int k) const { return k < N ? MK : 16; }
+  MQ_HD int nvars(int k) const { return k < N ? NV : NX; }
+
+  // ---- warp reductions -------------------------------------------------------------------
+  MQ_HD double wmax(double v) const {
+#if MQ_DEV
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+    return v;
+  }
+  MQ_HD double wsum(double v) const {
+#if MQ_DEV
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+  }
+  MQ_HD bool wany(bool p) const {
+#if MQ_DEV
+    return __any_sync(0xffffffffu, p);
+#else
+    return p;
+#endif
+  }
+
+  // ---- un-scaled bounds of row i of stage k (MP.cpp:1074-1146) -----------------------------
+  MQ_HD void row_bounds(int k, int i, double& lo, double& hi) const {
+    if (i < 8) { double v = (k == 0) ? -x0p[i] : 0.0; lo = v; hi = v; }
+    else if (i < NBR) { lo = sh.blo[i - 8]; hi = sh.bhi[i - 8]; }
+    else { lo = LO_(i - NBR, k); hi = INFINITY; }
+  }
+  // rho class on SCALED bounds (auxil.h: set_rho_vec): -1 loose, 1 equality, 0 inequality
+  MQ_HD int row_type(double e, double lo, double hi) const {
+    double ls = e * lo, us = e * hi;
+    if (ls < -kInfty * kMinScaling && us > kInfty * kMinScaling) return -1;
+    if (us - ls < kRhoTol) return 1;
+    return 0;
+  }
+  MQ_HD double rho_of_type(int t) const { return t < 0 ? kRhoMin : (t > 0 ? kRhoEqOverIneq * rho : rho); }
+
+  // (A v)_i for row i of stage k; v(j,k) accessor.  Row content: MP.cpp:989-1071.
+  template <class F> MQ_HD double row_ax(int k, int i, F v) const {
+    if (i < 8) {
+      double s = -v(i, k);
+      if (k > 0) {
+        if (i < 3) s += v(i, k - 1) + sh.a_pv * v(3 + i, k - 1) + sh.b_pa * v(8 + i, k - 1);
+        else if (i < 6) s += v(i, k - 1) + sh.b_va * v(5 + i, k - 1);
+        else s += v(5 + i, k - 1);
+      }
+      return s;
+    } else if (i < NBR) return v(i - 8, k);
+    int o = i - NBR;
+    return G3_(3 * o, k) * v(0, k) + G3_(3 * o + 1, k) * v(1, k) + G3_(3 * o + 2, k) * v(2, k) - v(11 + SLK_(o, k), k);
+  }
+  // (A' t)_j for variable j of stage k; t(i,k) accessor over rows (must be readable for stage k+1).
+  template <class F> MQ_HD double col_aty(int k, int j, F t) const {
+    double s = t(8 + j, k);
+    if (j < 8) s -= t(j, k);
+    if (k < N) {
+      if (j < 3) { s += t(j, k + 1); for (int o = 0; o < R; ++o) s += G3_(3 * o + j, k) * t(NBR + o, k); }
+      else if (j < 6) s += sh.a_pv * t(j - 3, k + 1) + t(j, k + 1);
+      else if (j < 8) {}
+      else if (j < 11) s += sh.b_pa * t(j - 8, k + 1) + sh.b_va * t(j - 5, k + 1);
+      else { s += t(j - 5, k + 1); for (int o = 0; o < R; ++o) if (SLK_(o, k) == j - 11) s -= t(NBR + o, k); }
+    }
+    return s;
+  }
+
+  // ---- setup: load, Ruiz equilibration (scaling.h: scale_data), rho vector, warm start --------
+  MQ_NOINL void load_and_scale(const Batch& bt, int b) {
+    const double* q = bt.q + (size_t)b * sh.n;
+    const double* gp = bt.g + (size_t)b * N * R * 3;
+    const double* lp = bt.low + (size_t)b * N * R;
+    MQ_FOR_STAGES(k) {
+      for (int j = 0; j < NV; ++j) {
+        bool ex = j < nvars(k);
+        CQ_(j, k) = ex ? (j < 8 ? q[8 * k + j] : q[8 * NS + 5 * k + (j - 8)]) : 0.0;
+        SD_(j, k) = 1.0;  // D during Ruiz
+        B_(j, k) = 0.0; W_(j, k) = 0.0; X_(j, k) = 0.0;
+      }
+      for (int i = 0; i < MK; ++i) { RH_(i, k) = 1.0; Z_(i, k) = 0.0; U_(i, k) = 0.0; }  // RH holds E during Ruiz
+      for (int o = 0; o < R; ++o) {
+        bool ex = k < N;
+        G3_(3 * o, k) = ex ? gp[(k * R + o) * 3] : 0.0;
+        G3_(3 * o + 1, k) = ex ? gp[(k * R + o) * 3 + 1] : 0.0;
+        G3_(3 * o + 2, k) = ex ? gp[(k * R + o) * 3 + 2] : 0.0;
+        LO_(o, k) = ex ? lp[k * R + o] : 0.0;
+      }
+      for (int r = 0; r < 8; ++r) TD_(r, k) = 0.0;
+      for (int cc = 0; cc < 3; ++cc) MA_(cc, k) = 0.0;
+    }
+    c = 1.0;
+    MQ_SYNC();
+    const double apv = fabs(sh.a_pv), bpa = fabs(sh.b_pa), bva = fabs(sh.b_va);
+    for (int pass = 0; pass < st.scaling; ++pass) {
+      // column norms of [P A'; A 0] -> W (Dt), row norms of A -> Z (Et); D lives in SD, E in RH
+      MQ_FOR_STAGES(k) {
+        const int nv = nvars(k), nr = nrows(k);
+        for (int j = 0; j < nv; ++j) {
+          double dj = SD_(j, k);
+          double an = RH_(8 + j, k);
+          if (j < 8) an = fmax(an, RH_(j, k));
+          if (k < N) {
+            if (j < 3) { an = fmax(an, RH_(j, k + 1)); for (int o = 0; o < R; ++o) an = fmax(an, RH_(NBR + o, k) * fabs(G3_(3 * o + j, k))); }
+            else if (j < 6) an = fmax(an, fmax(RH_(j - 3, k + 1) * apv, RH_(j, k + 1)));
+            else if (j < 8) {}
+            else if (j < 11) an = fmax(an, fmax(RH_(j - 8, k + 1) * bpa, RH_(j - 5, k + 1) * bva));
+            else { an = fmax(an, RH_(j - 5, k + 1)); for (int o = 0; o < R; ++o) if (SLK_(o, k) == j - 11) an = fmax(an, RH_(NBR + o, k)); }
+          }
+          double pn = fabs(c * pd[k * NV + j]) * dj * dj;
+          W_(j, k) = 1.0 / sqrt(limit_scaling(fmax(pn, an * dj)));
+        }
+        for (int i = 0; i < nr; ++i) {
+          double rn;
+          if (i < 8) {
+            rn = SD_(i, k);
+            if (k > 0) {
+              if (i < 3) rn = fmax(rn, fmax(SD_(i, k - 1), fmax(apv * SD_(3 + i, k - 1), bpa * SD_(8 + i, k - 1))));
+              else if (i < 6) rn = fmax(rn, fmax(SD_(i, k - 1), bva * SD_(5 + i, k - 1)));
+              else rn = fmax(rn, SD_(5 + i, k - 1));
+            }
+          } else if (i < NBR) rn = SD_(i - 8, k);
+          else {
+            int o = i - NBR;
+            rn = SD_(11 + SLK_(o, k), k);
+            for (int cc = 0; cc < 3; ++cc) rn = fmax(rn, fabs(G3_(3 * o + cc, k)) * SD_(cc, k));
+          }
+          Z_(i, k) = 1.0 / sqrt(limit_scaling(rn * RH_(i, k)));
+        }
+      }
+      MQ_SYNC();
+      double psum = 0.0, qmax = 0.0;
+      MQ_FOR_STAGES(k) {
+        const int nv = nvars(k), nr = nrows(k);
+        for (int j = 0; j < nv; ++j) {
+          double dj = SD_(j, k) * W_(j, k);
+          SD_(j, k) = dj;
+          psum += fabs(c * pd[k * NV + j]) * dj * dj;
+          qmax = fmax(qmax, fabs(c * CQ_(j, k) * dj));
+        }
+        for (int i = 0; i < nr; ++i) RH_(i, k) *= Z_(i, k);
+      }
+      psum = wsum(psum); qmax = wmax(qmax);
+      double ct = psum / (double)sh.n;
+      double nqv = limit_scaling(qmax);
+      if (nqv > ct) ct = nqv;
+      ct = limit_scaling(ct);
+      c *= 1.0 / ct;
+      MQ_SYNC();
+    }
+    cinv = 1.0 / c;
+    // finalise: stash E, D (needed for rho estimates / rho updates), form Rh, sigma/D^2, c q
+    rho = fmin(fmax(st.rho, kRhoMin), kRhoMax);
+    double nq0 = 0.0, nq1 = 0.0;
+    MQ_FOR_STAGES(k) {
+      for (int j = 0; j < NV; ++j) {
+        double dj = SD_(j, k);
+        WSD_(j, k) = dj;
+        double cq = c * CQ_(j, k);
+        nq0 = fmax(nq0, fabs(CQ_(j, k)));
+        nq1 = fmax(nq1, fabs(dj * cq));
+        CQ_(j, k) = cq;
+        SD_(j, k) = st.sigma / (dj * dj);
+        W_(j, k) = 0.0; WSDX_(j, k) = 0.0;
+      }
+      const int nr = nrows(k);
+      for (int i = 0; i < MK; ++i) {
+        double e = RH_(i, k);
+        WSE_(i, k) = e; WSDY_(i, k) = 0.0; Z_(i, k) = 0.0;
+        if (i < nr) { double lo, hi; row_bounds(k, i, lo, hi); RH_(i, k) = rho_of_type(row_type(e, lo, hi)) * e * e; }
+        else RH_(i, k) = 0.0;
+      }
+    }
+    nq = wmax(nq0); nq_s = wmax(nq1);
+    // warm start (osqp.h:157): x given, y = 0 (MP.cpp:487), z = A x
+    if (bt.warm_x && st.warm_start) {
+      const double* wx = bt.warm_x + (size_t)b * sh.n;
+      MQ_FOR_STAGES(k) { const int nv = nvars(k); for (int j = 0; j < nv; ++j) X_(j, k) = j < 8 ? wx[8 * k + j] : wx[8 * NS + 5 * k + (j - 8)]; }
+    }
+    MQ_SYNC();
+    MQ_FOR_STAGES(k) { const int nr = nrows(k); for (int i = 0; i < nr; ++i) Z_(i, k) = row_ax(k, i, [&](int j, int kk) { return X_(j, kk); }); }
+    MQ_SYNC();
+  }
+
+  // ---- factorisation of the reduced KKT matrix ---------------------------------------------
+  // Build leaf factors + T blocks per stage (parallel), then the twisted block recursion.
+  MQ_NOINL void factor() {
+    const double apv = sh.a_pv, bpa = sh.b_pa, bva = sh.b_va;
+    // pass 1: leaves, own contributions to Tkk (-> SI) and Tnk (-> GG[0..11])
+    MQ_FOR_STAGES(k) {
+      double hd[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        double h = c * pd[k * NV + j] + SD_(j, k) + RH_(8 + j, k);
+        if (j < 8) h += RH_(j, k);
+        hd[j] = (j < 8 || k < N) ? h : 1.0;
+      }
+      double T[36];
+#pragma unroll
+      for (int e = 0; e < 36; ++e) T[e] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) T[i * 6 + i] = hd[i];
+      // own slack states
+      DSI_(0, k) = 1.0 / hd[6]; DSI_(1, k) = 1.0 / hd[7];
+      double es0 = k > 0 ? -RH_(6, k) : 0.0, es1 = k > 0 ? -RH_(7, k) : 0.0;
+      ESD_(0, k) = es0 / hd[6]; ESD_(1, k) = es1 / hd[7];
+      if (k < N) {
+        double rn[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) rn[r] = RH_(r, k + 1);
+        // slack inputs: eliminate s_{k+1,t} first, then sigma_{k,t}
+        double dsg[2], fs[6];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          double dsn = c * pd[(k + 1) * NV + 6 + t] + SD_(6 + t, k + 1) + RH_(14 + t, k + 1) + rn[6 + t];
+          dsg[t] = hd[11 + t] + rn[6 + t] - rn[6 + t] * rn[6 + t] / dsn;
+          fs[3 * t] = fs[3 * t + 1] = fs[3 * t + 2] = 0.0;
+        }
+        for (int o = 0; o < R; ++o) {
+          double ro = RH_(NBR + o, k), g0 = G3_(3 * o, k), g1 = G3_(3 * o + 1, k), g2 = G3_(3 * o + 2, k);
+          int t = SLK_(o, k);
+          if (t == 0) { dsg[0] += ro; fs[0] -= ro * g0; fs[1] -= ro * g1; fs[2] -= ro * g2; }
+          else { dsg[1] += ro; fs[3] -= ro * g0; fs[4] -= ro * g1; fs[5] -= ro * g2; }
+          T[0] += ro * g0 * g0; T[1] += ro * g0 * g1; T[2] += ro * g0 * g2;
+          T[7] += ro * g1 * g1; T[8] += ro * g1 * g2; T[14] += ro * g2 * g2;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          double di = 1.0 / dsg[t];
+          DGI_(t, k) = di;
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) FS_(3 * t + cc, k) = fs[3 * t + cc];
+          T[0] -= fs[3 * t] * fs[3 * t] * di; T[1] -= fs[3 * t] * fs[3 * t + 1] * di; T[2] -= fs[3 * t] * fs[3 * t + 2] * di;
+          T[7] -= fs[3 * t + 1] * fs[3 * t + 1] * di; T[8] -= fs[3 * t + 1] * fs[3 * t + 2] * di; T[14] -= fs[3 * t + 2] * fs[3 * t + 2] * di;
+        }
+        T[6] = T[1]; T[12] = T[2]; T[13] = T[8];
+        // accelerations + dynamics rows of stage k+1
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          double r1 = rn[cc], r2 = rn[3 + cc];
+          double da = hd[8 + cc] + r1 * bpa * bpa + r2 * bva * bva;
+          double dai = 1.0 / da;
+          double cv0 = r1 * bpa, cv1 = r1 * bpa * apv + r2 * bva, cv2 = -r1 * bpa, cv3 = -r2 * bva;
+          DAI_(cc, k) = dai;
+          CV_(4 * cc, k) = cv0; CV_(4 * cc + 1, k) = cv1; CV_(4 * cc + 2, k) = cv2; CV_(4 * cc + 3, k) = cv3;
+          int ip = cc, iv = 3 + cc;
+          T[ip * 6 + ip] += r1 - cv0 * cv0 * dai;
+          double off = r1 * apv - cv0 * cv1 * dai;
+          T[ip * 6 + iv] += off; T[iv * 6 + ip] += off;
+          T[iv * 6 + iv] += r1 * apv * apv + r2 - cv1 * cv1 * dai;
+          // coupling block (rows stage k+1, cols stage k), axis cc: [pp, pv, vp, vv]
+          GG_(4 * cc, k) = -r1 - cv2 * cv0 * dai;
+          GG_(4 * cc + 1, k) = -r1 * apv - cv2 * cv1 * dai;
+          GG_(4 * cc + 2, k) = -cv3 * cv0 * dai;
+          GG_(4 * cc + 3, k) = -r2 - cv3 * cv1 * dai;
+        }
+      } else {
+        DGI_(0, k) = DGI_(1, k) = 1.0;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) FS_(e, k) = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) { DAI_(cc, k) = 1.0; CV_(4 * cc, k) = CV_(4 * cc + 1, k) = CV_(4 * cc + 2, k) = CV_(4 * cc + 3, k) = 0.0; }
+      }
+#pragma unroll
+      for (int e = 0; e < 36; ++e) SI_(e, k) = T[e];
+    }
+    MQ_SYNC();
+    // pass 2: pull the acceleration-leaf Schur terms of stage k-1 into Tkk[k]
+    MQ_FOR_STAGES(k) {
+      if (k > 0) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          double dai = DAI_(cc, k - 1), cv2 = CV_(4 * cc + 2, k - 1), cv3 = CV_(4 * cc + 3, k - 1);
+          int ip = cc, iv = 3 + cc;
+          SI_(ip * 6 + ip, k) -= cv2 * cv2 * dai;
+          SI_(ip * 6 + iv, k) -= cv2 * cv3 * dai;
+          SI_(iv * 6 + ip, k) -= cv2 * cv3 * dai;
+          SI_(iv * 6 + iv, k) -= cv3 * cv3 * dai;
+        }
+      }
+    }
+    MQ_SYNC();
+    // pass 3: twisted recursion.  chain 0 walks k = 0..mid-1 upward, chain 1 walks k = N..mid+1 downward;
+    // both run the same instruction stream on two lanes.  Their Schur corrections onto the middle block
+    // are parked in the (idle during factorisation) B/W/TD/MA scratch columns mid and mid+1.
+    const int mid = NS / 2;
+#if MQ_DEV
+    const int chain = lane == 0 ? 0 : (lane == 6 ? 1 : -1);
+    if (chain >= 0) factor_chain(chain, mid);
+#else
+    factor_chain(0, mid); factor_chain(1, mid);
+#endif
+    MQ_SYNC();
+#if MQ_DEV
+    if (lane == 0)
+#endif
+    {
+      double S[36];
+#pragma unroll
+      for (int e = 0; e < 36; ++e) {
+        double v = SI_(e, mid);
+        if (mid > 0) v -= PK_(0, e);
+        if (N - mid > 0) v -= PK_(1, e);
+        S[e] = v;
+      }
+      inv6(S);
+#pragma unroll
+      for (int e = 0; e < 36; ++e) SI_(e, mid) = S[e];
+    }
+    MQ_SYNC();
+  }
+  MQ_HD void factor_chain(int chain, int mid) {
+    const int steps = chain == 0 ? mid : N - mid;
+    if (steps <= 0) return;
+    int k = chain == 0 ? 0 : N;
+    const int dk = chain == 0 ? 1 : -1;
+    double S[36], G[36];
+#pragma unroll
+    for (int e = 0; e < 36; ++e) S[e] = SI_(e, k);
+    for (int s = 0; s < steps; ++s) {
+      inv6(S);
+#pragma unroll
+      for (int e = 0; e < 36; ++e) SI_(e, k) = S[e];
+      // coupling C (rows: next stage in walking direction, cols: stage k); per axis [pp pv; vp vv]
+      const int kc = chain == 0 ? k : k - 1;
+      double cpp[3], cpv[3], cvp[3], cvv[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        double a = GG_(4 * cc, kc), bq = GG_(4 * cc + 1, kc), d = GG_(4 * cc + 2, kc), e2 = GG_(4 * cc + 3, kc);
+        cpp[cc] = a; cvv[cc] = e2; cpv[cc] = chain == 0 ? bq : d; cvp[cc] = chain == 0 ? d : bq;
+      }
+      // G = C * Sinv
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          G[cc * 6 + j] = cpp[cc] * S[cc * 6 + j] + cpv[cc] * S[(3 + cc) * 6 + j];
+          G[(3 + cc) * 6 + j] = cvp[cc] * S[cc * 6 + j] + cvv[cc] * S[(3 + cc) * 6 + j];
+        }
+      const int kn = k + dk;
+      // S_next = Tkk[kn] - G * C'
+      double Snext[36];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          Snext[i * 6 + cc] = G[i * 6 + cc] * cpp[cc] + G[i * 6 + 3 + cc] * cpv[cc];
+          Snext[i * 6 + 3 + cc] = G[i * 6 + cc] * cvp[cc] + G[i * 6 + 3 + cc] * cvv[cc];
+        }
+      // store G of stage k.  Chain 0 read its coupling from this very column above; chain 1 read
+      // it from column k-1, which it overwrites only at its next step.
+#pragma unroll
+      for (int e = 0; e < 36; ++e) GG_(e, k) = G[e];
+      if (kn == mid) {
+#pragma unroll
+        for (int e = 0; e < 36; ++e) PK_(chain, e) = Snext[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 36; ++e) S[e] = SI_(e, kn) - Snext[e];
+      }
+      k = kn;
+    }
+  }
+
+  // ---- one ADMM iteration (auxil.h:67-112: update_xz_tilde, update_x, update_z, update_y) --------
+  // rows_phase<MODE>: MODE 0 = normal iteration tail, 1 = (re)build the right-hand side only (no iterate
+  // update), 2 = normal + record delta_x / delta_y for the infeasibility tests.
+  // Reads x~ from W (own stage and stage k-1), updates X, Z, U in place and leaves in B the part of the next
+  // right-hand side  sigma D^-2 x - c q + A' Rh (z - u)  that comes from stage k's own rows; TD gets the
+  // dynamics-row terms that stage k-1 must add (rhs_finish).
+  template <int MODE> MQ_HD void rows_phase() {
+    const double al = st.alpha, om = 1.0 - st.alpha;
+    MQ_FOR_STAGES(k) {
+      double xo[NV], xm[NV], racc[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { racc[j] = 0.0; xo[j] = 0.0; xm[j] = 0.0; }
+      if (MODE != 1) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { xo[j] = W_(j, k); xm[j] = k > 0 ? W_(j, k - 1) : 0.0; }
+      }
+      // dynamics rows
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        double z = Z_(r, k), u = U_(r, k);
+        if (MODE != 1) {
+          double zt = -xo[r];
+          if (r < 3) zt += xm[r] + sh.a_pv * xm[3 + r] + sh.b_pa * xm[8 + r];
+          else if (r < 6) zt += xm[r] + sh.b_va * xm[5 + r];
+          else zt += xm[5 + r];
+          double bnd = (k == 0) ? -x0p[r] : 0.0;
+          double v = al * zt + om * z + u;
+          z = fmin(fmax(v, bnd), bnd);
+          double un = v - z;
+          if (MODE == 2) WSDY_(r, k) = RH_(r, k) * (un - u);
+          u = un;
+          Z_(r, k) = z; U_(r, k) = u;
+        }
+        double t = RH_(r, k) * (z - u);
+        TD_(r, k) = t;
+        racc[r] -= t;
+      }
+      // box rows
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (j < 8 || k < N) {
+          double z = Z_(8 + j, k), u = U_(8 + j, k);
+          if (MODE != 1) {
+            double v = al * xo[j] + om * z + u;
+            z = fmin(fmax(v, sh.blo[j]), sh.bhi[j]);
+            double un = v - z;
+            if (MODE == 2) WSDY_(8 + j, k) = RH_(8 + j, k) * (un - u);
+            u = un;
+            Z_(8 + j, k) = z; U_(8 + j, k) = u;
+          }
+          racc[j] += RH_(8 + j, k) * (z - u);
+        }
+      }
+      // obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low
+      if (k < N) {
+        for (int o = 0; o < R; ++o) {
+          const int i = NBR + o;
+          double g0 = G3_(3 * o, k), g1 = G3_(3 * o + 1, k), g2 = G3_(3 * o + 2, k);
+          const int sl = SLK_(o, k);
+          double z = Z_(i, k), u = U_(i, k);
+          if (MODE != 1) {
+            double zt = g0 * xo[0] + g1 * xo[1] + g2 * xo[2] - (sl ? xo[12] : xo[11]);
+            double v = al * zt + om * z + u;
+            z = fmax(v, LO_(o, k));
+            double un = v - z;
+            if (MODE == 2) WSDY_(i, k) = RH_(i, k) * (un - u);
+            u = un;
+            Z_(i, k) = z; U_(i, k) = u;
+          }
+          double t = RH_(i, k) * (z - u);
+          racc[0] += g0 * t; racc[1] += g1 * t; racc[2] += g2 * t;
+          if (sl) racc[12] -= t; else racc[11] -= t;
+        }
+      }
+      // x update (auxil.h:83 update_x) and the variable part of the next rhs
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        double x = X_(j, k);
+        if (MODE != 1) {
+          double xn = al * xo[j] + om * x;
+          if (MODE == 2) WSDX_(j, k) = xn - x;
+          x = xn;
+          X_(j, k) = x;
+        }
+        B_(j, k) = (j < 8 || k < N) ? racc[j] + SD_(j, k) * x - CQ_(j, k) : 0.0;
+      }
+    }
+    MQ_SYNC();
+  }
+  // Add the dynamics-row terms of stage k+1 to stage k's rhs; publish the acceleration-leaf message.
+  MQ_HD void rhs_finish() {
+    MQ_FOR_STAGES(k) {
+      if (k < N) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          double tp = TD_(cc, k + 1), tv = TD_(3 + cc, k + 1);
+          B_(cc, k) += tp;
+          B_(3 + cc, k) += sh.a_pv * tp + tv;
+          double ba = B_(8 + cc, k) + sh.b_pa * tp + sh.b_va * tv;
+          B_(8 + cc, k) = ba;
+          MA_(cc, k) = DAI_(cc, k) * ba;
+        }
+        B_(11, k) += TD_(6, k + 1);
+        B_(12, k) += TD_(7, k + 1);
+      }
+    }
+    MQ_SYNC();
+  }
+  // Forward elimination of the leaf variables -> reduced 6-vector per stage in B(0..5).
+  MQ_HD void leaf_forward() {
+    MQ_FOR_STAGES(k) {
+      double r[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) r[i] = B_(i, k);
+      if (k < N) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          double r11 = B_(11 + t, k) - ESD_(t, k + 1) * B_(6 + t, k + 1);
+          B_(11 + t, k) = r11;
+          double f = DGI_(t, k) * r11;
+          r[0] -= FS_(3 * t, k) * f; r[1] -= FS_(3 * t + 1, k) * f; r[2] -= FS_(3 * t + 2, k) * f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) { double mm = MA_(cc, k); r[cc] -= CV_(4 * cc, k) * mm; r[3 + cc] -= CV_(4 * cc + 1, k) * mm; }
+      }
+      if (k > 0) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) { double mm = MA_(cc, k - 1); r[cc] -= CV_(4 * cc + 2, k - 1) * mm; r[3 + cc] -= CV_(4 * cc + 3, k - 1) * mm; }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) W_(i, k) = r[i];
+    }
+    MQ_SYNC();
+  }
+  // Twisted block LDL' solve on W(0..5, .):  L w = r (two chains meeting at mid), v = S^-1 w, L' y = v.
+  MQ_HD void chain_solve() {
+    const int mid = NS / 2;
+    const int s_top = mid, s_bot = N - mid;
+    const int nst = s_top > s_bot ? s_top : s_bot;
+#if MQ_DEV
+    const int half = lane / 6, i = lane - 6 * half;
+    const bool mine = half < 2;
+    const int base = mine ? 6 * half : 0;
+    const int dk = half == 0 ? 1 : -1;
+    const int k0 = half == 0 ? 0 : N;
+    const int mysteps = half == 0 ? s_top : (half == 1 ? s_bot : 0);
+    // forward
+    double wi = mine ? W_(i, k0) : 0.0, cm = 0.0;
+    for (int s = 0; s < nst; ++s) {
+      const bool act = s < mysteps;
+      const int k = k0 + dk * s, kn = k + dk;
+      double acc = 0.0;
+      double gr[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) gr[j] = act ? GG_(i * 6 + j, k) : 0.0;
+      double rn = (act && kn != mid) ? W_(i, kn) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc += gr[j] * __shfl_sync(0xffffffffu, wi, base + j);
+      if (act) {
+        if (kn != mid) { wi = rn - acc; W_(i, kn) = wi; }
+        else cm = acc;
+      }
+    }
+    {
+      double cb = __shfl_sync(0xffffffffu, cm, 6 + (lane % 6));
+      if (lane < 6) W_(lane, mid) = W_(lane, mid) - cm - cb;
+    }
+    MQ_SYNC();
+    // v = Sinv w  (lane = stage)
+    MQ_FOR_STAGES(k) {
+      double w[6], v[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) w[j] = W_(j, k);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) s += SI_(a * 6 + j, k) * w[j];
+        v[a] = s;
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) W_(j, k) = v[j];
+    }
+    MQ_SYNC();
+    // backward
+    double yi = W_(lane % 6, mid);
+    for (int s = 0; s < nst; ++s) {
+      const bool act = s < mysteps;
+      const int k = half == 0 ? mid - 1 - s : mid + 1 + s;
+      double gc[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) gc[j] = act ? GG_(j * 6 + i, k) : 0.0;
+      double vk = act ? W_(i, k) : 0.0;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc += gc[j] * __shfl_sync(0xffffffffu, yi, base + j);
+      if (act) { yi = vk - acc; W_(i, k) = yi; }
+    }
+    MQ_SYNC();
+#else
+    for (int k = 0; k < s_top; ++k) {
+      double acc[6];
+      for (int a = 0; a < 6; ++a) { acc[a] = 0; for (int j = 0; j < 6; ++j) acc[a] += GG_(a * 6 + j, k) * W_(j, k); }
+      for (int a = 0; a < 6; ++a) W_(a, k + 1) -= acc[a];
+    }
+    double cb[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = N; k > mid; --k) {
+      double acc[6];
+      for (int a = 0; a < 6; ++a) { acc[a] = 0; for (int j = 0; j < 6; ++j) acc[a] += GG_(a * 6 + j, k) * W_(j, k); }
+      for (int a = 0; a < 6; ++a) W_(a, k - 1) -= acc[a];
+    }
+    (void)cb;
+    for (int k = 0; k < NS; ++k) {
+      double v[6];
+      for (int a = 0; a < 6; ++a) { v[a] = 0; for (int j = 0; j < 6; ++j) v[a] += SI_(a * 6 + j, k) * W_(j, k); }
+      for (int a = 0; a < 6; ++a) W_(a, k) = v[a];
+    }
+    for (int k = mid - 1; k >= 0; --k)
+      for (int a = 0; a < 6; ++a) { double s = 0; for (int j = 0; j < 6; ++j) s += GG_(j * 6 + a, k) * W_(j, k + 1); W_(a, k) -= s; }
+    for (int k = mid + 1; k <= N; ++k)
+      for (int a = 0; a < 6; ++a) { double s = 0; for (int j = 0; j < 6; ++j) s += GG_(j * 6 + a, k) * W_(j, k - 1); W_(a, k) -= s; }
+#endif
+  }
+  // Back-substitution of the leaf variables: accelerations and slack inputs, then slack states.
+  MQ_HD void leaf_backward() {
+    MQ_FOR_STAGES(k) {
+      if (k < N) {
+        double yk[6], yn[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { yk[i] = W_(i, k); yn[i] = W_(i, k + 1); }
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          W_(8 + cc, k) = DAI_(cc, k) * (B_(8 + cc, k) - CV_(4 * cc, k) * yk[cc] - CV_(4 * cc + 1, k) * yk[3 + cc] -
+                                         CV_(4 * cc + 2, k) * yn[cc] - CV_(4 * cc + 3, k) * yn[3 + cc]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          W_(11 + t, k) = DGI_(t, k) * (B_(11 + t, k) - FS_(3 * t, k) * yk[0] - FS_(3 * t + 1, k) * yk[1] - FS_(3 * t + 2, k) * yk[2]);
+      } else {
+#pragma unroll
+        for (int j = 8; j < NV; ++j) W_(j, k) = 0.0;
+      }
+    }
+    MQ_SYNC();
+    MQ_FOR_STAGES(k) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        double v = DSI_(t, k) * B_(6 + t, k);
+        if (k > 0) v -= ESD_(t, k) * W_(11 + t, k - 1);
+        W_(6 + t, k) = v;
+      }
+    }
+    MQ_SYNC();
+  }
+  template <int MODE> MQ_HD void iterate() {
+    leaf_forward();
+    chain_solve();
+    leaf_backward();
+    rows_phase<MODE>();
+    rhs_finish();
+  }
+
+  // ---- update_info (auxil.h:154): un-scaled residuals, objective, and the scaled norms adapt_rho needs ----
+  MQ_NOINL void update_info(int iter) {
+    double red[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) red[e] = 0.0;
+    double ob = 0.0;
+    auto xv = [&](int j, int kk) { return X_(j, kk); };
+    auto yv = [&](int i, int kk) { return RH_(i, kk) * U_(i, kk); };
+    MQ_FOR_STAGES(k) {
+      const int nr = nrows(k), nv = nvars(k);
+      for (int i = 0; i < nr; ++i) {
+        double ax = row_ax(k, i, xv), z = Z_(i, k), e = WSE_(i, k);
+        double d = fabs(ax - z);
+        red[0] = fmax(red[0], d); red[1] = fmax(red[1], fabs(ax)); red[2] = fmax(red[2], fabs(z));
+        red[3] = fmax(red[3], e * d); red[4] = fmax(red[4], e * fabs(ax)); red[5] = fmax(red[5], e * fabs(z));
+      }
+      for (int j = 0; j < nv; ++j) {
+        double x = X_(j, k), p = pd[k * NV + j];
+        double px = c * p * x, aty = col_aty(k, j, yv), dj = WSD_(j, k);
+        double d = fabs(px + CQ_(j, k) + aty);
+        red[6] = fmax(red[6], d); red[7] = fmax(red[7], fabs(px)); red[8] = fmax(red[8], fabs(aty));
+        red[9] = fmax(red[9], dj * d); red[10] = fmax(red[10], dj * fabs(px)); red[11] = fmax(red[11], dj * fabs(aty));
+        ob += (0.5 * p * x + CQ_(j, k) * cinv) * x;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) red[e] = wmax(red[e]);
+    obj = wsum(ob);
+    pri_res = red[0]; nAx = red[1]; nZ = red[2]; pri_s = red[3]; nAx_s = red[4]; nZ_s = red[5];
+    dua_res = red[6] * cinv; nPx = red[7] * cinv; nAty = red[8] * cinv; dua_s = red[9]; nPx_s = red[10]; nAty_s = red[11];
+    info_iter = iter;
+  }
+
+  // auxil.h:137 is_primal_infeasible — delta_y certificate test in un-scaled coordinates (E cancels).
+  MQ_NOINL bool is_primal_infeasible(double eps) {
+    double nd = 0.0;
+    MQ_FOR_STAGES(k) {
+      const int nr = nrows(k);
+      for (int i = 0; i < nr; ++i) {
+        double lo, hi; row_bounds(k, i, lo, hi);
+        double e = WSE_(i, k), ls = e * lo, us = e * hi, dy = WSDY_(i, k);
+        if (us > kInfty * kMinScaling) { if (ls < -kInfty * kMinScaling) dy = 0.0; else dy = fmin(dy, 0.0); }
+        else if (ls < -kInfty * kMinScaling) dy = fmax(dy, 0.0);
+        WSDY_(i, k) = dy;
+        nd = fmax(nd, fabs(dy));
+      }
+    }
+    nd = wmax(nd);
+    MQ_SYNC();
+    if (!(nd > eps)) return false;
+    // IEEE semantics kept on purpose: an infinite bound times a zero multiplier is NaN, which makes the
+    // comparison false — with the reference's +-inf bounds (MP.cpp:913-914) OSQP never declares primal
+    // infeasibility, and neither do we.
+    double lhs = 0.0;
+    MQ_FOR_STAGES(k) {
+      const int nr = nrows(k);
+      for (int i = 0; i < nr; ++i) {
+        double lo, hi; row_bounds(k, i, lo, hi);
+        double dy = WSDY_(i, k);
+        lhs += hi * fmax(dy, 0.0) + lo * fmin(dy, 0.0);
+      }
+    }
+    lhs = wsum(lhs);
+    if (!(lhs < -eps * nd)) return false;
+    double na = 0.0;
+    auto dv = [&](int i, int kk) { return WSDY_(i, kk); };
+    MQ_FOR_STAGES(k) { const int nv = nvars(k); for (int j = 0; j < nv; ++j) na = fmax(na, fabs(col_aty(k, j, dv))); }
+    na = wmax(na);
+    return na < eps * nd;
+  }
+  // auxil.h:148 is_dual_infeasible — delta_x certificate test.
+  MQ_NOINL bool is_dual_infeasible(double eps) {
+    double nd = 0.0, qd = 0.0, pm = 0.0;
+    MQ_FOR_STAGES(k) {
+      const int nv = nvars(k);
+      for (int j = 0; j < nv; ++j) {
+        double dx = WSDX_(j, k);
+        nd = fmax(nd, fabs(dx)); qd += CQ_(j, k) * dx; pm = fmax(pm, fabs(c * pd[k * NV + j] * dx));
+      }
+    }
+    nd = wmax(nd); qd = wsum(qd); pm = wmax(pm);
+    if (!(nd > eps)) return false;
+    if (!(qd < -c * eps * nd)) return false;
+    if (!(pm < c * eps * nd)) return false;
+    bool bad = false;
+    auto dv = [&](int j, int kk) { return WSDX_(j, kk); };
+    MQ_FOR_STAGES(k) {
+      const int nr = nrows(k);
+      for (int i = 0; i < nr; ++i) {
+        double lo, hi; row_bounds(k, i, lo, hi);
+        double e = WSE_(i, k), adx = row_ax(k, i, dv);
+        if ((e * hi < kInfty * kMinScaling && adx > eps * nd) || (e * lo > -kInfty * kMinScaling && adx < -eps * nd)) bad = true;
+      }
+    }
+    return !wany(bad);
+  }
+  // auxil.h:133 check_termination
+  MQ_NOINL bool check_termination(bool approx) {
+    double ea = st.eps_abs, er = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+    if (pri_res > kInfty || dua_res > kInfty) { status = kNonCvx; obj = kOsqpNan; return true; }
+    if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+    bool pr = false, dr = false, pinf = false, dinf = false;
+    if (sh.m == 0) pr = true;
+    else { double eps_p = ea + er * fmax(nZ, nAx); if (pri_res < eps_p) pr = true; else pinf = is_primal_infeasible(epi); }
+    double eps_d = ea + er * fmax(nq, fmax(nAty, nPx));
+    if (dua_res < eps_d) dr = true; else dinf = is_dual_infeasible(edi);
+    if (pr && dr) { status = approx ? kSolvedInacc : kSolved; return true; }
+    if (pinf) { status = approx ? kPrimInfInacc : kPrimInf; obj = kInfty; return true; }
+    if (dinf) { status = approx ? kDualInfInacc : kDualInf; obj = -kInfty; return true; }
+    return false;
+  }
+  // auxil.h:21-38 compute_rho_estimate / adapt_rho, osqp.h osqp_update_rho
+  MQ_NOINL void adapt_rho() {
+    double pn = pri_s / (fmax(nZ_s, nAx_s) + 1e-10);
+    double dn = dua_s / (fmax(nq_s, fmax(nAty_s, nPx_s)) + 1e-10);
+    double rn = rho * sqrt(pn / (dn + 1e-10));
+    rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+    if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+      rho = rn;
+      MQ_FOR_STAGES(k) {
+        const int nr = nrows(k);
+        for (int i = 0; i < nr; ++i) {
+          double lo, hi; row_bounds(k, i, lo, hi);
+          double e = WSE_(i, k);
+          int t = row_type(e, lo, hi);
+          if (t >= 0) {
+            double rold = RH_(i, k), rnew = rho_of_type(t) * e * e;
+            U_(i, k) = U_(i, k) * rold / rnew;   // y is kept across a rho update; u = y / Rh
+            RH_(i, k) = rnew;
+          }
+        }
+      }
+      MQ_SYNC();
+      factor();
+      rows_phase<1>();
+      rhs_finish();
+      rho_updates += 1;
+    }
+  }
+
+  // ---- osqp_solve (osqp.h:78) ---------------------------------------------------------------------
+  MQ_NOINL void solve() {
+    status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
+    rows_phase<1>();
+    rhs_finish();
+    int iter; bool can_check = false;
+    for (iter = 1; iter <= st.max_iter; ++iter) {
+      can_check = st.check_termination && (iter % st.check_termination == 0);
+      const bool can_adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+      if (can_check || iter == st.max_iter) iterate<2>(); else iterate<0>();
+      if (can_check) { update_info(iter); if (check_termination(false)) break; }
+      if (can_adapt) { if (!can_check) update_info(iter); adapt_rho(); }
+    }
+    if (!can_check) { update_info(iter - 1); check_termination(false); }
+    if (status == kUnsolved) { if (!check_termination(true)) status = kMaxIter; }
+  }
+
+  // auxil.h:118 store_solution (+ scaling.h unscale_solution): x = D x_s = xh, y = E y_s / c = Rh u / c
+  MQ_NOINL void store(const Batch& bt, int b) {
+    const bool has = status != kPrimInf && status != kPrimInfInacc && status != kDualInf && status != kDualInfInacc && status != kNonCvx;
+    double* xo = bt.x + (size_t)b * sh.n;
+    double* yo = bt.y ? bt.y + (size_t)b * sh.m : nullptr;
+    MQ_FOR_STAGES(k) {
+      const int nv = nvars(k), nr = nrows(k);
+      for (int j = 0; j < nv; ++j) xo[j < 8 ? 8 * k + j : 8 * NS + 5 * k + (j - 8)] = has ? X_(j, k) : kOsqpNan;
+      if (yo) for (int i = 0; i < nr; ++i) {
+        int gi = i < 8 ? 8 * k + i : (i < 16 ? 8 * NS + 8 * k + (i - 8) : (i < NBR ? 16 * NS + 5 * k + (i - 16) : 16 * NS + 5 * N + k * R + (i - NBR)));
+        yo[gi] = has ? RH_(i, k) * U_(i, k) * cinv : kOsqpNan;
+      }
+    }
+#if MQ_DEV
+    if (lane == 0)
+#endif
+    {
+      bt.status[b] = status; bt.iter[b] = info_iter; bt.rho_updates[b] = rho_updates;
+      bt.obj[b] = obj; bt.pri_res[b] = pri_res; bt.dua_res[b] = dua_res;
+    }
+  }
+
+  MQ_HD void init(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_) {
+    sm = smem; sh = shape; st = set; NS = shape.NS; N = NS - 1; R = shape.R; MK = NBR + R; lane = lane_;
+    L.init(NS, R);
+    pd = bt.pd; slack = bt.slack;
+    wsE = ws; wsD = wsE + MK * NS; wsDY = wsD + NV * NS; wsDX = wsDY + MK * NS;
+  }
+  MQ_HD void run(const Batch& bt, int b) {
+    x0p = bt.x0 + (size_t)b * 8;
+    load_and_scale(bt, b);
+    factor();
+    solve();
+    store(bt, b);
+    MQ_SYNC();
+  }
+};
+
+}  // namespace mpcqp

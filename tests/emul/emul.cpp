@@ -1,0 +1,33 @@
+// TEST INFRASTRUCTURE ONLY: compiles intent-mpc_b200/csrc/mpcqp_core.cuh for the host (lane loops become
+// plain loops) so the kernel's logic can be checked against the oracle in the CPU-only test tier.
+// Never linked into the shipped library; the product has no host solve path.
+#define MPCQP_HOST_EMUL 1
+#include "../../intent-mpc_b200/csrc/mpcqp_core.cuh"
+#include <vector>
+#include <cstring>
+
+extern "C" int emul_solve_batch(int NS, int R, int B, double a_pv, double b_pa, double b_va, const double* blo,
+                                const double* bhi, const double* settings_d, const int* settings_i,
+                                const double* pd, const unsigned char* slack, const double* q, const double* x0,
+                                const double* g, const double* low, const double* warm_x, double* x, double* y,
+                                int* status, int* iter, int* rho_updates, double* obj, double* pri_res,
+                                double* dua_res) {
+  using namespace mpcqp;
+  Shape sh; sh.NS = NS; sh.R = R; sh.n = 8 * NS + 5 * (NS - 1); sh.m = 16 * NS + 5 * (NS - 1) + R * (NS - 1);
+  sh.a_pv = a_pv; sh.b_pa = b_pa; sh.b_va = b_va;
+  for (int j = 0; j < NV; ++j) { sh.blo[j] = blo[j]; sh.bhi[j] = bhi[j]; }
+  Settings st;
+  st.rho = settings_d[0]; st.sigma = settings_d[1]; st.alpha = settings_d[2]; st.eps_abs = settings_d[3];
+  st.eps_rel = settings_d[4]; st.eps_prim_inf = settings_d[5]; st.eps_dual_inf = settings_d[6];
+  st.adaptive_rho_tolerance = settings_d[7];
+  st.max_iter = settings_i[0]; st.scaling = settings_i[1]; st.adaptive_rho = settings_i[2];
+  st.adaptive_rho_interval = settings_i[3]; st.check_termination = settings_i[4]; st.warm_start = settings_i[5];
+  Batch bt; memset(&bt, 0, sizeof bt);
+  bt.pd = pd; bt.slack = slack; bt.q = q; bt.x0 = x0; bt.g = g; bt.low = low; bt.warm_x = warm_x;
+  bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates; bt.obj = obj;
+  bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B;
+  std::vector<double> sm((size_t)smem_doubles(NS, R)), ws((size_t)ws_doubles(NS, R));
+  Qp qp; qp.init(sm.data(), sh, st, bt, ws.data(), 0);
+  for (int b = 0; b < B; ++b) qp.run(bt, b);
+  return 0;
+}
