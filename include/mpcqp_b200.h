@@ -1,0 +1,143 @@
+/* mpcqp_b200.h — C ABI of the B200-native batched MPC QP engine.
+ *
+ * This is the FFI line a maintainer of kotakondo/Intent-MPC binds instead of OSQP's C API
+ * (reference: trajectory_planner/include/trajectory_planner/third_party/osqp/osqp.h:41-400, used through
+ * OsqpEigen::Solver at trajectory_planner/include/trajectory_planner/mpcPlanner.cpp:436-527).
+ * Plain C types only; no torch, no Eigen.  All functions return 0 on success, a negative mpcqp_error
+ * otherwise; mpcqp_engine_last_error() gives the message.  There is NO CPU fallback: every solve runs the
+ * sm_100a kernels, and engine creation fails if no CUDA device is usable.
+ *
+ * Three groups:
+ *   (1) engine lifecycle, one engine per GPU / host thread;
+ *   (2) the batched entry point: B independent mpcPlanner control-step QPs are ASSEMBLED ON THE DEVICE from
+ *       the planner's own inputs (current state, reference window, per-stage obstacle ellipsoids,
+ *       linearisation point, warm start) and solved, one warp per QP;
+ *   (3) an OSQP-shaped single-problem set (setup / warm_start / solve / info / solution / cleanup) taking
+ *       explicit CSC matrices, which is what the OsqpEigen::Solver-shaped C++ facade
+ *       (intent-mpc_b200/host/OsqpEigenB200.hpp) calls.
+ */
+#ifndef MPCQP_B200_H
+#define MPCQP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpcqp_engine mpcqp_engine;
+typedef struct mpcqp_problem mpcqp_problem;
+
+enum mpcqp_error {
+  MPCQP_OK = 0,
+  MPCQP_ERR_CUDA = -1,          /* a CUDA call failed (no device, out of memory, launch failure) */
+  MPCQP_ERR_ARG = -2,           /* null pointer / bad size */
+  MPCQP_ERR_DATA = -3,          /* OSQP_DATA_VALIDATION_ERROR analogue (osqp constants.h:41-49): l > u, bad dims */
+  MPCQP_ERR_SETTINGS = -4,      /* OSQP_SETTINGS_VALIDATION_ERROR analogue, or a setting the engine does not implement */
+  MPCQP_ERR_STRUCTURE = -5,     /* CSC problem is not the mpcPlanner stage structure (no generic kernel yet) */
+  MPCQP_ERR_NOT_INIT = -7       /* OSQP_WORKSPACE_NOT_INIT_ERROR analogue */
+};
+
+/* Solver status values — identical to OSQP's (third_party/osqp/constants.h:18-30). */
+enum mpcqp_status {
+  MPCQP_DUAL_INFEASIBLE_INACCURATE = 4, MPCQP_PRIMAL_INFEASIBLE_INACCURATE = 3, MPCQP_SOLVED_INACCURATE = 2,
+  MPCQP_SOLVED = 1, MPCQP_MAX_ITER_REACHED = -2, MPCQP_PRIMAL_INFEASIBLE = -3, MPCQP_DUAL_INFEASIBLE = -4,
+  MPCQP_NON_CVX = -7, MPCQP_UNSOLVED = -10
+};
+
+/* Mirrors OSQPSettings (third_party/osqp/types.h:139-176).  Fields the engine does not implement must keep
+ * their default or setup fails with MPCQP_ERR_SETTINGS: polish (0), scaled_termination (0), time_limit (0).
+ * Defaults are OSQP's (constants.h:59-118) except the two determinism pins of SURVEY.md §8(c):
+ * adaptive_rho_interval = 25 (OSQP's 0 derives it from wall-clock time) and time_limit = 0. */
+typedef struct {
+  double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  double adaptive_rho_tolerance, adaptive_rho_fraction, delta, time_limit;
+  int64_t max_iter, scaling, adaptive_rho, adaptive_rho_interval, check_termination, warm_start;
+  int64_t scaled_termination, polish, polish_refine_iter, verbose;
+} mpcqp_settings;
+
+/* Replaces osqp_set_default_settings (osqp.h:41). */
+void mpcqp_set_default_settings(mpcqp_settings* s);
+
+/* Planner parameters = mpcPlanner::initParam keys (mpcPlanner.cpp:19-173) that shape the QP. */
+typedef struct {
+  int32_t horizon;                 /* stages; mpcWindow N = horizon-1 (mpcPlanner.cpp:382) */
+  double ts;
+  double max_vel, max_acc;         /* updateMaxVel / updateMaxAcc */
+  double y_min, y_max, z_min, z_max;
+  double static_safety_dist, dynamic_safety_dist;
+  double static_slack, dynamic_slack;
+  double position_weight, velocity_weight, acceleration_weight;
+} mpcqp_mpc_params;
+
+/* intent_mpc_demo defaults (autonomous_flight/cfg/mpc_navigation/planner_param.yaml:25-39). */
+void mpcqp_default_mpc_params(mpcqp_mpc_params* p);
+
+/* ---- (1) engine lifecycle ------------------------------------------------------------------------- */
+int mpcqp_engine_create(int device, mpcqp_engine** out);
+int mpcqp_engine_destroy(mpcqp_engine* e);
+const char* mpcqp_engine_last_error(const mpcqp_engine* e);
+/* Device time (ms, CUDA events on the engine's stream) of the kernels of the last batch call, and how many
+ * kernels it launched. */
+double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e);
+int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
+/* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */
+int mpcqp_engine_sync(mpcqp_engine* e);
+/* FP64 FMA-pipe microbenchmark (all SMs, 8 independent DFMA chains per thread): the measured roofline
+ * denominator for the solve kernel, in TFLOP/s. */
+int mpcqp_fp64_fma_peak(mpcqp_engine* e, double* tflops);
+/* The engine's CUDA stream (cudaStream_t) so callers can order their own work against it. */
+void* mpcqp_engine_stream(const mpcqp_engine* e);
+
+/* ---- (2) batched entry point ---------------------------------------------------------------------- *
+ * Replaces, for B instances at once, mpcPlanner::solveTraj's assemble + initSolver + setWarmStart +
+ * solveProblem + getSolution sequence (mpcPlanner.cpp:375-541).  Array shapes (row-major, N = horizon-1,
+ * R = num_obs, n = 8*horizon + 5*N, m = 16*horizon + 5*N + R*N):
+ *   x0       [B][6]        current position, velocity            (updateCurrStates, mpcPlanner.cpp:257-263)
+ *   xref     [B][N+1][3]   reference positions                   (getXRef, mpcPlanner.cpp:968-981)
+ *   obs_c    [B][N][R][3]  obstacle centre per stage             (updateObstacleParam, mpcPlanner.cpp:1148-1197)
+ *   obs_semi [B][N][R][3]  semi-axes = size/2 + safety distance
+ *   obs_yaw  [B][N][R]
+ *   obs_dyn  [N][R] int32  1: row is softened by slack input 3 (dynamic), 0: by slack input 4 (static)
+ *   lin_pt   [B][N][3]     linearisation point (previous plan, unshifted, or current position; :1042-1051)
+ *   warm_x   [B][n] or NULL  primal warm start (previous plan; dual warm start is always 0, :487)
+ * Outputs: x [B][n]; y [B][m] or NULL; status/iter/rho_updates [B] int32; obj/pri_res/dua_res [B].
+ * The *_host form takes host pointers (copies in and out on the engine's stream, synchronous on return);
+ * the *_device form takes device pointers and is asynchronous on the engine's stream. */
+int mpcqp_solve_mpc_batch_host(mpcqp_engine* e, const mpcqp_mpc_params* p, const mpcqp_settings* s, int32_t B,
+                               int32_t num_obs, const double* x0, const double* xref, const double* obs_c,
+                               const double* obs_semi, const double* obs_yaw, const int32_t* obs_dyn,
+                               const double* lin_pt, const double* warm_x, double* x, double* y, int32_t* status,
+                               int32_t* iter, int32_t* rho_updates, double* obj, double* pri_res, double* dua_res);
+int mpcqp_solve_mpc_batch_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mpcqp_settings* s, int32_t B,
+                                 int32_t num_obs, const double* x0, const double* xref, const double* obs_c,
+                                 const double* obs_semi, const double* obs_yaw, const int32_t* obs_dyn,
+                                 const double* lin_pt, const double* warm_x, double* x, double* y, int32_t* status,
+                                 int32_t* iter, int32_t* rho_updates, double* obj, double* pri_res,
+                                 double* dua_res);
+
+/* ---- (3) OSQP-shaped single problem (explicit CSC) -------------------------------------------------- *
+ * mpcqp_setup replaces osqp_setup (osqp.h:58): data is copied, the caller's arrays may die afterwards.
+ * P is upper-triangular CSC (n x n), A is CSC (m x n), indices int64 like OSQP's c_int (glob_opts.h:80).
+ * The problem must have the mpcPlanner stage structure (diagonal P; dynamics / box / obstacle row blocks as
+ * mpcPlanner.cpp:989-1071 lays them out); anything else returns MPCQP_ERR_STRUCTURE. */
+int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int64_t m, const int64_t* P_colptr,
+                const int64_t* P_rowidx, const double* P_val, const double* q, const int64_t* A_colptr,
+                const int64_t* A_rowidx, const double* A_val, const double* l, const double* u,
+                const mpcqp_settings* s);
+int mpcqp_warm_start(mpcqp_problem* pr, const double* x, const double* y);   /* osqp_warm_start, osqp.h:157 */
+int mpcqp_warm_start_x(mpcqp_problem* pr, const double* x);                  /* osqp_warm_start_x */
+int mpcqp_update_lin_cost(mpcqp_problem* pr, const double* q_new);           /* osqp_update_lin_cost */
+int mpcqp_update_bounds(mpcqp_problem* pr, const double* l_new, const double* u_new); /* osqp_update_bounds */
+int mpcqp_solve(mpcqp_problem* pr);                                          /* osqp_solve, osqp.h:78 */
+typedef struct {                                                             /* OSQPInfo subset, types.h:66-91 */
+  int64_t iter, status_val, rho_updates;
+  double obj_val, pri_res, dua_res, setup_time, solve_time;
+} mpcqp_info;
+int mpcqp_get_info(const mpcqp_problem* pr, mpcqp_info* info);
+int mpcqp_get_solution(const mpcqp_problem* pr, double* x, double* y);       /* work->solution->x / ->y */
+int mpcqp_cleanup(mpcqp_problem* pr);                                        /* osqp_cleanup */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

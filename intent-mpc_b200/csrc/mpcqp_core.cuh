@@ -30,10 +30,12 @@
 #if defined(__CUDACC__) && !defined(MPCQP_HOST_EMUL)
 #define MQ_DEV 1
 #define MQ_HD __device__ __forceinline__
+#define MQ_HHD __host__ __device__ __forceinline__
 #define MQ_NOINL __device__ __noinline__
 #else
 #define MQ_DEV 0
 #define MQ_HD inline
+#define MQ_HHD inline
 #define MQ_NOINL inline
 #endif
 
@@ -83,7 +85,7 @@ struct Batch {              // device pointers
 struct Lay {  // shared-memory slot map; element (slot, k) is at sm[slot*NS + k]
   int NS, R, MK;
   int oX, oZ, oU, oRH, oSD, oCQ, oG3, oLO, oB, oW, oTD, oMA, oSI, oGG, oDSI, oESD, oDGI, oFS, oDAI, oCV, nslots;
-  MQ_HD void init(int NS_, int R_) {
+  MQ_HHD void init(int NS_, int R_) {
     NS = NS_; R = R_; MK = NBR + R_;
     int o = 0;
     oX = o; o += NV; oZ = o; o += MK; oU = o; o += MK; oRH = o; o += MK; oSD = o; o += NV; oCQ = o; o += NV;
@@ -125,7 +127,7 @@ MQ_HD void inv6(double* a) {
 }
 
 struct Qp {
-  double* sm; Lay L; Shape sh; Settings st; int NS, N, R, MK, lane;
+  double* sm; Lay L; const Shape& sh; const Settings& st; int NS, N, R, MK, lane;
   const double* pd; const unsigned char* slack; const double* x0p;
   double *wsE, *wsD, *wsDY, *wsDX;
   double c, cinv, rho, nq, nq_s;                 // cost scaling, current rho, |q|_inf norms (unscaled / scaled)
@@ -964,8 +966,8 @@ struct Qp {
     }
   }
 
-  MQ_HD void init(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_) {
-    sm = smem; sh = shape; st = set; NS = shape.NS; N = NS - 1; R = shape.R; MK = NBR + R; lane = lane_;
+  MQ_HD Qp(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_) : sh(shape), st(set) {
+    sm = smem; NS = shape.NS; N = NS - 1; R = shape.R; MK = NBR + R; lane = lane_;
     L.init(NS, R);
     pd = bt.pd; slack = bt.slack;
     wsE = ws; wsD = wsE + MK * NS; wsDY = wsD + NV * NS; wsDX = wsDY + MK * NS;

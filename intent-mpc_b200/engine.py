@@ -1,0 +1,175 @@
+"""Host-side Python mirror of the C ABI (include/mpcqp_b200.h) — ctypes only, no solve logic.
+
+`Engine.solve_mpc_batch` is the batched counterpart of `mpcPlanner::solveTraj`
+(trajectory_planner/include/trajectory_planner/mpcPlanner.cpp:375-541): same inputs (current state,
+reference window, per-stage obstacle ellipsoids, linearisation point, warm start), same outputs
+(stacked states/controls solution, OSQP status), for B instances at once.  There is no CPU fallback:
+if the CUDA library is missing or no GPU is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpcqp_b200.so")
+
+STATUS_NAMES = {1: "solved", 2: "solved inaccurate", 3: "primal infeasible inaccurate",
+                4: "dual infeasible inaccurate", -2: "maximum iterations reached", -3: "primal infeasible",
+                -4: "dual infeasible", -7: "non convex", -10: "unsolved"}
+
+
+class Settings(C.Structure):
+    """mpcqp_settings (mirrors OSQPSettings, third_party/osqp/types.h:139-176)."""
+    _fields_ = [(k, C.c_double) for k in ("rho", "sigma", "alpha", "eps_abs", "eps_rel", "eps_prim_inf",
+                                          "eps_dual_inf", "adaptive_rho_tolerance", "adaptive_rho_fraction",
+                                          "delta", "time_limit")] + \
+               [(k, C.c_int64) for k in ("max_iter", "scaling", "adaptive_rho", "adaptive_rho_interval",
+                                         "check_termination", "warm_start", "scaled_termination", "polish",
+                                         "polish_refine_iter", "verbose")]
+
+
+class MpcParamsC(C.Structure):
+    """mpcqp_mpc_params."""
+    _fields_ = [("horizon", C.c_int32)] + \
+               [(k, C.c_double) for k in ("ts", "max_vel", "max_acc", "y_min", "y_max", "z_min", "z_max",
+                                          "static_safety_dist", "dynamic_safety_dist", "static_slack",
+                                          "dynamic_slack", "position_weight", "velocity_weight",
+                                          "acceleration_weight")]
+
+
+class Info(C.Structure):
+    _fields_ = [("iter", C.c_int64), ("status_val", C.c_int64), ("rho_updates", C.c_int64),
+                ("obj_val", C.c_double), ("pri_res", C.c_double), ("dua_res", C.c_double),
+                ("setup_time", C.c_double), ("solve_time", C.c_double)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the in-tree CUDA library; fail loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.mpcqp_engine_last_error.restype = C.c_char_p
+        lib.mpcqp_engine_last_kernel_ms.restype = C.c_double
+        lib.mpcqp_engine_last_launches.restype = C.c_int64
+        lib.mpcqp_engine_stream.restype = C.c_void_p
+        _lib = lib
+    return _lib
+
+
+def default_settings(**overrides) -> Settings:
+    s = Settings()
+    load_library().mpcqp_set_default_settings(C.byref(s))
+    for k, v in overrides.items():
+        if not hasattr(s, k):
+            raise AttributeError(f"unknown setting {k}")
+        setattr(s, k, v)
+    return s
+
+
+def params_to_c(p) -> MpcParamsC:
+    c = MpcParamsC()
+    for k, _ in MpcParamsC._fields_:
+        setattr(c, k, getattr(p, k))
+    return c
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine per GPU / host thread (mpcqp_engine_create)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.mpcqp_engine_create(C.c_int(device), C.byref(self.h))
+        if rc != 0 or not self.h:
+            raise EngineError(f"mpcqp_engine_create(device={device}) failed with {rc}: no usable CUDA device "
+                              "(this engine has no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpcqp_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(f"mpcqp error {rc}: {self.lib.mpcqp_engine_last_error(self.h).decode()}")
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.mpcqp_engine_last_kernel_ms(self.h))
+
+    @property
+    def last_launches(self) -> int:
+        return int(self.lib.mpcqp_engine_last_launches(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.mpcqp_engine_stream(self.h) or 0)
+
+    def sync(self):
+        self._check(self.lib.mpcqp_engine_sync(self.h))
+
+    # ---- batched entry point, host buffers -------------------------------------------------------
+    def solve_mpc_batch(self, mb, settings: Settings | None = None, want_y: bool = False, out: dict | None = None):
+        """Solve every instance of an `MpcBatch` (workloads.py).  Returns dict(x[B,n], y[B,m]|None,
+        status, iter, rho_updates [B] int32, obj, pri_res, dua_res [B])."""
+        s = settings or default_settings()
+        p = params_to_c(mb.params)
+        B, R = mb.B, mb.num_obs
+        n, m = mb.params.n, mb.params.m(R)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        x0, xref, oc, os_, oy, lp, wx = map(f, (mb.x0, mb.xref, mb.obs_c, mb.obs_semi, mb.obs_yaw, mb.lin_pt, mb.warm_x))
+        od = np.ascontiguousarray(mb.obs_dyn, dtype=np.int32)
+        if out is None:
+            out = dict(x=np.empty((B, n)), y=np.empty((B, m)) if want_y else None, status=np.empty(B, np.int32),
+                       iter=np.empty(B, np.int32), rho_updates=np.empty(B, np.int32), obj=np.empty(B),
+                       pri_res=np.empty(B), dua_res=np.empty(B))
+        rc = self.lib.mpcqp_solve_mpc_batch_host(self.h, C.byref(p), C.byref(s), C.c_int32(B), C.c_int32(R), _dp(x0),
+                                                 _dp(xref), _dp(oc), _dp(os_), _dp(oy), _ip(od), _dp(lp), _dp(wx),
+                                                 _dp(out["x"]), _dp(out["y"]), _ip(out["status"]), _ip(out["iter"]),
+                                                 _ip(out["rho_updates"]), _dp(out["obj"]), _dp(out["pri_res"]),
+                                                 _dp(out["dua_res"]))
+        self._check(rc)
+        return out
+
+    # ---- batched entry point, raw pointers (device-resident or pinned host) ----------------------
+    def solve_mpc_batch_ptr(self, params, settings: Settings, B: int, R: int, ptrs: dict, obs_dyn: np.ndarray,
+                            device: bool):
+        """ptrs: name -> integer address for x0,xref,obs_c,obs_semi,obs_yaw,lin_pt,warm_x,x,y,status,iter,
+        rho_updates,obj,pri_res,dua_res (0 / missing = NULL).  device=True: device pointers, asynchronous on the
+        engine stream (call sync()); device=False: host pointers, synchronous."""
+        p = params_to_c(params)
+        od = np.ascontiguousarray(obs_dyn, dtype=np.int32)
+        g = lambda k: C.c_void_p(ptrs.get(k) or None)
+        fn = self.lib.mpcqp_solve_mpc_batch_device if device else self.lib.mpcqp_solve_mpc_batch_host
+        rc = fn(self.h, C.byref(p), C.byref(settings), C.c_int32(B), C.c_int32(R), g("x0"), g("xref"), g("obs_c"),
+                g("obs_semi"), g("obs_yaw"), _ip(od), g("lin_pt"), g("warm_x"), g("x"), g("y"), g("status"), g("iter"),
+                g("rho_updates"), g("obj"), g("pri_res"), g("dua_res"))
+        self._check(rc)

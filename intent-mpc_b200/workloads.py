@@ -148,3 +148,30 @@ def snapshot(params: MpcParams | None = None) -> MpcBatch:
     obs_dyn[:, : min(ns, nd)] = 0            # quirk: static loop clears flags [0, numStatic)
     warm_x, lin_pt = _const_vel_plan(p, x0)
     return MpcBatch(p, x0, xref, obs_c, obs_semi, obs_yaw, obs_dyn, lin_pt, warm_x)
+
+
+def stress_batch(B: int, seed0: int = 0, num_obs: int = 2) -> MpcBatch:
+    """BASELINE.json configs[3]: doubled horizon, tight bounds and infeasible instances (SURVEY.md §8d
+    "Config 4"): horizon 60, maxVel = maxAcc = 1.5, z in [1.9, 2.1].  Instance b cycles through four kinds:
+    0 nominal inside the bounds, 1 start above the z box (oracle: status -2 after 4000 iterations),
+    2 initial speed above maxVel (same), 3 an obstacle whose ellipsoid contains the start (slack saturation)."""
+    p = MpcParams(horizon=60, max_vel=1.5, max_acc=1.5, z_min=1.9, z_max=2.1)
+    mb = static_batch(B, num_obs=num_obs, params=p, seed0=seed0 + 100000)
+    N = p.N
+    for b in range(B):
+        kind = b % 4
+        r = np.random.default_rng(seed0 + 200000 + b)
+        mb.x0[b, 2] = r.uniform(1.95, 2.05)
+        mb.x0[b, 3:6] = r.uniform(-1.0, 1.0, size=3)
+        mb.x0[b, 5] *= 0.05
+        if kind == 1:
+            mb.x0[b, 2] = 2.6
+        elif kind == 2:
+            mb.x0[b, 3] = 2.5
+        elif kind == 3:
+            mb.obs_c[b, :, 0, :] = mb.x0[b, 0:3] + np.array([0.3, 0.1, 0.0])
+        d = GOAL - mb.x0[b, 0:3]
+        d = d / np.linalg.norm(d)
+        mb.xref[b] = mb.x0[b, None, 0:3] + d[None, :] * 1.2 * (np.arange(N + 1) * p.ts)[:, None]
+    mb.warm_x, mb.lin_pt = _const_vel_plan(p, mb.x0)
+    return mb
