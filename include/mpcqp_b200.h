@@ -80,6 +80,11 @@ const char* mpcqp_engine_last_error(const mpcqp_engine* e);
  * kernels it launched. */
 double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e);
 int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
+/* Which solve kernel the last batch ran: 1 = register-resident fast path (compile-time horizon/num_obs),
+ * 0 = generic shared-memory kernel (any horizon/num_obs that fits).  force_generic(1) pins the generic kernel
+ * (used by the tests to cover both). */
+int mpcqp_engine_last_path(const mpcqp_engine* e);
+int mpcqp_engine_force_generic(mpcqp_engine* e, int on);
 /* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */
 int mpcqp_engine_sync(mpcqp_engine* e);
 /* FP64 FMA-pipe microbenchmark (all SMs, 8 independent DFMA chains per thread): the measured roofline

@@ -30,8 +30,8 @@
 #if defined(__CUDACC__) && !defined(MPCQP_HOST_EMUL)
 #define MQ_DEV 1
 #define MQ_HD __device__ __forceinline__
-#define MQ_HHD __host__ __device__ __forceinline__
-#define MQ_NOINL __device__ __noinline__
+#define MQ_HHD __host__ __device__ inline
+#define MQ_NOINL __device__ __forceinline__
 #else
 #define MQ_DEV 0
 #define MQ_HD inline
@@ -82,21 +82,42 @@ struct Batch {              // device pointers
   int B;
 };
 
-struct Lay {  // shared-memory slot map; element (slot, k) is at sm[slot*NS + k]
-  int NS, R, MK;
-  int oX, oZ, oU, oRH, oSD, oCQ, oG3, oLO, oB, oW, oTD, oMA, oSI, oGG, oDSI, oESD, oDGI, oFS, oDAI, oCV, nslots;
-  MQ_HHD void init(int NS_, int R_) {
-    NS = NS_; R = R_; MK = NBR + R_;
-    int o = 0;
-    oX = o; o += NV; oZ = o; o += MK; oU = o; o += MK; oRH = o; o += MK; oSD = o; o += NV; oCQ = o; o += NV;
-    oG3 = o; o += 3 * R; oLO = o; o += R; oB = o; o += NV; oW = o; o += NV; oTD = o; o += 8; oMA = o; o += 3;
-    oSI = o; o += 36; oGG = o; o += 36; oDSI = o; o += 2; oESD = o; o += 2; oDGI = o; o += 2; oFS = o; o += 6;
-    oDAI = o; o += 3; oCV = o; o += 12;
-    nslots = o;
-  }
+// Where each per-stage array lives.  Element (slot j, stage k) of array A is A[j*NS + k].
+//   generic mode (runtime dims, any horizon): everything the iteration touches is in shared memory.
+//   fast mode (compile-time dims, horizon <= 32): the iterates x, z, u and the right-hand side live in
+//   REGISTERS during a burst of iterations and are parked in the per-warp global scratch between bursts,
+//   so shared memory only holds the read-only scaled data, the factor and the 6-vector exchange buffer.
+struct Mem {
+  double *X, *Z, *U, *B, *TD, *MA;                       // iterates, rhs, exchange (cold in fast mode)
+  double *RH, *SD, *CQ, *G3, *LO, *W;                    // read-only per iteration + work vector
+  double *SI, *GG, *DSI, *ESD, *DGI, *FS, *DAI, *CV, *PK; // factor (+ 72-double parking area)
+  double *E, *D, *DY, *DX;                               // always in global scratch
 };
-inline int smem_doubles(int NS, int R) { Lay L; L.init(NS, R); return L.nslots * NS; }
-inline int ws_doubles(int NS, int R) { return (2 * (NBR + R) + 2 * NV) * NS; }
+MQ_HHD int hot_slots(int R) { return (NBR + R) + NV + NV + 3 * R + R + NV + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12; }
+MQ_HHD int iter_slots(int R) { return NV + 2 * (NBR + R) + NV + 8 + 3; }
+MQ_HHD int smem_doubles(int NS, int R, bool fast) { return (hot_slots(R) + (fast ? 0 : iter_slots(R))) * NS + 72; }
+MQ_HHD int ws_doubles(int NS, int R, bool fast) { return (2 * (NBR + R) + 2 * NV + (fast ? iter_slots(R) : 0)) * NS; }
+MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, bool fast) {
+  const int MK = NBR + R;
+  double* p = sm;
+  m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
+  m.W = p; p += NV * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
+  m.DGI = p; p += 2 * NS; m.FS = p; p += 6 * NS; m.DAI = p; p += 3 * NS; m.CV = p; p += 12 * NS; m.PK = p; p += 72;
+  double* g = ws;
+  m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
+  double*& c = fast ? g : p;
+  m.X = c; c += NV * NS; m.Z = c; c += MK * NS; m.U = c; c += MK * NS; m.B = c; c += NV * NS; m.TD = c; c += 8 * NS; m.MA = c; c += 3 * NS;
+}
+
+// Dimensions: compile-time in fast mode, runtime otherwise.
+template <int NST, int RT> struct DimsT {
+  static constexpr int NS = NST, N = NST - 1, R = RT, MK = NBR + RT;
+  MQ_HHD DimsT(int, int) {}
+};
+template <> struct DimsT<0, 0> {
+  int NS, N, R, MK;
+  MQ_HHD DimsT(int ns, int r) : NS(ns), N(ns - 1), R(r), MK(NBR + r) {}
+};
 
 #if MQ_DEV
 #define MQ_FOR_STAGES(k) for (int k = lane; k < NS; k += 32)
@@ -126,39 +147,41 @@ MQ_HD void inv6(double* a) {
   }
 }
 
-struct Qp {
-  double* sm; Lay L; const Shape& sh; const Settings& st; int NS, N, R, MK, lane;
+template <int NST, int RT> struct Qp : DimsT<NST, RT> {
+  using Dm = DimsT<NST, RT>;
+  using Dm::NS; using Dm::N; using Dm::R; using Dm::MK;
+  static constexpr bool kFast = NST > 0;
+  Mem m; const Shape& sh; const Settings& st; int lane;
   const double* pd; const unsigned char* slack; const double* x0p;
-  double *wsE, *wsD, *wsDY, *wsDX;
   double c, cinv, rho, nq, nq_s;                 // cost scaling, current rho, |q|_inf norms (unscaled / scaled)
   double pri_res, dua_res, obj, nAx, nZ, nPx, nAty, pri_s, dua_s, nAx_s, nZ_s, nPx_s, nAty_s;
   int status, info_iter, rho_updates;
 
-#define X_(j, k) sm[(L.oX + (j)) * NS + (k)]
-#define Z_(i, k) sm[(L.oZ + (i)) * NS + (k)]
-#define U_(i, k) sm[(L.oU + (i)) * NS + (k)]
-#define RH_(i, k) sm[(L.oRH + (i)) * NS + (k)]
-#define SD_(j, k) sm[(L.oSD + (j)) * NS + (k)]
-#define CQ_(j, k) sm[(L.oCQ + (j)) * NS + (k)]
-#define G3_(i, k) sm[(L.oG3 + (i)) * NS + (k)]
-#define LO_(o, k) sm[(L.oLO + (o)) * NS + (k)]
-#define B_(j, k) sm[(L.oB + (j)) * NS + (k)]
-#define W_(j, k) sm[(L.oW + (j)) * NS + (k)]
-#define TD_(r, k) sm[(L.oTD + (r)) * NS + (k)]
-#define MA_(c, k) sm[(L.oMA + (c)) * NS + (k)]
-#define SI_(e, k) sm[(L.oSI + (e)) * NS + (k)]
-#define GG_(e, k) sm[(L.oGG + (e)) * NS + (k)]
-#define DSI_(t, k) sm[(L.oDSI + (t)) * NS + (k)]
-#define ESD_(t, k) sm[(L.oESD + (t)) * NS + (k)]
-#define DGI_(t, k) sm[(L.oDGI + (t)) * NS + (k)]
-#define FS_(e, k) sm[(L.oFS + (e)) * NS + (k)]
-#define DAI_(c, k) sm[(L.oDAI + (c)) * NS + (k)]
-#define CV_(e, k) sm[(L.oCV + (e)) * NS + (k)]
-#define PK_(chain, e) sm[(L.oB + (e)) * NS + (NS / 2) + (chain)]
-#define WSE_(i, k) wsE[(i) * NS + (k)]
-#define WSD_(j, k) wsD[(j) * NS + (k)]
-#define WSDY_(i, k) wsDY[(i) * NS + (k)]
-#define WSDX_(j, k) wsDX[(j) * NS + (k)]
+#define X_(j, k) m.X[(j) * NS + (k)]
+#define Z_(i, k) m.Z[(i) * NS + (k)]
+#define U_(i, k) m.U[(i) * NS + (k)]
+#define RH_(i, k) m.RH[(i) * NS + (k)]
+#define SD_(j, k) m.SD[(j) * NS + (k)]
+#define CQ_(j, k) m.CQ[(j) * NS + (k)]
+#define G3_(i, k) m.G3[(i) * NS + (k)]
+#define LO_(o, k) m.LO[(o) * NS + (k)]
+#define B_(j, k) m.B[(j) * NS + (k)]
+#define W_(j, k) m.W[(j) * NS + (k)]
+#define TD_(r, k) m.TD[(r) * NS + (k)]
+#define MA_(c, k) m.MA[(c) * NS + (k)]
+#define SI_(e, k) m.SI[(e) * NS + (k)]
+#define GG_(e, k) m.GG[(e) * NS + (k)]
+#define DSI_(t, k) m.DSI[(t) * NS + (k)]
+#define ESD_(t, k) m.ESD[(t) * NS + (k)]
+#define DGI_(t, k) m.DGI[(t) * NS + (k)]
+#define FS_(e, k) m.FS[(e) * NS + (k)]
+#define DAI_(c, k) m.DAI[(c) * NS + (k)]
+#define CV_(e, k) m.CV[(e) * NS + (k)]
+#define PK_(chain, e) m.PK[(chain) * 36 + (e)]
+#define WSE_(i, k) m.E[(i) * NS + (k)]
+#define WSD_(j, k) m.D[(j) * NS + (k)]
+#define WSDY_(i, k) m.DY[(i) * NS + (k)]
+#define WSDX_(j, k) m.DX[(j) * NS + (k)]
 #define SLK_(o, k) ((int)slack[(k) * R + (o)])
 
   MQ_HD int nrows(int k) const { return k < N ? MK : 16; }
@@ -899,49 +922,298 @@ struct Qp {
     return false;
   }
   // auxil.h:21-38 compute_rho_estimate / adapt_rho, osqp.h osqp_update_rho
-  MQ_NOINL void adapt_rho() {
+  MQ_NOINL bool adapt_rho() {
     double pn = pri_s / (fmax(nZ_s, nAx_s) + 1e-10);
     double dn = dua_s / (fmax(nq_s, fmax(nAty_s, nPx_s)) + 1e-10);
     double rn = rho * sqrt(pn / (dn + 1e-10));
     rn = fmin(fmax(rn, kRhoMin), kRhoMax);
-    if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
-      rho = rn;
-      MQ_FOR_STAGES(k) {
-        const int nr = nrows(k);
-        for (int i = 0; i < nr; ++i) {
-          double lo, hi; row_bounds(k, i, lo, hi);
-          double e = WSE_(i, k);
-          int t = row_type(e, lo, hi);
-          if (t >= 0) {
-            double rold = RH_(i, k), rnew = rho_of_type(t) * e * e;
-            U_(i, k) = U_(i, k) * rold / rnew;   // y is kept across a rho update; u = y / Rh
-            RH_(i, k) = rnew;
-          }
+    if (!(rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance)) return false;
+    rho = rn;
+    MQ_FOR_STAGES(k) {
+      const int nr = nrows(k);
+      for (int i = 0; i < nr; ++i) {
+        double lo, hi; row_bounds(k, i, lo, hi);
+        double e = WSE_(i, k);
+        int t = row_type(e, lo, hi);
+        if (t >= 0) {
+          double rold = RH_(i, k), rnew = rho_of_type(t) * e * e;
+          U_(i, k) = U_(i, k) * rold / rnew;   // y is kept across a rho update; u = y / Rh
+          RH_(i, k) = rnew;
         }
       }
-      MQ_SYNC();
-      factor();
-      rows_phase<1>();
-      rhs_finish();
-      rho_updates += 1;
     }
+    MQ_SYNC();
+    rho_updates += 1;
+    return true;                                 // caller refactorises and rebuilds the rhs
   }
 
-  // ---- osqp_solve (osqp.h:78) ---------------------------------------------------------------------
-  MQ_NOINL void solve() {
-    status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
-    rows_phase<1>();
-    rhs_finish();
-    int iter; bool can_check = false;
-    for (iter = 1; iter <= st.max_iter; ++iter) {
-      can_check = st.check_termination && (iter % st.check_termination == 0);
-      const bool can_adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
-      if (can_check || iter == st.max_iter) iterate<2>(); else iterate<0>();
-      if (can_check) { update_info(iter); if (check_termination(false)) break; }
-      if (can_adapt) { if (!can_check) update_info(iter); adapt_rho(); }
+  // ---- bursts of iterations ------------------------------------------------------------------------
+  // A burst is a run of ADMM iterations with no termination check in between; its last iteration records
+  // delta_x / delta_y for the infeasibility tests.
+  MQ_HD void burst(int niter) {
+#if MQ_DEV
+    if constexpr (kFast) { burst_fast(niter); return; }
+#endif
+    for (int it = 0; it < niter; ++it) { if (it == niter - 1) iterate<2>(); else iterate<0>(); }
+  }
+
+#if MQ_DEV
+  // Fast path: stage k = lane; x, z, u and the rhs stay in registers for the whole burst, neighbour-stage
+  // values travel by warp shuffle, shared memory is only read (scaled data, factor) except for the
+  // 6-vector exchange with the 12 chain lanes.
+  MQ_HD void burst_fast(int niter) {
+    static_assert(!kFast || NST <= 32, "fast path needs horizon <= 32");
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int mid = NS / 2, s_top = mid, s_bot = N - mid, nst = s_top > s_bot ? s_top : s_bot;
+    const int k = lane < NS ? lane : NS - 1;          // ghost lanes shadow the last stage, never write
+    const bool live = lane < NS, hasu = lane < N, notfirst = lane > 0 && live;
+    const int kp = k < N ? k + 1 : k, km = k > 0 ? k - 1 : 0;
+    const double al = st.alpha, om = 1.0 - st.alpha, apv = sh.a_pv, bpa = sh.b_pa, bva = sh.b_va;
+    double x[NV], b[NV], z[MK], u[MK], bnd[8];
+    int sl[R > 0 ? R : 1];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { x[j] = X_(j, k); b[j] = B_(j, k); }
+#pragma unroll
+    for (int i = 0; i < MK; ++i) { z[i] = Z_(i, k); u[i] = U_(i, k); }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) bnd[r] = (k == 0) ? -x0p[r] : 0.0;
+#pragma unroll
+    for (int o = 0; o < R; ++o) sl[o] = hasu ? SLK_(o, k) : 0;
+    // chain-lane geometry
+    const int half = lane / 6, ci = lane - 6 * half;
+    const bool chl = lane < 12;
+    const int cbase = chl ? 6 * half : 0;
+    const int dk = chl ? (half == 0 ? 1 : -1) : 0;
+    const int k0 = chl ? (half == 0 ? 0 : N) : 0;
+    const int mysteps = chl ? (half == 0 ? s_top : s_bot) : 0;
+    const int cr = chl ? ci : 0;
+
+    for (int it = 0; it < niter; ++it) {
+      if (it == niter - 1 && live) {                 // park the old x, u: deltas are formed after the update
+#pragma unroll
+        for (int j = 0; j < NV; ++j) WSDX_(j, k) = x[j];
+#pragma unroll
+        for (int i = 0; i < MK; ++i) WSDY_(i, k) = u[i];
+      }
+      // ---- forward elimination of the leaves -> reduced rhs r[0..5]
+      double r[6], r11[2], ma[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) r[i] = b[i];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        double bn = __shfl_down_sync(FULL, b[6 + t], 1);
+        double v = b[11 + t] - ESD_(t, kp) * bn;
+        r11[t] = hasu ? v : 0.0;
+        double f = DGI_(t, k) * r11[t];
+        r[0] -= FS_(3 * t, k) * f; r[1] -= FS_(3 * t + 1, k) * f; r[2] -= FS_(3 * t + 2, k) * f;
+      }
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        ma[cc] = DAI_(cc, k) * b[8 + cc];
+        r[cc] -= CV_(4 * cc, k) * ma[cc]; r[3 + cc] -= CV_(4 * cc + 1, k) * ma[cc];
+        double mm = __shfl_up_sync(FULL, ma[cc], 1);
+        mm = notfirst ? mm : 0.0;
+        r[cc] -= CV_(4 * cc + 2, km) * mm; r[3 + cc] -= CV_(4 * cc + 3, km) * mm;
+      }
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) W_(i, k) = r[i];
+      }
+      __syncwarp();
+      // ---- twisted chain, forward: L w = r
+      {
+        const double* pg = m.GG + (cr * 6) * NS + k0;
+        double* pw = m.W + cr * NS + k0;
+        double wi = pw[0], cm = 0.0;
+#pragma unroll
+        for (int s = 0; s < nst; ++s) {
+          const bool act = s < mysteps, last = s == mysteps - 1;
+          double g0 = pg[0], g1 = pg[NS], g2 = pg[2 * NS], g3 = pg[3 * NS], g4 = pg[4 * NS], g5 = pg[5 * NS];
+          double rn = pw[dk];
+          double a0 = g0 * __shfl_sync(FULL, wi, cbase);
+          double a1 = g1 * __shfl_sync(FULL, wi, cbase + 1);
+          a0 = fma(g2, __shfl_sync(FULL, wi, cbase + 2), a0);
+          a1 = fma(g3, __shfl_sync(FULL, wi, cbase + 3), a1);
+          a0 = fma(g4, __shfl_sync(FULL, wi, cbase + 4), a0);
+          a1 = fma(g5, __shfl_sync(FULL, wi, cbase + 5), a1);
+          double acc = a0 + a1;
+          if (act) {
+            if (!last) { wi = rn - acc; pw[dk] = wi; }
+            else cm = acc;
+          }
+          pg += dk; pw += dk;
+        }
+        double cb = __shfl_sync(FULL, cm, 6 + (lane % 6));
+        if (lane < 6) { double* pm = m.W + lane * NS + mid; *pm = *pm - cm - (s_bot > 0 ? cb : 0.0); }
+      }
+      __syncwarp();
+      // ---- v = S^-1 w per stage
+      {
+        double w[6], v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w[j] = W_(j, k);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double s0 = SI_(a * 6, k) * w[0], s1 = SI_(a * 6 + 1, k) * w[1];
+          s0 = fma(SI_(a * 6 + 2, k), w[2], s0); s1 = fma(SI_(a * 6 + 3, k), w[3], s1);
+          s0 = fma(SI_(a * 6 + 4, k), w[4], s0); s1 = fma(SI_(a * 6 + 5, k), w[5], s1);
+          v[a] = s0 + s1;
+        }
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) W_(j, k) = v[j];
+        }
+      }
+      __syncwarp();
+      // ---- twisted chain, backward: L' y = v
+      {
+        const int kb = chl ? (half == 0 ? mid - 1 : mid + 1) : 0;
+        const int db = chl ? (half == 0 ? -1 : 1) : 0;
+        const double* pg = m.GG + cr * NS + (mysteps > 0 ? kb : 0);     // column cr of G: element (j, cr) at pg[j*6*NS]
+        double* pw = m.W + cr * NS + (mysteps > 0 ? kb : 0);
+        double yi = m.W[(lane % 6) * NS + mid];
+#pragma unroll
+        for (int s = 0; s < nst; ++s) {
+          const bool act = s < mysteps;
+          double g0 = pg[0], g1 = pg[6 * NS], g2 = pg[12 * NS], g3 = pg[18 * NS], g4 = pg[24 * NS], g5 = pg[30 * NS];
+          double vk = pw[0];
+          double a0 = fma(-g0, __shfl_sync(FULL, yi, cbase), vk);
+          double a1 = -g1 * __shfl_sync(FULL, yi, cbase + 1);
+          a0 = fma(-g2, __shfl_sync(FULL, yi, cbase + 2), a0);
+          a1 = fma(-g3, __shfl_sync(FULL, yi, cbase + 3), a1);
+          a0 = fma(-g4, __shfl_sync(FULL, yi, cbase + 4), a0);
+          a1 = fma(-g5, __shfl_sync(FULL, yi, cbase + 5), a1);
+          if (act) { yi = a0 + a1; pw[0] = yi; }
+          if (s + 1 < mysteps) { pg += db; pw += db; }
+        }
+      }
+      __syncwarp();
+      // ---- back-substitution of the leaves -> x~ (xt)
+      double xt[NV];
+      {
+        double yn[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { xt[i] = W_(i, k); yn[i] = __shfl_down_sync(FULL, xt[i], 1); }
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          xt[8 + cc] = DAI_(cc, k) * (b[8 + cc] - CV_(4 * cc, k) * xt[cc] - CV_(4 * cc + 1, k) * xt[3 + cc] -
+                                      CV_(4 * cc + 2, k) * yn[cc] - CV_(4 * cc + 3, k) * yn[3 + cc]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          xt[11 + t] = DGI_(t, k) * (r11[t] - FS_(3 * t, k) * xt[0] - FS_(3 * t + 1, k) * xt[1] - FS_(3 * t + 2, k) * xt[2]);
+          double xp = __shfl_up_sync(FULL, xt[11 + t], 1);
+          xt[6 + t] = DSI_(t, k) * b[6 + t] - (notfirst ? ESD_(t, k) * xp : 0.0);
+        }
+        if (!hasu) {
+#pragma unroll
+          for (int j = 8; j < NV; ++j) xt[j] = 0.0;
+        }
+      }
+      // ---- z, u, x updates and the next right-hand side
+      double racc[NV], td[8];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) racc[j] = 0.0;
+      {
+        double xm[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { double v = __shfl_up_sync(FULL, xt[j], 1); xm[j] = notfirst ? v : 0.0; }
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          double zt = -xt[rr];
+          if (rr < 3) zt += xm[rr] + apv * xm[3 + rr] + bpa * xm[8 + rr];
+          else if (rr < 6) zt += xm[rr] + bva * xm[5 + rr];
+          else zt += xm[5 + rr];
+          double v = al * zt + om * z[rr] + u[rr];
+          double zn = fmin(fmax(v, bnd[rr]), bnd[rr]);
+          z[rr] = zn; u[rr] = v - zn;
+          double t = RH_(rr, k) * (zn - u[rr]);
+          td[rr] = t; racc[rr] -= t;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        double v = al * xt[j] + om * z[8 + j] + u[8 + j];
+        double zn = fmin(fmax(v, sh.blo[j]), sh.bhi[j]);
+        if (j >= 8 && !hasu) { zn = 0.0; v = 0.0; }
+        z[8 + j] = zn; u[8 + j] = v - zn;
+        racc[j] += RH_(8 + j, k) * (zn - u[8 + j]);
+      }
+#pragma unroll
+      for (int o = 0; o < R; ++o) {
+        const int i = NBR + o;
+        double g0 = G3_(3 * o, k), g1 = G3_(3 * o + 1, k), g2 = G3_(3 * o + 2, k);
+        double zt = g0 * xt[0] + g1 * xt[1] + g2 * xt[2] - (sl[o] ? xt[12] : xt[11]);
+        double v = al * zt + om * z[i] + u[i];
+        double zn = fmax(v, LO_(o, k));
+        if (!hasu) { zn = 0.0; v = 0.0; }
+        z[i] = zn; u[i] = v - zn;
+        double t = RH_(i, k) * (zn - u[i]);
+        racc[0] += g0 * t; racc[1] += g1 * t; racc[2] += g2 * t;
+        if (sl[o]) racc[12] -= t; else racc[11] -= t;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        x[j] = al * xt[j] + om * x[j];
+        b[j] = (j < 8 || hasu) ? racc[j] + SD_(j, k) * x[j] - CQ_(j, k) : 0.0;
+      }
+      // dynamics rows of stage k+1 feed stage k's rhs
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        double tp = __shfl_down_sync(FULL, td[cc], 1), tv = __shfl_down_sync(FULL, td[3 + cc], 1);
+        if (hasu) { b[cc] += tp; b[3 + cc] += apv * tp + tv; b[8 + cc] += bpa * tp + bva * tv; }
+      }
+      {
+        double t6 = __shfl_down_sync(FULL, td[6], 1), t7 = __shfl_down_sync(FULL, td[7], 1);
+        if (hasu) { b[11] += t6; b[12] += t7; }
+      }
     }
-    if (!can_check) { update_info(iter - 1); check_termination(false); }
-    if (status == kUnsolved) { if (!check_termination(true)) status = kMaxIter; }
+    // park the state; form the deltas of the last iteration
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { X_(j, k) = x[j]; B_(j, k) = b[j]; WSDX_(j, k) = x[j] - WSDX_(j, k); }
+#pragma unroll
+      for (int i = 0; i < MK; ++i) { Z_(i, k) = z[i]; U_(i, k) = u[i]; WSDY_(i, k) = RH_(i, k) * (u[i] - WSDY_(i, k)); }
+    }
+    __syncwarp();
+  }
+#endif
+
+  // ---- osqp_solve (osqp.h:78) ---------------------------------------------------------------------
+  // Written as one loop with a single call site per phase (factor, burst, update_info, check_termination,
+  // adapt_rho) so that everything inlines into the kernel once: shared-memory addresses then fold to
+  // immediates and the settings / shape fields to constant-bank operands.
+  MQ_HD void solve() {
+    status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
+    int iter = 0;
+    bool refactor = true, last_checked = false, approx = false;
+    for (;;) {
+      bool do_info, do_check, do_adapt = false;
+      const bool final_pass = iter >= st.max_iter;
+      if (!final_pass) {
+        if (refactor) { factor(); rows_phase<1>(); rhs_finish(); refactor = false; }
+        int nb = st.max_iter;
+        if (st.check_termination) { int c2 = (iter / st.check_termination + 1) * st.check_termination; if (c2 < nb) nb = c2; }
+        if (st.adaptive_rho && st.adaptive_rho_interval) { int c2 = (iter / st.adaptive_rho_interval + 1) * st.adaptive_rho_interval; if (c2 < nb) nb = c2; }
+        burst(nb - iter);
+        iter = nb;
+        do_check = st.check_termination && (iter % st.check_termination == 0);
+        do_adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+        do_info = do_check || do_adapt;
+        last_checked = do_check;
+      } else if (!approx) {          // loop ran out: one exact check if the last iteration was not checked
+        do_info = !last_checked; do_check = !last_checked;
+      } else {                       // approximate (10x) check decides between *_inaccurate and max_iter
+        do_info = false; do_check = true;
+      }
+      if (do_info) update_info(iter);
+      if (do_check && check_termination(approx)) break;
+      if (final_pass) {
+        if (approx) { status = kMaxIter; break; }
+        approx = true;
+        continue;
+      }
+      if (do_adapt && adapt_rho()) refactor = true;
+    }
   }
 
   // auxil.h:118 store_solution (+ scaling.h unscale_solution): x = D x_s = xh, y = E y_s / c = Rh u / c
@@ -966,16 +1238,15 @@ struct Qp {
     }
   }
 
-  MQ_HD Qp(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_) : sh(shape), st(set) {
-    sm = smem; NS = shape.NS; N = NS - 1; R = shape.R; MK = NBR + R; lane = lane_;
-    L.init(NS, R);
+  MQ_HD Qp(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_)
+      : Dm(shape.NS, shape.R), sh(shape), st(set) {
+    lane = lane_;
+    map_memory(m, smem, ws, NS, R, kFast);
     pd = bt.pd; slack = bt.slack;
-    wsE = ws; wsD = wsE + MK * NS; wsDY = wsD + NV * NS; wsDX = wsDY + MK * NS;
   }
   MQ_HD void run(const Batch& bt, int b) {
     x0p = bt.x0 + (size_t)b * 8;
     load_and_scale(bt, b);
-    factor();
     solve();
     store(bt, b);
     MQ_SYNC();

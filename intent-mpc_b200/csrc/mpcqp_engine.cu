@@ -66,11 +66,12 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
 // ------------------------------------------------------------------------------------------------
 // solve kernel: persistent, one warp (= one CTA) per QP at a time, work fetched from a global counter
 // ------------------------------------------------------------------------------------------------
+template <int NST, int RT>
 __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
                                                          const __grid_constant__ Batch bt, int ws_stride, int* counter) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x;
-  Qp qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  Qp<NST, RT> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(counter, 1);
@@ -78,6 +79,25 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
     if (b >= bt.B) break;
     qp.run(bt, b);
   }
+}
+
+typedef void (*SolveKernel)(const Shape, const Settings, const Batch, int, int*);
+// Fast-path instantiations (compile-time dims, register-resident iterates); anything else runs the generic kernel.
+#ifndef MPCQP_FAST_R_LIST
+#define MPCQP_FAST_R_LIST X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#endif
+static SolveKernel pick_kernel(int NS, int R, bool* fast) {
+  *fast = true;
+  if (NS == 30) {
+    switch (R) {
+#define X(r) case r: return mpcqp_solve_kernel<30, r>;
+      MPCQP_FAST_R_LIST
+#undef X
+      default: break;
+    }
+  }
+  *fast = false;
+  return mpcqp_solve_kernel<0, 0>;
 }
 
 }  // namespace mpcqp
@@ -107,7 +127,7 @@ struct mpcqp_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
-  double last_ms = 0.0; long long last_launches = 0;
+  double last_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter;
   // staging for the *_host entry point
@@ -169,6 +189,8 @@ extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
 extern "C" const char* mpcqp_engine_last_error(const mpcqp_engine* e) { return e ? e->err.c_str() : "null engine"; }
 extern "C" double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e) { return e ? e->last_ms : 0.0; }
 extern "C" int64_t mpcqp_engine_last_launches(const mpcqp_engine* e) { return e ? e->last_launches : 0; }
+extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->last_fast : -1; }
+extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
 extern "C" void* mpcqp_engine_stream(const mpcqp_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 static int check_settings(mpcqp_engine* e, const mpcqp_settings* s, Settings* o) {
@@ -223,25 +245,29 @@ static int shape_from_params(mpcqp_engine* e, const mpcqp_mpc_params* p, int R, 
 
 // Launch the solve kernel on structured data already on the device.
 static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Batch bt) {
-  const size_t smem = (size_t)smem_doubles(sh.NS, sh.R) * sizeof(double);
+  bool fast = false;
+  SolveKernel kern = pick_kernel(sh.NS, sh.R, &fast);
+  if (e->force_generic) { fast = false; kern = mpcqp_solve_kernel<0, 0>; }
+  const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, fast) * sizeof(double);
   if ((long long)smem > (long long)e->max_smem_optin) {
     e->err = "problem does not fit shared memory: horizon/num_obs too large (" + std::to_string(smem) + " B needed)";
     return MPCQP_ERR_ARG;
   }
-  CK(cudaFuncSetAttribute(mpcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpcqp_solve_kernel, 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
   if (occ < 1) { e->err = "solve kernel cannot be resident"; return MPCQP_ERR_CUDA; }
   long long grid = (long long)e->num_sms * occ;
   if (grid > bt.B) grid = bt.B;
-  const int wsd = ws_doubles(sh.NS, sh.R);
+  const int wsd = ws_doubles(sh.NS, sh.R, fast);
   CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
   CK(e->counter.need(sizeof(int)));
   bt.ws = e->ws.as<double>();
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
-  mpcqp_solve_kernel<<<(unsigned)grid, 32, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+  kern<<<(unsigned)grid, 32, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
   CK(cudaGetLastError());
   e->last_launches += 1;
+  e->last_fast = fast ? 1 : 0;
   return MPCQP_OK;
 }
 

@@ -130,6 +130,19 @@ class Engine:
         return int(self.lib.mpcqp_engine_last_launches(self.h))
 
     @property
+    def last_path(self) -> str:
+        """'fast' (register-resident kernel, compile-time dims) or 'generic' (shared-memory kernel)."""
+        return "fast" if int(self.lib.mpcqp_engine_last_path(self.h)) == 1 else "generic"
+
+    def force_generic(self, on: bool = True):
+        self._check(self.lib.mpcqp_engine_force_generic(self.h, C.c_int(1 if on else 0)))
+
+    def fp64_fma_peak_tflops(self) -> float:
+        tf = C.c_double()
+        self._check(self.lib.mpcqp_fp64_fma_peak(self.h, C.byref(tf)))
+        return float(tf.value)
+
+    @property
     def stream(self) -> int:
         return int(self.lib.mpcqp_engine_stream(self.h) or 0)
 

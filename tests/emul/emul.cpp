@@ -26,8 +26,8 @@ extern "C" int emul_solve_batch(int NS, int R, int B, double a_pv, double b_pa, 
   bt.pd = pd; bt.slack = slack; bt.q = q; bt.x0 = x0; bt.g = g; bt.low = low; bt.warm_x = warm_x;
   bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates; bt.obj = obj;
   bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B;
-  std::vector<double> sm((size_t)smem_doubles(NS, R)), ws((size_t)ws_doubles(NS, R));
-  Qp qp(sm.data(), sh, st, bt, ws.data(), 0);
+  std::vector<double> sm((size_t)smem_doubles(NS, R, false)), ws((size_t)ws_doubles(NS, R, false));
+  Qp<0, 0> qp(sm.data(), sh, st, bt, ws.data(), 0);
   for (int b = 0; b < B; ++b) qp.run(bt, b);
   return 0;
 }

@@ -34,6 +34,30 @@ def test_gpu_matches_reference_golden(eng, name):
     assert np.abs((out["obj"] - g[name + "_obj"]) / g[name + "_obj"]).max() < TOL
 
 
+@pytest.mark.parametrize("name", ["snapshot", "static4", "static0", "static8"])
+def test_generic_kernel_matches_reference_golden(eng, name):
+    """The shared-memory kernel (used for horizons/obstacle counts without a compiled fast path) on the same
+    golden cases; the default dispatch above runs them on the register-resident fast path."""
+    g = np.load(GOLD)
+    eng.force_generic(True)
+    try:
+        out = eng.solve_mpc_batch(cases()[name])
+        assert eng.last_path == "generic"
+    finally:
+        eng.force_generic(False)
+    assert (out["status"] == g[name + "_status"]).all()
+    assert (out["iter"] == g[name + "_iter"]).all()
+    assert (out["rho_updates"] == g[name + "_rho_updates"]).all()
+    assert rel_inf(out["x"], g[name + "_x"]).max() < TOL
+
+
+def test_dispatch_uses_fast_path_for_default_shape(eng):
+    eng.solve_mpc_batch(W.static_batch(4, num_obs=4))
+    assert eng.last_path == "fast"
+    eng.solve_mpc_batch(W.static_batch(4, num_obs=2, params=W.MpcParams(horizon=60)))
+    assert eng.last_path == "generic"
+
+
 def _oracle():
     return OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
 
