@@ -93,15 +93,15 @@ struct Mem {
   double *SI, *GG, *DSI, *ESD, *DGI, *FS, *DAI, *CV, *PK; // factor (+ 72-double parking area)
   double *E, *D, *DY, *DX;                               // always in global scratch
 };
-MQ_HHD int hot_slots(int R) { return (NBR + R) + NV + NV + 3 * R + R + NV + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12; }
+MQ_HHD int hot_slots(int R, bool fast) { return (NBR + R) + NV + NV + 3 * R + R + (fast ? 6 : NV) + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12; }
 MQ_HHD int iter_slots(int R) { return NV + 2 * (NBR + R) + NV + 8 + 3; }
-MQ_HHD int smem_doubles(int NS, int R, bool fast) { return (hot_slots(R) + (fast ? 0 : iter_slots(R))) * NS + 72; }
+MQ_HHD int smem_doubles(int NS, int R, bool fast) { return (hot_slots(R, fast) + (fast ? 0 : iter_slots(R))) * NS + 72; }
 MQ_HHD int ws_doubles(int NS, int R, bool fast) { return (2 * (NBR + R) + 2 * NV + (fast ? iter_slots(R) : 0)) * NS; }
 MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, bool fast) {
   const int MK = NBR + R;
   double* p = sm;
   m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
-  m.W = p; p += NV * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
+  m.W = p; p += (fast ? 6 : NV) * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
   m.DGI = p; p += 2 * NS; m.FS = p; p += 6 * NS; m.DAI = p; p += 3 * NS; m.CV = p; p += 12 * NS; m.PK = p; p += 72;
   double* g = ws;
   m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
@@ -151,6 +151,11 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
   using Dm = DimsT<NST, RT>;
   using Dm::NS; using Dm::N; using Dm::R; using Dm::MK;
   static constexpr bool kFast = NST > 0;
+  static constexpr int kWS = 6;    // fast mode: W holds one 6-vector per stage, stage-major (16-byte aligned rows)
+  // Fast mode stores the per-stage chain data (G, W) in CHAIN order so that both chains of the twisted
+  // recursion walk upward in memory: stages 0..mid-1 -> slots 0..mid-1, mid -> slot mid, stages N..mid+1 ->
+  // slots mid+1..N.
+  MQ_HD int cslot(int k) const { return k <= NS / 2 ? k : (NS / 2 + 1) + (N - k); }
   Mem m; const Shape& sh; const Settings& st; int lane;
   const double* pd; const unsigned char* slack; const double* x0p;
   double c, cinv, rho, nq, nq_s;                 // cost scaling, current rho, |q|_inf norms (unscaled / scaled)
@@ -166,11 +171,11 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
 #define G3_(i, k) m.G3[(i) * NS + (k)]
 #define LO_(o, k) m.LO[(o) * NS + (k)]
 #define B_(j, k) m.B[(j) * NS + (k)]
-#define W_(j, k) m.W[(j) * NS + (k)]
+#define W_(j, k) m.W[kFast ? cslot(k) * kWS + (j) : (j) * NS + (k)]
 #define TD_(r, k) m.TD[(r) * NS + (k)]
 #define MA_(c, k) m.MA[(c) * NS + (k)]
 #define SI_(e, k) m.SI[(e) * NS + (k)]
-#define GG_(e, k) m.GG[(e) * NS + (k)]
+#define GG_(e, k) m.GG[kFast ? cslot(k) * 36 + (e) : (e) * NS + (k)]
 #define DSI_(t, k) m.DSI[(t) * NS + (k)]
 #define ESD_(t, k) m.ESD[(t) * NS + (k)]
 #define DGI_(t, k) m.DGI[(t) * NS + (k)]
@@ -263,7 +268,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
         bool ex = j < nvars(k);
         CQ_(j, k) = ex ? (j < 8 ? q[8 * k + j] : q[8 * NS + 5 * k + (j - 8)]) : 0.0;
         SD_(j, k) = 1.0;  // D during Ruiz
-        B_(j, k) = 0.0; W_(j, k) = 0.0; X_(j, k) = 0.0;
+        B_(j, k) = 0.0; X_(j, k) = 0.0;
       }
       for (int i = 0; i < MK; ++i) { RH_(i, k) = 1.0; Z_(i, k) = 0.0; U_(i, k) = 0.0; }  // RH holds E during Ruiz
       for (int o = 0; o < R; ++o) {
@@ -280,7 +285,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
     MQ_SYNC();
     const double apv = fabs(sh.a_pv), bpa = fabs(sh.b_pa), bva = fabs(sh.b_va);
     for (int pass = 0; pass < st.scaling; ++pass) {
-      // column norms of [P A'; A 0] -> W (Dt), row norms of A -> Z (Et); D lives in SD, E in RH
+      // column norms of [P A'; A 0] -> B (Dt), row norms of A -> Z (Et); D lives in SD, E in RH
       MQ_FOR_STAGES(k) {
         const int nv = nvars(k), nr = nrows(k);
         for (int j = 0; j < nv; ++j) {
@@ -295,7 +300,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
             else { an = fmax(an, RH_(j - 5, k + 1)); for (int o = 0; o < R; ++o) if (SLK_(o, k) == j - 11) an = fmax(an, RH_(NBR + o, k)); }
           }
           double pn = fabs(c * pd[k * NV + j]) * dj * dj;
-          W_(j, k) = 1.0 / sqrt(limit_scaling(fmax(pn, an * dj)));
+          B_(j, k) = 1.0 / sqrt(limit_scaling(fmax(pn, an * dj)));
         }
         for (int i = 0; i < nr; ++i) {
           double rn;
@@ -320,7 +325,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
       MQ_FOR_STAGES(k) {
         const int nv = nvars(k), nr = nrows(k);
         for (int j = 0; j < nv; ++j) {
-          double dj = SD_(j, k) * W_(j, k);
+          double dj = SD_(j, k) * B_(j, k);
           SD_(j, k) = dj;
           psum += fabs(c * pd[k * NV + j]) * dj * dj;
           qmax = fmax(qmax, fabs(c * CQ_(j, k) * dj));
@@ -348,7 +353,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
         nq1 = fmax(nq1, fabs(dj * cq));
         CQ_(j, k) = cq;
         SD_(j, k) = st.sigma / (dj * dj);
-        W_(j, k) = 0.0; WSDX_(j, k) = 0.0;
+        B_(j, k) = 0.0; WSDX_(j, k) = 0.0;
       }
       const int nr = nrows(k);
       for (int i = 0; i < MK; ++i) {
@@ -964,7 +969,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
   MQ_HD void burst_fast(int niter) {
     static_assert(!kFast || NST <= 32, "fast path needs horizon <= 32");
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int mid = NS / 2, s_top = mid, s_bot = N - mid, nst = s_top > s_bot ? s_top : s_bot;
+    constexpr int mid = NS / 2, s_top = mid, s_bot = N - mid;
     const int k = lane < NS ? lane : NS - 1;          // ghost lanes shadow the last stage, never write
     const bool live = lane < NS, hasu = lane < N, notfirst = lane > 0 && live;
     const int kp = k < N ? k + 1 : k, km = k > 0 ? k - 1 : 0;
@@ -979,14 +984,19 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
     for (int r = 0; r < 8; ++r) bnd[r] = (k == 0) ? -x0p[r] : 0.0;
 #pragma unroll
     for (int o = 0; o < R; ++o) sl[o] = hasu ? SLK_(o, k) : 0;
-    // chain-lane geometry
-    const int half = lane / 6, ci = lane - 6 * half;
-    const bool chl = lane < 12;
-    const int cbase = chl ? 6 * half : 0;
-    const int dk = chl ? (half == 0 ? 1 : -1) : 0;
-    const int k0 = chl ? (half == 0 ? 0 : N) : 0;
-    const int mysteps = chl ? (half == 0 ? s_top : s_bot) : 0;
-    const int cr = chl ? ci : 0;
+    // chain-lane geometry.  Lanes 0-5: upper chain (stages 0..mid-1), lanes 6-11: lower chain (stages N..mid+1);
+    // lanes 12-31 shadow lanes 0-11 with their writes disabled so the whole warp runs one instruction stream.
+    static_assert(NS % 2 == 0, "fast path assumes an even number of stages (16-byte aligned rows)");
+    constexpr int nst = s_top > s_bot ? s_top : s_bot;
+    const int cl = lane % 12, chalf = cl / 6, ci = cl - 6 * chalf;
+    const bool cwr = lane < 12;
+    const int mysteps = chalf == 0 ? s_top : s_bot;
+    const int slot0 = chalf == 0 ? 0 : mid + 1;             // first source slot of the forward walk
+    const int slotT = chalf == 0 ? mid - 1 : N;             // first target slot of the backward walk
+    const double* pGr = m.GG + slot0 * 36 + ci * 6;         // row ci of G at the forward source slot
+    double* pWc = m.W + slot0 * kWS;
+    const double* pGt = m.GG + slotT * 36 + ci;             // column ci of G at the backward target slot
+    double* pWt = m.W + slotT * kWS;
 
     for (int it = 0; it < niter; ++it) {
       if (it == niter - 1 && live) {                 // park the old x, u: deltas are formed after the update
@@ -1020,31 +1030,30 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
         for (int i = 0; i < 6; ++i) W_(i, k) = r[i];
       }
       __syncwarp();
-      // ---- twisted chain, forward: L w = r
+      // ---- twisted chain, forward: L w = r.  6 lanes per chain (lane = row of the 6x6 block); lanes 0-5 walk up
+      // from stage 0, lanes 6-11 walk down from stage N, both upward in chain-slot order.  The running vector is
+      // exchanged through the W row that has to be written anyway (1 STS + 3 broadcast LDS.128 per step).
       {
-        const double* pg = m.GG + (cr * 6) * NS + k0;
-        double* pw = m.W + cr * NS + k0;
-        double wi = pw[0], cm = 0.0;
+        double cm = 0.0;
 #pragma unroll
         for (int s = 0; s < nst; ++s) {
-          const bool act = s < mysteps, last = s == mysteps - 1;
-          double g0 = pg[0], g1 = pg[NS], g2 = pg[2 * NS], g3 = pg[3 * NS], g4 = pg[4 * NS], g5 = pg[5 * NS];
-          double rn = pw[dk];
-          double a0 = g0 * __shfl_sync(FULL, wi, cbase);
-          double a1 = g1 * __shfl_sync(FULL, wi, cbase + 1);
-          a0 = fma(g2, __shfl_sync(FULL, wi, cbase + 2), a0);
-          a1 = fma(g3, __shfl_sync(FULL, wi, cbase + 3), a1);
-          a0 = fma(g4, __shfl_sync(FULL, wi, cbase + 4), a0);
-          a1 = fma(g5, __shfl_sync(FULL, wi, cbase + 5), a1);
-          double acc = a0 + a1;
-          if (act) {
-            if (!last) { wi = rn - acc; pw[dk] = wi; }
-            else cm = acc;
-          }
-          pg += dk; pw += dk;
+          const bool act = s < mysteps, lastst = s == mysteps - 1;
+          const double2 ga = *reinterpret_cast<const double2*>(pGr + s * 36), gb = *reinterpret_cast<const double2*>(pGr + s * 36 + 2),
+                        gc = *reinterpret_cast<const double2*>(pGr + s * 36 + 4);
+          double rn = pWc[(s + 1) * kWS + ci];
+          if (lastst && chalf == 1) rn = 0.0;
+          const double2 wa = *reinterpret_cast<const double2*>(pWc + s * kWS), wb = *reinterpret_cast<const double2*>(pWc + s * kWS + 2),
+                        wc = *reinterpret_cast<const double2*>(pWc + s * kWS + 4);
+          double a0 = -ga.x * wa.x, a1 = fma(-ga.y, wa.y, rn);
+          a0 = fma(-gb.x, wb.x, a0); a1 = fma(-gb.y, wb.y, a1);
+          a0 = fma(-gc.x, wc.x, a0); a1 = fma(-gc.y, wc.y, a1);
+          const double wn = a0 + a1;
+          if (act && !lastst && cwr) pWc[(s + 1) * kWS + ci] = wn;
+          if (act && lastst) cm = wn;
+          __syncwarp();
         }
-        double cb = __shfl_sync(FULL, cm, 6 + (lane % 6));
-        if (lane < 6) { double* pm = m.W + lane * NS + mid; *pm = *pm - cm - (s_bot > 0 ? cb : 0.0); }
+        const double cb = __shfl_sync(FULL, cm, 6 + ci);
+        if (lane < 6) m.W[mid * kWS + lane] = cm + (s_bot > 0 ? cb : 0.0);
       }
       __syncwarp();
       // ---- v = S^-1 w per stage
@@ -1065,26 +1074,22 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
         }
       }
       __syncwarp();
-      // ---- twisted chain, backward: L' y = v
+      // ---- twisted chain, backward: L' y = v (lane = column of G)
       {
-        const int kb = chl ? (half == 0 ? mid - 1 : mid + 1) : 0;
-        const int db = chl ? (half == 0 ? -1 : 1) : 0;
-        const double* pg = m.GG + cr * NS + (mysteps > 0 ? kb : 0);     // column cr of G: element (j, cr) at pg[j*6*NS]
-        double* pw = m.W + cr * NS + (mysteps > 0 ? kb : 0);
-        double yi = m.W[(lane % 6) * NS + mid];
 #pragma unroll
         for (int s = 0; s < nst; ++s) {
           const bool act = s < mysteps;
-          double g0 = pg[0], g1 = pg[6 * NS], g2 = pg[12 * NS], g3 = pg[18 * NS], g4 = pg[24 * NS], g5 = pg[30 * NS];
-          double vk = pw[0];
-          double a0 = fma(-g0, __shfl_sync(FULL, yi, cbase), vk);
-          double a1 = -g1 * __shfl_sync(FULL, yi, cbase + 1);
-          a0 = fma(-g2, __shfl_sync(FULL, yi, cbase + 2), a0);
-          a1 = fma(-g3, __shfl_sync(FULL, yi, cbase + 3), a1);
-          a0 = fma(-g4, __shfl_sync(FULL, yi, cbase + 4), a0);
-          a1 = fma(-g5, __shfl_sync(FULL, yi, cbase + 5), a1);
-          if (act) { yi = a0 + a1; pw[0] = yi; }
-          if (s + 1 < mysteps) { pg += db; pw += db; }
+          const double* ps = s == 0 ? m.W + mid * kWS : pWt - (s - 1) * kWS;      // y of the inner neighbour
+          const double* pgc = pGt - s * 36;
+          const double g0 = pgc[0], g1 = pgc[6], g2 = pgc[12], g3 = pgc[18], g4 = pgc[24], g5 = pgc[30];
+          const double vk = pWt[-s * kWS + ci];
+          const double2 ya = *reinterpret_cast<const double2*>(ps), yb = *reinterpret_cast<const double2*>(ps + 2),
+                        yc = *reinterpret_cast<const double2*>(ps + 4);
+          double a0 = -g0 * ya.x, a1 = fma(-g1, ya.y, vk);
+          a0 = fma(-g2, yb.x, a0); a1 = fma(-g3, yb.y, a1);
+          a0 = fma(-g4, yc.x, a0); a1 = fma(-g5, yc.y, a1);
+          if (act && cwr) pWt[-s * kWS + ci] = a0 + a1;
+          __syncwarp();
         }
       }
       __syncwarp();
