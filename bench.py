@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — batched MPC QP solves/sec on N B200s (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA engine through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own OSQP binary on the host cores
+
+A "step" is one pass of the hot path over one batch: device-side assembly of B mpcPlanner QPs + the batched
+ADMM solve.  Workload = BASELINE.json configs[1]: B = 1,024 randomised default-shape QPs per GPU (horizon 30,
+4 static obstacles, warm-started from the constant-velocity plan), seeds sharded by rank (weak scaling, no
+collective on the solve path; one NCCL all_gather of the solutions after the timed region for verification).
+`value` is timed with CUDA events on the engine's stream with inputs resident in HBM and the L2 flushed
+between steps; `e2e` is the same metric through mpcqp_solve_mpc_batch_host with pinned host buffers (H2D and
+D2H inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "batched MPC QP solves/sec"
+UNIT = "QPs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
+    ap.add_argument("--num-obs", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(B, R):
+    return f"configs[1]: {B} randomised default-shape QPs per GPU (horizon 30, n=385, m={625 + 29 * R}, {R} static obstacles, warm start)"
+
+
+# ---- algorithmic work per QP --------------------------------------------
+def algorithmic_flops(N, R, iters, rho_updates):
+    b, n, m = 13, 8 * (N + 1) + 5 * N, 16 * (N + 1) + 5 * N + R * N
+    nnzA, nnzP = 240 + 17 * N + n + 4 * N * R, 295 if N == 29 else 6 * (N + 1) + 5 * N
+    f_iter = 6 * b * b * N + 6 * 64 + 4 * nnzA + 2 * n + 10 * m
+    f_fact = (7.0 / 3.0) * b ** 3 * N + 32 * R * N + 2 * nnzA
+    f_chk = 4 * nnzA + 2 * nnzP + 6 * (n + m)
+    f_scale = 10 * (6 * (nnzP + 2 * nnzA) + 4 * (n + m))
+    it = np.asarray(iters, dtype=np.float64); nf = 1.0 + np.asarray(rho_updates, dtype=np.float64)
+    return f_scale + nf * f_fact + it * f_iter + np.ceil(it / 25.0) * f_chk
+
+
+def algorithmic_bytes(N, R):
+    return (870 + 174 * R) * 8.0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.stop_flag = False; self.rows = []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path: libosqp.so (OSQP 0.6.2) through its C API exactly as
+    OsqpEigen::Solver drives it (oracle/ref_driver.c), one QP per thread on all host cores, setup on the clock."""
+    if rank != 0:
+        return
+    from intent_mpc_b200 import workloads as W
+    from oracle import bindings as OB
+    from tests.helpers import to_qp_batch
+    kind = "reference" if OB.RefOsqp.available() else "port"
+    orc = OB.RefOsqp() if kind == "reference" else OB.PortOsqp()
+    cores = os.cpu_count() or 1
+    B, R = args.batch, args.num_obs
+    qb = to_qp_batch(W.static_batch(B, num_obs=R, seed0=0))
+    for _ in range(max(args.warmup, 0)):
+        orc.solve_batch(qb, want_y=False, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = orc.solve_batch(qb, want_y=False, nthreads=cores)
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(B, R), "pins": "adaptive_rho_interval=25,time_limit=0"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"the full {B}-QP batch per step, one QP per thread, osqp_setup+warm_start+solve+cleanup per QP"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "p50_latency_ms": float(np.median(out["wall_time"]) * 1e3), "status_hist": _hist(out["status"])}
+    print(json.dumps(line), flush=True)
+
+
+def _hist(a):
+    v, c = np.unique(np.asarray(a), return_counts=True)
+    return {str(int(k)): int(n) for k, n in zip(v, c)}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from intent_mpc_b200 import engine, workloads as W
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = engine.Engine(local_rank)
+    B, R, K, Wm = args.batch, args.num_obs, args.steps, max(args.warmup, 3)
+    mb = W.static_batch(B, num_obs=R, seed0=rank * B)
+    p = mb.params
+    N, n, m = p.N, p.n, p.m(R)
+    st = engine.default_settings()
+    dev = torch.device("cuda", local_rank)
+    names = ["x0", "xref", "obs_c", "obs_semi", "obs_yaw", "lin_pt", "warm_x"]
+    host = {k: np.ascontiguousarray(getattr(mb, k), dtype=np.float64) for k in names}
+    din = {k: torch.from_numpy(v).to(dev) for k, v in host.items()}
+    dout = {"x": torch.empty((B, n), dtype=torch.float64, device=dev), "status": torch.empty(B, dtype=torch.int32, device=dev),
+            "iter": torch.empty(B, dtype=torch.int32, device=dev), "rho_updates": torch.empty(B, dtype=torch.int32, device=dev),
+            "obj": torch.empty(B, dtype=torch.float64, device=dev), "pri_res": torch.empty(B, dtype=torch.float64, device=dev),
+            "dua_res": torch.empty(B, dtype=torch.float64, device=dev)}
+    ptrs = {k: int(v.data_ptr()) for k, v in {**din, **dout}.items()}
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MiB > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_device():
+        eng.solve_mpc_batch_ptr(p, st, B, R, ptrs, mb.obs_dyn, device=True)
+
+    for _ in range(Wm):
+        step_device()
+    eng.sync()
+    peak_tf = eng.fp64_fma_peak_tflops()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    solve_ms = []
+    for a, b in evs:
+        with torch.cuda.stream(stream):
+            flush.zero_()                                  # L2 flush, outside the timed pair
+            a.record(stream)
+        step_device()
+        with torch.cuda.stream(stream):
+            b.record(stream)
+        eng.sync()
+        solve_ms.append(eng.last_solve_kernel_ms)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * K / (total_ms * 1e-3)
+
+    iters = dout["iter"].cpu().numpy(); rhou = dout["rho_updates"].cpu().numpy(); status = dout["status"].cpu().numpy()
+
+    # ---- e2e: host (pinned) buffers through the public host entry point --------------------------------
+    pin = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    pout = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dout.items()}
+    hp = {k: int(v.data_ptr()) for k, v in {**pin, **pout}.items()}
+    for _ in range(2):
+        eng.solve_mpc_batch_ptr(p, st, B, R, hp, mb.obs_dyn, device=False)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.solve_mpc_batch_ptr(p, st, B, R, hp, mb.obs_dyn, device=False)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    d2h = sum(v.numel() * v.element_size() for v in pout.values())
+    assert np.array_equal(pout["iter"].numpy(), iters), "host and device entry points disagree"
+
+    # ---- verification gather (NCCL over NVLink; not on the solve path, not timed into `value`) ------------
+    gather_ms = None
+    if world > 1:
+        allx = torch.empty((world * B, n), dtype=torch.float64, device=dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(); dist.all_gather_into_tensor(allx, dout["x"]); g1.record(); torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sampler.join(timeout=2)
+
+    # ---- parity spot check against the oracle (untimed) and the CPU baseline ---------------------------
+    parity = cpu = None
+    try:
+        from oracle import bindings as OB
+        from tests.helpers import to_qp_batch, rel_inf
+        kind = "reference" if OB.RefOsqp.available() else "port"
+        orc = OB.RefOsqp() if kind == "reference" else OB.PortOsqp()
+        cores = os.cpu_count() or 1
+        qb = to_qp_batch(mb)
+        if not args.no_cpu_baseline:
+            orc.solve_batch(qb, want_y=False, nthreads=cores)
+            ref = orc.solve_batch(qb, want_y=False, nthreads=cores)
+            cpu = {"value": B / ref["wall"], "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"the full {B}-QP batch once (after one warm-up pass), one QP per thread; {ref['wall']:.2f} s wall",
+                   "p50_latency_ms": float(np.median(ref["wall_time"]) * 1e3)}
+            xg = dout["x"].cpu().numpy()
+            parity = {"checked": int(B), "status_equal": bool((ref["status"] == status).all()),
+                      "iter_equal": bool((ref["iter"] == iters).all()),
+                      "x_rel_err_max": float(rel_inf(xg, ref["x"]).max()),
+                      "obj_rel_err_max": float(np.abs((dout["obj"].cpu().numpy() - ref["obj"]) / ref["obj"]).max())}
+    except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU number
+        parity = {"error": repr(ex)}
+
+    flops = float(algorithmic_flops(N, R, iters, rhou).sum())
+    solve_avg_ms = float(np.mean(solve_ms))
+    ach_tf = flops / (solve_avg_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_ach = algorithmic_bytes(N, R) * B / (solve_avg_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(B, R), "batch_per_gpu": B, "num_obs": R, "horizon": p.horizon,
+                   "pins": "adaptive_rho_interval=25,time_limit=0", "l2": "flushed between steps (256 MiB write)",
+                   "kernel_path": eng.last_path, "iterations_total": int(iters.sum()), "iterations_max": int(iters.max())},
+        "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s / K},
+        "gpu_launches": 2 * K,
+        "p50_latency_ms": float(np.median(solve_ms)),
+        "status_hist": _hist(status),
+        "roofline": {"bound": "fp64_fma", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                     "traffic": None, "kernel": "mpcqp_solve_kernel", "kernel_ms": solve_avg_ms,
+                     "peak_source": "fp64 DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                     "algorithmic_flops_per_launch": flops,
+                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"}},
+        "cpu_baseline": cpu, "parity": parity, "clocks": sampler.summary(),
+    }
+    if gather_ms is not None:
+        line["verification_gather_ms"] = gather_ms
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

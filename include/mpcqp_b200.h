@@ -79,6 +79,8 @@ const char* mpcqp_engine_last_error(const mpcqp_engine* e);
 /* Device time (ms, CUDA events on the engine's stream) of the kernels of the last batch call, and how many
  * kernels it launched. */
 double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e);
+/* Same, solve kernel alone (the dominant kernel; excludes the device-side builder). */
+double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e);
 int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
 /* Which solve kernel the last batch ran: 1 = register-resident fast path (compile-time horizon/num_obs),
  * 0 = generic shared-memory kernel (any horizon/num_obs that fits).  force_generic(1) pins the generic kernel

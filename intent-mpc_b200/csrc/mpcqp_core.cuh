@@ -997,6 +997,8 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
     double* pWc = m.W + slot0 * kWS;
     const double* pGt = m.GG + slotT * 36 + ci;             // column ci of G at the backward target slot
     double* pWt = m.W + slotT * kWS;
+    double* dummy = m.PK + 8 * (lane & 7);                  // scratch slot for lanes whose result is not needed
+    double* pWk = live ? m.W + cslot(k) * kWS : dummy;      // this stage's 6-vector (ghost lanes: dummy)
 
     for (int it = 0; it < niter; ++it) {
       if (it == niter - 1 && live) {                 // park the old x, u: deltas are formed after the update
@@ -1025,35 +1027,41 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
         mm = notfirst ? mm : 0.0;
         r[cc] -= CV_(4 * cc + 2, km) * mm; r[3 + cc] -= CV_(4 * cc + 3, km) * mm;
       }
-      if (live) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) W_(i, k) = r[i];
-      }
+      for (int i = 0; i < 6; ++i) pWk[i] = r[i];
       __syncwarp();
       // ---- twisted chain, forward: L w = r.  6 lanes per chain (lane = row of the 6x6 block); lanes 0-5 walk up
       // from stage 0, lanes 6-11 walk down from stage N, both upward in chain-slot order.  The running vector is
       // exchanged through the W row that has to be written anyway (1 STS + 3 broadcast LDS.128 per step).
       {
         double cm = 0.0;
+        // software pipeline: the G row and the rhs entry of step s+1 are loaded before the store of step s
+        double2 ga = *reinterpret_cast<const double2*>(pGr), gb = *reinterpret_cast<const double2*>(pGr + 2),
+                gc = *reinterpret_cast<const double2*>(pGr + 4);
+        double rn = pWc[kWS + ci];
 #pragma unroll
         for (int s = 0; s < nst; ++s) {
           const bool act = s < mysteps, lastst = s == mysteps - 1;
-          const double2 ga = *reinterpret_cast<const double2*>(pGr + s * 36), gb = *reinterpret_cast<const double2*>(pGr + s * 36 + 2),
-                        gc = *reinterpret_cast<const double2*>(pGr + s * 36 + 4);
-          double rn = pWc[(s + 1) * kWS + ci];
           if (lastst && chalf == 1) rn = 0.0;
           const double2 wa = *reinterpret_cast<const double2*>(pWc + s * kWS), wb = *reinterpret_cast<const double2*>(pWc + s * kWS + 2),
                         wc = *reinterpret_cast<const double2*>(pWc + s * kWS + 4);
           double a0 = -ga.x * wa.x, a1 = fma(-ga.y, wa.y, rn);
           a0 = fma(-gb.x, wb.x, a0); a1 = fma(-gb.y, wb.y, a1);
           a0 = fma(-gc.x, wc.x, a0); a1 = fma(-gc.y, wc.y, a1);
+          if (s + 1 < nst) {
+            ga = *reinterpret_cast<const double2*>(pGr + (s + 1) * 36); gb = *reinterpret_cast<const double2*>(pGr + (s + 1) * 36 + 2);
+            gc = *reinterpret_cast<const double2*>(pGr + (s + 1) * 36 + 4);
+            rn = pWc[(s + 2) * kWS + ci];
+          }
           const double wn = a0 + a1;
-          if (act && !lastst && cwr) pWc[(s + 1) * kWS + ci] = wn;
-          if (act && lastst) cm = wn;
+          double* dst = (act && !lastst && cwr) ? pWc + (s + 1) * kWS + ci : dummy;   // branch-free: idle lanes hit a dummy slot
+          *dst = wn;
+          cm = (act && lastst) ? wn : cm;
           __syncwarp();
         }
         const double cb = __shfl_sync(FULL, cm, 6 + ci);
-        if (lane < 6) m.W[mid * kWS + lane] = cm + (s_bot > 0 ? cb : 0.0);
+        double* dst = lane < 6 ? m.W + mid * kWS + lane : dummy;
+        *dst = cm + (s_bot > 0 ? cb : 0.0);
       }
       __syncwarp();
       // ---- v = S^-1 w per stage
@@ -1068,27 +1076,30 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
           s0 = fma(SI_(a * 6 + 4, k), w[4], s0); s1 = fma(SI_(a * 6 + 5, k), w[5], s1);
           v[a] = s0 + s1;
         }
-        if (live) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) W_(j, k) = v[j];
-        }
+        for (int j = 0; j < 6; ++j) pWk[j] = v[j];
       }
       __syncwarp();
       // ---- twisted chain, backward: L' y = v (lane = column of G)
       {
+        double g0 = pGt[0], g1 = pGt[6], g2 = pGt[12], g3 = pGt[18], g4 = pGt[24], g5 = pGt[30];
+        double vk = pWt[ci];
 #pragma unroll
         for (int s = 0; s < nst; ++s) {
           const bool act = s < mysteps;
           const double* ps = s == 0 ? m.W + mid * kWS : pWt - (s - 1) * kWS;      // y of the inner neighbour
-          const double* pgc = pGt - s * 36;
-          const double g0 = pgc[0], g1 = pgc[6], g2 = pgc[12], g3 = pgc[18], g4 = pgc[24], g5 = pgc[30];
-          const double vk = pWt[-s * kWS + ci];
           const double2 ya = *reinterpret_cast<const double2*>(ps), yb = *reinterpret_cast<const double2*>(ps + 2),
                         yc = *reinterpret_cast<const double2*>(ps + 4);
           double a0 = -g0 * ya.x, a1 = fma(-g1, ya.y, vk);
           a0 = fma(-g2, yb.x, a0); a1 = fma(-g3, yb.y, a1);
           a0 = fma(-g4, yc.x, a0); a1 = fma(-g5, yc.y, a1);
-          if (act && cwr) pWt[-s * kWS + ci] = a0 + a1;
+          if (s + 1 < nst) {
+            const double* pgc = pGt - (s + 1) * 36;
+            g0 = pgc[0]; g1 = pgc[6]; g2 = pgc[12]; g3 = pgc[18]; g4 = pgc[24]; g5 = pgc[30];
+            vk = pWt[-(s + 1) * kWS + ci];
+          }
+          double* dst = (act && cwr) ? pWt - s * kWS + ci : dummy;
+          *dst = a0 + a1;
           __syncwarp();
         }
       }
@@ -1114,32 +1125,34 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
           for (int j = 8; j < NV; ++j) xt[j] = 0.0;
         }
       }
-      // ---- z, u, x updates and the next right-hand side
+      // ---- z, u, x updates and the next right-hand side.  Clamps are spelled as OSQP's c_min/c_max macros
+      // (a > b ? a : b), which is both the reference semantics for NaN and cheaper than fmin/fmax.
       double racc[NV], td[8];
 #pragma unroll
       for (int j = 0; j < NV; ++j) racc[j] = 0.0;
       {
-        double xm[NV];
+        // what stage k-1 contributes to stage k's dynamics rows: Ad x~_{k-1} + Bd u~_{k-1}  (8 values, one shuffle each)
+        double pr[8];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) { double v = __shfl_up_sync(FULL, xt[j], 1); xm[j] = notfirst ? v : 0.0; }
+        for (int cc = 0; cc < 3; ++cc) { pr[cc] = xt[cc] + apv * xt[3 + cc] + bpa * xt[8 + cc]; pr[3 + cc] = xt[3 + cc] + bva * xt[8 + cc]; }
+        pr[6] = xt[11]; pr[7] = xt[12];
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
-          double zt = -xt[rr];
-          if (rr < 3) zt += xm[rr] + apv * xm[3 + rr] + bpa * xm[8 + rr];
-          else if (rr < 6) zt += xm[rr] + bva * xm[5 + rr];
-          else zt += xm[5 + rr];
+          double pv = __shfl_up_sync(FULL, pr[rr], 1);
+          double zt = (notfirst ? pv : 0.0) - xt[rr];
           double v = al * zt + om * z[rr] + u[rr];
-          double zn = fmin(fmax(v, bnd[rr]), bnd[rr]);
-          z[rr] = zn; u[rr] = v - zn;
-          double t = RH_(rr, k) * (zn - u[rr]);
+          z[rr] = bnd[rr];                         // equality row: the projection onto [b, b] is b
+          u[rr] = v - bnd[rr];
+          double t = RH_(rr, k) * (bnd[rr] - u[rr]);
           td[rr] = t; racc[rr] -= t;
         }
       }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         double v = al * xt[j] + om * z[8 + j] + u[8 + j];
-        double zn = fmin(fmax(v, sh.blo[j]), sh.bhi[j]);
-        if (j >= 8 && !hasu) { zn = 0.0; v = 0.0; }
+        const double lo = sh.blo[j], hi = sh.bhi[j];
+        double zn = v > lo ? v : lo;
+        zn = zn < hi ? zn : hi;
         z[8 + j] = zn; u[8 + j] = v - zn;
         racc[j] += RH_(8 + j, k) * (zn - u[8 + j]);
       }
@@ -1149,8 +1162,8 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
         double g0 = G3_(3 * o, k), g1 = G3_(3 * o + 1, k), g2 = G3_(3 * o + 2, k);
         double zt = g0 * xt[0] + g1 * xt[1] + g2 * xt[2] - (sl[o] ? xt[12] : xt[11]);
         double v = al * zt + om * z[i] + u[i];
-        double zn = fmax(v, LO_(o, k));
-        if (!hasu) { zn = 0.0; v = 0.0; }
+        const double lo = LO_(o, k);
+        double zn = v > lo ? v : lo;
         z[i] = zn; u[i] = v - zn;
         double t = RH_(i, k) * (zn - u[i]);
         racc[0] += g0 * t; racc[1] += g1 * t; racc[2] += g2 * t;

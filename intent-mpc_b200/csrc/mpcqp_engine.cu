@@ -125,9 +125,9 @@ struct DevBuf {
 struct mpcqp_engine {
   int device = 0, num_sms = 0, max_smem_optin = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   std::string err;
-  double last_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter;
   // staging for the *_host entry point
@@ -168,7 +168,7 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
   e->num_sms = pr.multiProcessorCount;
   e->max_smem_optin = (int)pr.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) { delete e; return MPCQP_ERR_CUDA; }
+      cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreate(&e->evs) != cudaSuccess) { delete e; return MPCQP_ERR_CUDA; }
   *out = e;
   return MPCQP_OK;
 }
@@ -181,6 +181,7 @@ extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
   for (DevBuf* b : bufs) b->release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->evs) cudaEventDestroy(e->evs);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return MPCQP_OK;
@@ -188,6 +189,7 @@ extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
 
 extern "C" const char* mpcqp_engine_last_error(const mpcqp_engine* e) { return e ? e->err.c_str() : "null engine"; }
 extern "C" double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e) { return e ? e->last_ms : 0.0; }
+extern "C" double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e) { return e ? e->last_solve_ms : 0.0; }
 extern "C" int64_t mpcqp_engine_last_launches(const mpcqp_engine* e) { return e ? e->last_launches : 0; }
 extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->last_fast : -1; }
 extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
@@ -264,6 +266,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   CK(e->counter.need(sizeof(int)));
   bt.ws = e->ws.as<double>();
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
+  CK(cudaEventRecord(e->evs, e->stream));
   kern<<<(unsigned)grid, 32, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
   CK(cudaGetLastError());
   e->last_launches += 1;
@@ -336,6 +339,7 @@ extern "C" int mpcqp_engine_sync(mpcqp_engine* e) {
   CK(cudaStreamSynchronize(e->stream));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms;
+  if (cudaEventElapsedTime(&ms, e->evs, e->ev1) == cudaSuccess) e->last_solve_ms = ms;
   return MPCQP_OK;
 }
 

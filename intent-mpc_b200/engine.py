@@ -59,6 +59,7 @@ def load_library() -> C.CDLL:
         lib = C.CDLL(LIB_PATH)
         lib.mpcqp_engine_last_error.restype = C.c_char_p
         lib.mpcqp_engine_last_kernel_ms.restype = C.c_double
+        lib.mpcqp_engine_last_solve_kernel_ms.restype = C.c_double
         lib.mpcqp_engine_last_launches.restype = C.c_int64
         lib.mpcqp_engine_stream.restype = C.c_void_p
         _lib = lib
@@ -124,6 +125,10 @@ class Engine:
     @property
     def last_kernel_ms(self) -> float:
         return float(self.lib.mpcqp_engine_last_kernel_ms(self.h))
+
+    @property
+    def last_solve_kernel_ms(self) -> float:
+        return float(self.lib.mpcqp_engine_last_solve_kernel_ms(self.h))
 
     @property
     def last_launches(self) -> int:
