@@ -74,6 +74,7 @@ struct Batch {              // device pointers
   const double* g;              // [B][NS-1][R][3] obstacle-row gradients
   const double* low;            // [B][NS-1][R]    obstacle-row lower bounds (upper = +inf)
   const double* warm_x;         // [B][n] or nullptr
+  const double* warm_y;         // [B][m] or nullptr (dual warm start; the reference always passes zeros, MP.cpp:487)
   double* x;                    // [B][n]
   double* y;                    // [B][m] or nullptr
   int* status; int* iter; int* rho_updates;
@@ -190,6 +191,10 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
 #define SLK_(o, k) ((int)slack[(k) * R + (o)])
 
   MQ_HD int nrows(int k) const { return k < N ? MK : 16; }
+  // position of row i of stage k in the reference's constraint ordering (MP.cpp:989-1071)
+  MQ_HD int row_index(int k, int i) const {
+    return i < 8 ? 8 * k + i : (i < 16 ? 8 * NS + 8 * k + (i - 8) : (i < NBR ? 16 * NS + 5 * k + (i - 16) : 16 * NS + 5 * N + k * R + (i - NBR)));
+  }
   MQ_HD int nvars(int k) const { return k < N ? NV : NX; }
 
   // ---- warp reductions -------------------------------------------------------------------
@@ -371,6 +376,13 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
     }
     MQ_SYNC();
     MQ_FOR_STAGES(k) { const int nr = nrows(k); for (int i = 0; i < nr; ++i) Z_(i, k) = row_ax(k, i, [&](int j, int kk) { return X_(j, kk); }); }
+    if (bt.warm_y && st.warm_start) {   // y_s = c E^-1 y  =>  u = E^-1 y_s / rho = c y / Rh
+      const double* wy = bt.warm_y + (size_t)b * sh.m;
+      MQ_FOR_STAGES(k) {
+        const int nr = nrows(k);
+        for (int i = 0; i < nr; ++i) U_(i, k) = c * wy[row_index(k, i)] / RH_(i, k);
+      }
+    }
     MQ_SYNC();
   }
 
@@ -1243,8 +1255,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
       const int nv = nvars(k), nr = nrows(k);
       for (int j = 0; j < nv; ++j) xo[j < 8 ? 8 * k + j : 8 * NS + 5 * k + (j - 8)] = has ? X_(j, k) : kOsqpNan;
       if (yo) for (int i = 0; i < nr; ++i) {
-        int gi = i < 8 ? 8 * k + i : (i < 16 ? 8 * NS + 8 * k + (i - 8) : (i < NBR ? 16 * NS + 5 * k + (i - 16) : 16 * NS + 5 * N + k * R + (i - NBR)));
-        yo[gi] = has ? RH_(i, k) * U_(i, k) * cinv : kOsqpNan;
+        yo[row_index(k, i)] = has ? RH_(i, k) * U_(i, k) * cinv : kOsqpNan;
       }
     }
 #if MQ_DEV
