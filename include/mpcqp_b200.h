@@ -82,9 +82,10 @@ double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e);
 /* Same, solve kernel alone (the dominant kernel; excludes the device-side builder). */
 double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e);
 int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
-/* Which solve kernel the last batch ran: 1 = register-resident fast path (compile-time horizon/num_obs),
- * 0 = generic shared-memory kernel (any horizon/num_obs that fits).  force_generic(1) pins the generic kernel
- * (used by the tests to cover both). */
+/* Which solve kernel the last batch ran: 2 = CTA kernel (one 4-warp CTA per QP, parallel-cyclic-reduction solve,
+ * horizon 30, num_obs <= 8), 1 = one-warp-per-QP register-resident kernel (same shapes), 0 = generic one-warp
+ * shared-memory kernel (any horizon/num_obs that fits).  force_generic(1) pins the generic kernel, (2) the
+ * one-warp register kernel, (0) restores the default dispatch (used by the tests to cover all three). */
 int mpcqp_engine_last_path(const mpcqp_engine* e);
 int mpcqp_engine_force_generic(mpcqp_engine* e, int on);
 /* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */

@@ -84,28 +84,58 @@ struct Batch {              // device pointers
 };
 
 // Where each per-stage array lives.  Element (slot j, stage k) of array A is A[j*NS + k].
-//   generic mode (runtime dims, any horizon): everything the iteration touches is in shared memory.
-//   fast mode (compile-time dims, horizon <= 32): the iterates x, z, u and the right-hand side live in
-//   REGISTERS during a burst of iterations and are parked in the per-warp global scratch between bursts,
-//   so shared memory only holds the read-only scaled data, the factor and the 6-vector exchange buffer.
+//   mode 0, generic (runtime dims, any horizon): everything the iteration touches is in shared memory; one warp
+//           per QP; twisted block LDL' chain.
+//   mode 1, warp-fast (compile-time dims, horizon <= 32): one warp per QP; the iterates x, z, u and the right-hand
+//           side live in REGISTERS during a burst of iterations and are parked in the per-warp global scratch
+//           between bursts; shared memory holds the read-only scaled data, the twisted factor and the 6-vector
+//           exchange buffer.
+//   mode 2, CTA (horizon == 30): one 4-warp CTA per QP; the block-tridiagonal solve is a parallel cyclic reduction
+//           whose per-level 6x6 matrices fill shared memory (86 KB); iterates live in registers split by axis
+//           across the warps; everything cold (factor workspace, parked iterates) is in the per-CTA global scratch.
+constexpr int kModeGeneric = 0, kModeWarp = 1, kModeCta = 2;
+constexpr int kPcrLevels = 5, kPcrLevelDoubles = 3 * 12 * 30 * 2, kPcrDoubles = kPcrLevels * kPcrLevelDoubles;
 struct Mem {
-  double *X, *Z, *U, *B, *TD, *MA;                       // iterates, rhs, exchange (cold in fast mode)
+  double *X, *Z, *U, *B, *TD, *MA;                       // iterates, rhs, exchange (cold in modes 1, 2)
   double *RH, *SD, *CQ, *G3, *LO, *W;                    // read-only per iteration + work vector
   double *SI, *GG, *DSI, *ESD, *DGI, *FS, *DAI, *CV, *PK; // factor (+ 72-double parking area)
   double *E, *D, *DY, *DX;                               // always in global scratch
+  double *PCR, *RA, *RS, *YB;                            // mode 2, shared: PCR matrices, r ping-pong, slack part of r, y
+  double *PD, *PL, *PI, *OG;                             // mode 2, global: PCR factor workspace (D, L x2, D^-1); parked obstacle part of the rhs
 };
-MQ_HHD int hot_slots(int R, bool fast) { return (NBR + R) + NV + NV + 3 * R + R + (fast ? 6 : NV) + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12; }
+MQ_HHD int hot_slots(int R, int mode) {
+  if (mode == kModeCta) return (NBR + R) + NV + NV + 3 * R + R;
+  return (NBR + R) + NV + NV + 3 * R + R + (mode == kModeWarp ? 6 : NV) + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12;
+}
 MQ_HHD int iter_slots(int R) { return NV + 2 * (NBR + R) + NV + 8 + 3; }
-MQ_HHD int smem_doubles(int NS, int R, bool fast) { return (hot_slots(R, fast) + (fast ? 0 : iter_slots(R))) * NS + 72; }
-MQ_HHD int ws_doubles(int NS, int R, bool fast) { return (2 * (NBR + R) + 2 * NV + (fast ? iter_slots(R) : 0)) * NS; }
-MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, bool fast) {
+MQ_HHD int smem_doubles(int NS, int R, int mode) {
+  if (mode == kModeCta) return kPcrDoubles + 2 * 6 * NS + 4 * NS + 6 * NS + hot_slots(R, mode) * NS;
+  return (hot_slots(R, mode) + (mode == kModeWarp ? 0 : iter_slots(R))) * NS + 72;
+}
+MQ_HHD int ws_doubles(int NS, int R, int mode) {
+  const int base = 2 * (NBR + R) + 2 * NV;
+  if (mode == kModeCta) return (base + iter_slots(R) + NV + 36 + 36 + 27 + 36 + 72 + 36 + 3) * NS;
+  return (base + (mode == kModeWarp ? iter_slots(R) : 0)) * NS;
+}
+MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) {
   const int MK = NBR + R;
   double* p = sm;
+  double* g = ws;
+  m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
+  if (mode == kModeCta) {
+    m.PCR = p; p += kPcrDoubles; m.RA = p; p += 2 * 6 * NS; m.RS = p; p += 4 * NS; m.YB = p; p += 6 * NS;
+    m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
+    m.X = g; g += NV * NS; m.Z = g; g += MK * NS; m.U = g; g += MK * NS; m.B = g; g += NV * NS; m.TD = g; g += 8 * NS; m.MA = g; g += 3 * NS;
+    m.W = g; g += NV * NS; m.SI = g; g += 36 * NS; m.GG = g; g += 36 * NS; m.DSI = g; g += 2 * NS; m.ESD = g; g += 2 * NS;
+    m.DGI = g; g += 2 * NS; m.FS = g; g += 6 * NS; m.DAI = g; g += 3 * NS; m.CV = g; g += 12 * NS; m.PK = nullptr;
+    m.PD = g; g += 36 * NS; m.PL = g; g += 72 * NS; m.PI = g; g += 36 * NS; m.OG = g; g += 3 * NS;
+    return;
+  }
+  const bool fast = mode == kModeWarp;
+  m.PCR = m.RA = m.RS = m.YB = m.PD = m.PL = m.PI = m.OG = nullptr;
   m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
   m.W = p; p += (fast ? 6 : NV) * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
   m.DGI = p; p += 2 * NS; m.FS = p; p += 6 * NS; m.DAI = p; p += 3 * NS; m.CV = p; p += 12 * NS; m.PK = p; p += 72;
-  double* g = ws;
-  m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
   double*& c = fast ? g : p;
   m.X = c; c += NV * NS; m.Z = c; c += MK * NS; m.U = c; c += MK * NS; m.B = c; c += NV * NS; m.TD = c; c += 8 * NS; m.MA = c; c += 3 * NS;
 }
@@ -148,10 +178,13 @@ MQ_HD void inv6(double* a) {
   }
 }
 
-template <int NST, int RT> struct Qp : DimsT<NST, RT> {
+template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> struct Qp : DimsT<NST, RT> {
   using Dm = DimsT<NST, RT>;
   using Dm::NS; using Dm::N; using Dm::R; using Dm::MK;
-  static constexpr bool kFast = NST > 0;
+  static constexpr bool kFast = QMODE == kModeWarp;
+  static constexpr bool kCta = QMODE == kModeCta;
+  static_assert(QMODE == kModeGeneric || NST > 0, "modes 1 and 2 need compile-time dims");
+  static_assert(QMODE != kModeCta || NST == 30, "the CTA path is built for horizon 30 (5 PCR levels)");
   static constexpr int kWS = 6;    // fast mode: W holds one 6-vector per stage, stage-major (16-byte aligned rows)
   // Fast mode stores the per-stage chain data (G, W) in CHAIN order so that both chains of the twisted
   // recursion walk upward in memory: stages 0..mid-1 -> slots 0..mid-1, mid -> slot mid, stages N..mid+1 ->
@@ -189,6 +222,10 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
 #define WSDY_(i, k) m.DY[(i) * NS + (k)]
 #define WSDX_(j, k) m.DX[(j) * NS + (k)]
 #define SLK_(o, k) ((int)slack[(k) * R + (o)])
+#define PD_(e, k) m.PD[(e) * NS + (k)]
+#define PL_(buf, e, k) m.PL[((buf) * 36 + (e)) * NS + (k)]
+#define PI_(e, k) m.PI[(e) * NS + (k)]
+#define OG_(c, k) m.OG[(c) * NS + (k)]
 
   MQ_HD int nrows(int k) const { return k < N ? MK : 16; }
   // position of row i of stage k in the reference's constraint ordering (MP.cpp:989-1071)
@@ -484,6 +521,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
       }
     }
     MQ_SYNC();
+    if constexpr (kCta) { pcr_factor(); return; }
     // pass 3: twisted recursion.  chain 0 walks k = 0..mid-1 upward, chain 1 walks k = N..mid+1 downward;
     // both run the same instruction stream on two lanes.  Their Schur corrections onto the middle block
     // are parked in the (idle during factorisation) B/W/TD/MA scratch columns mid and mid+1.
@@ -565,6 +603,153 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
       k = kn;
     }
   }
+
+
+  // ---- mode 2: block parallel cyclic reduction (PCR) of the reduced KKT matrix --------------------------
+  // The (p_k, v_k) system  L_k y_{k-s} + D_k y_k + L_{k+s}' y_{k+s} = r_k  (s = 1 initially, D_k = T_k from the
+  // leaf elimination above, L_k = coupling of stages k-1 and k) is reduced in log2 steps: eliminating the two
+  // neighbours at distance s gives the same form at distance 2s with
+  //     alpha_k = L_k D_{k-s}^-1,  gamma_k = L_{k+s}' D_{k+s}^-1,
+  //     r_k <- r_k - alpha_k r_{k-s} - gamma_k r_{k+s},   D_k <- D_k - alpha_k L_k' - gamma_k L_{k+s},
+  //     L_k <- -alpha_k L_{k-s}.
+  // With 30 stages, after strides 1, 2, 4, 8 every equation couples to ONE partner at distance 16 (or none), and
+  // the last step is folded into the final solve:  y_k = D'^-1 r_k - (D'^-1 M_k) r_partner.  All stages advance
+  // in parallel, so a solve is 5 dependent 6x6 mat-vec rounds instead of the 30 dependent steps of a block LDL'.
+  // Storage (shared memory, 5 x [3][12][NS][2] doubles): matrices are kept in AXIS-MAJOR order
+  // (p_x v_x p_y v_y p_z v_z) and split by row pair, so that warp w of the CTA reads rows 2w, 2w+1 of its stage
+  // as 12 conflict-free 16-byte loads per level.
+  MQ_HHD static int pcr_old(int a) { return (a >> 1) + 3 * (a & 1); }       // axis-major index -> (p, v)-major index
+  // element [a][b] (axis-major) of matrix `half` of level l: half 0 = alpha (level 4: D'^-1), 1 = gamma (level 4: D'^-1 M)
+  MQ_HD int pcr_idx(int l, int half, int a, int b, int k) const {
+    return l * kPcrLevelDoubles + (((a >> 1) * 12 + half * 6 + (a & 1) * 3 + (b >> 1)) * NS + k) * 2 + (b & 1);
+  }
+  MQ_NOINL void pcr_factor() {
+    MQ_FOR_STAGES(k) {
+      for (int e = 0; e < 36; ++e) { PD_(e, k) = SI_(e, k); PL_(0, e, k) = 0.0; }
+      if (k > 0) {
+        for (int cc = 0; cc < 3; ++cc) {
+          PL_(0, cc * 6 + cc, k) = GG_(4 * cc, k - 1); PL_(0, cc * 6 + 3 + cc, k) = GG_(4 * cc + 1, k - 1);
+          PL_(0, (3 + cc) * 6 + cc, k) = GG_(4 * cc + 2, k - 1); PL_(0, (3 + cc) * 6 + 3 + cc, k) = GG_(4 * cc + 3, k - 1);
+        }
+      }
+    }
+    MQ_SYNC();
+    int cur = 0;
+    for (int l = 0, s = 1; l < kPcrLevels; ++l, s <<= 1) {
+      const bool last = l == kPcrLevels - 1;
+      MQ_FOR_STAGES(k) {
+        double S[36];
+#pragma unroll
+        for (int e = 0; e < 36; ++e) S[e] = PD_(e, k);
+        inv6(S);
+#pragma unroll
+        for (int e = 0; e < 36; ++e) PI_(e, k) = S[e];
+      }
+      MQ_SYNC();
+      MQ_FOR_STAGES(k) {
+        const bool hm = k - s >= 0, hp = k + s <= N, hmm = k - 2 * s >= 0;
+        const int km = hm ? k - s : k, kp = hp ? k + s : k;
+        if (!last) {
+          // row by row, so that only a few 6-vectors are live
+#pragma unroll 1
+          for (int i = 0; i < 6; ++i) {
+            double a[6], g[6], d[6], ln[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sa = 0.0, sg = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) { sa += PL_(cur, i * 6 + t, k) * PI_(t * 6 + j, km); sg += PL_(cur, t * 6 + i, kp) * PI_(t * 6 + j, kp); }
+              a[j] = hm ? sa : 0.0; g[j] = hp ? sg : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sd = PD_(i * 6 + j, k), sl = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) { sd -= a[t] * PL_(cur, j * 6 + t, k); sl -= a[t] * PL_(cur, t * 6 + j, km); }
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sd -= g[t] * PL_(cur, t * 6 + j, kp);
+              d[j] = sd; ln[j] = hmm ? sl : 0.0;
+            }
+            // D_k is read by its own lane only and row i is complete: update in place.  L goes to the other buffer.
+            const int an = 2 * (i % 3) + i / 3;                      // axis-major position of (p,v)-major row i
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              PD_(i * 6 + j, k) = d[j]; PL_(1 - cur, i * 6 + j, k) = ln[j];
+              const int bn = 2 * (j % 3) + j / 3;
+              m.PCR[pcr_idx(l, 0, an, bn, k)] = a[j]; m.PCR[pcr_idx(l, 1, an, bn, k)] = g[j];
+            }
+          }
+        } else {
+          // single partner: M = alpha (partner k-s) or gamma (partner k+s); D' = D - M (.)', y = D'^-1 r - D'^-1 M r_partner
+          double M[36], S[36];
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sa = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sa += hm ? PL_(cur, i * 6 + t, k) * PI_(t * 6 + j, km) : PL_(cur, t * 6 + i, kp) * PI_(t * 6 + j, kp);
+              M[i * 6 + j] = (hm || hp) ? sa : 0.0;
+            }
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sd = PD_(i * 6 + j, k);
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sd -= M[i * 6 + t] * (hm ? PL_(cur, j * 6 + t, k) : PL_(cur, t * 6 + j, kp));
+              S[i * 6 + j] = sd;
+            }
+          inv6(S);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int an = 2 * (i % 3) + i / 3;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const int bn = 2 * (j % 3) + j / 3;
+              double sm = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sm += S[i * 6 + t] * M[t * 6 + j];
+              m.PCR[pcr_idx(l, 0, an, bn, k)] = S[i * 6 + j]; m.PCR[pcr_idx(l, 1, an, bn, k)] = sm;
+            }
+          }
+        }
+      }
+      MQ_SYNC();
+      cur ^= 1;
+    }
+  }
+#if !MQ_DEV
+  // Plain-loop PCR solve on W(0..5, .) — the executable specification of what the CTA kernel's three axis warps
+  // do (host emulation only).
+  void pcr_solve_ref() {
+    double r[2][32][6];
+    for (int k = 0; k < NS; ++k) for (int a = 0; a < 6; ++a) r[0][k][a] = W_(pcr_old(a), k);
+    int cur = 0;
+    for (int l = 0, s = 1; l < kPcrLevels - 1; ++l, s <<= 1) {
+      for (int k = 0; k < NS; ++k) {
+        const int km = k - s >= 0 ? k - s : k, kp = k + s <= N ? k + s : k;
+        for (int a = 0; a < 6; ++a) {
+          double v = r[cur][k][a];
+          for (int b = 0; b < 6; ++b) v -= m.PCR[pcr_idx(l, 0, a, b, k)] * r[cur][km][b];
+          for (int b = 0; b < 6; ++b) v -= m.PCR[pcr_idx(l, 1, a, b, k)] * r[cur][kp][b];
+          r[1 - cur][k][a] = v;
+        }
+      }
+      cur ^= 1;
+    }
+    const int l = kPcrLevels - 1, s = 1 << l;
+    for (int k = 0; k < NS; ++k) {
+      const int kq = k - s >= 0 ? k - s : (k + s <= N ? k + s : k);
+      for (int a = 0; a < 6; ++a) {
+        double v = 0.0;
+        for (int b = 0; b < 6; ++b) v += m.PCR[pcr_idx(l, 0, a, b, k)] * r[cur][k][b];
+        for (int b = 0; b < 6; ++b) v -= m.PCR[pcr_idx(l, 1, a, b, k)] * r[cur][kq][b];
+        W_(pcr_old(a), k) = v;
+      }
+    }
+  }
+#endif
 
   // ---- one ADMM iteration (auxil.h:67-112: update_xz_tilde, update_x, update_z, update_y) --------
   // rows_phase<MODE>: MODE 0 = normal iteration tail, 1 = (re)build the right-hand side only (no iterate
@@ -821,6 +1006,9 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
   }
   template <int MODE> MQ_HD void iterate() {
     leaf_forward();
+#if !MQ_DEV
+    if constexpr (kCta) pcr_solve_ref(); else
+#endif
     chain_solve();
     leaf_backward();
     rows_phase<MODE>();
@@ -1208,6 +1396,352 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
   }
 #endif
 
+
+#if MQ_DEV
+  // ================================================================================================
+  // mode 2: one 4-warp CTA per QP.  lane = stage in every warp; warps 0..2 own one axis each (variables p, v, a of
+  // that axis, their two dynamics rows and three box rows, and rows 2w, 2w+1 of the PCR solve); warp 3 owns the
+  // slack states / slack inputs, their rows and the obstacle rows.  All iterates live in registers during a burst;
+  // the warps exchange the reduced right-hand side, the PCR intermediate vectors and the solution through small
+  // shared-memory buffers with named barriers (6 per iteration).
+  // ================================================================================================
+  static MQ_HD void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+  static MQ_HD double up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+  static MQ_HD double dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+  static MQ_HD double clampd(double v, double lo, double hi) { double z = v > lo ? v : lo; return z < hi ? z : hi; }
+  static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3;
+
+  MQ_HD void burst_cta(int niter, int warp) {
+    const int k = lane < NS ? lane : NS - 1;            // ghost lanes shadow the last stage, never write
+    const bool live = lane < NS, hasu = lane < N, notfirst = lane > 0 && live;
+    const int kp = k < N ? k + 1 : k, km = k > 0 ? k - 1 : 0;
+    const double al = st.alpha, om = 1.0 - st.alpha, apv = sh.a_pv, bpa = sh.b_pa, bva = sh.b_va;
+    double2* const RA2 = reinterpret_cast<double2*>(m.RA);      // [2][NS][3] pairs
+    double2* const RS2 = reinterpret_cast<double2*>(m.RS);      // [NS][2] pairs: (x, y), (z, -)
+    double2* const YB2 = reinterpret_cast<double2*>(m.YB);      // [NS][3] pairs
+    if (warp < 3) {
+      // ------------------------------------------------------------------------------------------
+      // axis warp
+      // ------------------------------------------------------------------------------------------
+      const int cc = warp;
+      double x[3], zb[3], ub[3], b[3], rhb[3], sd[3], cq[3], lo[3], hi[3], ox[3], oub[3];
+      double zd[2], ud[2], rhd[2], bnd[2], oud[2];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const int j = e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc);
+        x[e] = X_(j, k); zb[e] = Z_(8 + j, k); ub[e] = U_(8 + j, k); b[e] = B_(j, k); rhb[e] = RH_(8 + j, k);
+        sd[e] = SD_(j, k); cq[e] = CQ_(j, k); lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; ox[e] = 0.0; oub[e] = 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = cc + 3 * e;
+        zd[e] = Z_(i, k); ud[e] = U_(i, k); rhd[e] = RH_(i, k); bnd[e] = (k == 0) ? -x0p[i] : 0.0; oud[e] = 0.0;
+      }
+      const double dai = DAI_(cc, k), cv0 = CV_(4 * cc, k), cv1 = CV_(4 * cc + 1, k), cv2 = CV_(4 * cc + 2, k), cv3 = CV_(4 * cc + 3, k);
+      const double cv2m = notfirst ? CV_(4 * cc + 2, km) : 0.0, cv3m = notfirst ? CV_(4 * cc + 3, km) : 0.0;
+      const double2* const M = reinterpret_cast<const double2*>(m.PCR) + (cc * 12) * NS + k;
+      const int kq = k >= 16 ? k - 16 : (k + 16 <= N ? k + 16 : k);
+
+      for (int it = 0; it < niter; ++it) {
+        if (it == niter - 1) {
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { ox[e] = x[e]; oub[e] = ub[e]; }
+          oud[0] = ud[0]; oud[1] = ud[1];
+        }
+        // ---- leaf forward (this axis' acceleration): reduced rhs rows (p, v); the slack/obstacle part comes from warp 3
+        double r0, r1;
+        {
+          const double ma = dai * b[2];
+          const double mm = up1(ma);
+          r0 = b[0] - cv0 * ma; r1 = b[1] - cv1 * ma;
+          r0 -= cv2m * mm; r1 -= cv3m * mm;             // cv2m = cv3m = 0 on stage 0
+        }
+        if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
+        bar_sync(kBarAll, 128);
+        r0 += m.RS[k * 4 + cc];
+        // ---- PCR levels 0..3
+#pragma unroll
+        for (int l = 0; l < kPcrLevels - 1; ++l) {
+          const int s = 1 << l, cur = l & 1;
+          const int kmm = k - s >= 0 ? k - s : k, kpp = k + s <= N ? k + s : k;
+          const double2* ra = RA2 + cur * 3 * NS;
+          double2 a0 = ra[kmm * 3], a1 = ra[kmm * 3 + 1], a2 = ra[kmm * 3 + 2];
+          double2 c0 = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
+          if (l == 0) {
+            const double2 sm0 = RS2[kmm * 2], sm1 = RS2[kmm * 2 + 1], sp0 = RS2[kpp * 2], sp1 = RS2[kpp * 2 + 1];
+            a0.x += sm0.x; a1.x += sm0.y; a2.x += sm1.x;
+            c0.x += sp0.x; c1.x += sp0.y; c2.x += sp1.x;
+          }
+          const double2* ml = M + l * (kPcrLevelDoubles / 2);
+          const double2 m0 = ml[0], m1 = ml[NS], m2 = ml[2 * NS], m3 = ml[3 * NS], m4 = ml[4 * NS], m5 = ml[5 * NS];
+          const double2 m6 = ml[6 * NS], m7 = ml[7 * NS], m8 = ml[8 * NS], m9 = ml[9 * NS], m10 = ml[10 * NS], m11 = ml[11 * NS];
+          double sa0 = m0.x * a0.x, sa1 = m3.x * a0.x, sg0 = m6.x * c0.x, sg1 = m9.x * c0.x;
+          sa0 = fma(m0.y, a0.y, sa0); sa1 = fma(m3.y, a0.y, sa1); sg0 = fma(m6.y, c0.y, sg0); sg1 = fma(m9.y, c0.y, sg1);
+          sa0 = fma(m1.x, a1.x, sa0); sa1 = fma(m4.x, a1.x, sa1); sg0 = fma(m7.x, c1.x, sg0); sg1 = fma(m10.x, c1.x, sg1);
+          sa0 = fma(m1.y, a1.y, sa0); sa1 = fma(m4.y, a1.y, sa1); sg0 = fma(m7.y, c1.y, sg0); sg1 = fma(m10.y, c1.y, sg1);
+          sa0 = fma(m2.x, a2.x, sa0); sa1 = fma(m5.x, a2.x, sa1); sg0 = fma(m8.x, c2.x, sg0); sg1 = fma(m11.x, c2.x, sg1);
+          sa0 = fma(m2.y, a2.y, sa0); sa1 = fma(m5.y, a2.y, sa1); sg0 = fma(m8.y, c2.y, sg0); sg1 = fma(m11.y, c2.y, sg1);
+          r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
+          if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
+          bar_sync(kBarAxis, 96);
+        }
+        // ---- last level fused with D'^-1:  y = D'^-1 r_k - (D'^-1 M) r_partner   (buffer 0 holds the level-4 input)
+        double y0, y1;
+        {
+          const double2* ra = RA2;
+          const double2 a0 = ra[k * 3], a1 = ra[k * 3 + 1], a2 = ra[k * 3 + 2];
+          const double2 c0 = ra[kq * 3], c1 = ra[kq * 3 + 1], c2 = ra[kq * 3 + 2];
+          const double2* ml = M + (kPcrLevels - 1) * (kPcrLevelDoubles / 2);
+          const double2 m0 = ml[0], m1 = ml[NS], m2 = ml[2 * NS], m3 = ml[3 * NS], m4 = ml[4 * NS], m5 = ml[5 * NS];
+          const double2 m6 = ml[6 * NS], m7 = ml[7 * NS], m8 = ml[8 * NS], m9 = ml[9 * NS], m10 = ml[10 * NS], m11 = ml[11 * NS];
+          double sa0 = m0.x * a0.x, sa1 = m3.x * a0.x, sg0 = m6.x * c0.x, sg1 = m9.x * c0.x;
+          sa0 = fma(m0.y, a0.y, sa0); sa1 = fma(m3.y, a0.y, sa1); sg0 = fma(m6.y, c0.y, sg0); sg1 = fma(m9.y, c0.y, sg1);
+          sa0 = fma(m1.x, a1.x, sa0); sa1 = fma(m4.x, a1.x, sa1); sg0 = fma(m7.x, c1.x, sg0); sg1 = fma(m10.x, c1.x, sg1);
+          sa0 = fma(m1.y, a1.y, sa0); sa1 = fma(m4.y, a1.y, sa1); sg0 = fma(m7.y, c1.y, sg0); sg1 = fma(m10.y, c1.y, sg1);
+          sa0 = fma(m2.x, a2.x, sa0); sa1 = fma(m5.x, a2.x, sa1); sg0 = fma(m8.x, c2.x, sg0); sg1 = fma(m11.x, c2.x, sg1);
+          sa0 = fma(m2.y, a2.y, sa0); sa1 = fma(m5.y, a2.y, sa1); sg0 = fma(m8.y, c2.y, sg0); sg1 = fma(m11.y, c2.y, sg1);
+          y0 = sa0 - sg0; y1 = sa1 - sg1;
+        }
+        if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
+        bar_sync(kBarY, 128);
+        // ---- leaf backward: acceleration of this axis
+        double xt[3];
+        xt[0] = y0; xt[1] = y1;
+        {
+          const double yn0 = dn1(y0), yn1 = dn1(y1);
+          const double a = dai * (b[2] - cv0 * y0 - cv1 * y1 - cv2 * yn0 - cv3 * yn1);
+          xt[2] = hasu ? a : 0.0;
+        }
+        // ---- dynamics rows (p, v) of this stage: Ad x~_{k-1} + Bd u~_{k-1} - x~_k, projected onto the equality
+        double td0, td1, racc[3];
+        {
+          const double pp = up1(xt[0] + apv * xt[1] + bpa * xt[2]), pv = up1(xt[1] + bva * xt[2]);
+          const double zt0 = (notfirst ? pp : 0.0) - xt[0], zt1 = (notfirst ? pv : 0.0) - xt[1];
+          const double v0 = al * zt0 + om * zd[0] + ud[0], v1 = al * zt1 + om * zd[1] + ud[1];
+          zd[0] = bnd[0]; zd[1] = bnd[1];
+          ud[0] = v0 - bnd[0]; ud[1] = v1 - bnd[1];
+          td0 = rhd[0] * (bnd[0] - ud[0]); td1 = rhd[1] * (bnd[1] - ud[1]);
+          racc[0] = -td0; racc[1] = -td1; racc[2] = 0.0;
+        }
+        // ---- box rows
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const double v = al * xt[e] + om * zb[e] + ub[e];
+          const double zn = clampd(v, lo[e], hi[e]);
+          zb[e] = zn; ub[e] = v - zn;
+          racc[e] += rhb[e] * (zn - ub[e]);
+        }
+        // ---- x update, next right-hand side
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          x[e] = al * xt[e] + om * x[e];
+          b[e] = (e < 2 || hasu) ? racc[e] + sd[e] * x[e] - cq[e] : 0.0;
+        }
+        {
+          const double tp = dn1(td0), tv = dn1(td1);
+          if (hasu) { b[0] += tp; b[1] += apv * tp + tv; b[2] += bpa * tp + bva * tv; }
+        }
+      }
+      // ---- park
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const int j = e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc);
+          X_(j, k) = x[e]; Z_(8 + j, k) = zb[e]; U_(8 + j, k) = ub[e]; B_(j, k) = b[e];
+          WSDX_(j, k) = x[e] - ox[e]; WSDY_(8 + j, k) = rhb[e] * (ub[e] - oub[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = cc + 3 * e;
+          Z_(i, k) = zd[e]; U_(i, k) = ud[e]; WSDY_(i, k) = rhd[e] * (ud[e] - oud[e]);
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------------------------------
+      // slack / obstacle warp: variables s_d, s_s (states 6, 7) and sigma_d, sigma_s (inputs 3, 4)
+      // ------------------------------------------------------------------------------------------
+      constexpr int RR = R > 0 ? R : 1;
+      double x[4], zb[4], ub[4], b[4], rhb[4], sd[4], cq[4], lo[4], hi[4], ox[4], oub[4];
+      double zd[2], ud[2], rhd[2], bnd[2], oud[2], dsi[2], esd[2], esdn[2], dgi[2], fs[6], og[3];
+      double zo[RR], uo[RR], rho_[RR], g3[3 * RR], lob[RR], ouo[RR];
+      int sl[RR];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = e < 2 ? 6 + e : 9 + e;
+        x[e] = X_(j, k); zb[e] = Z_(8 + j, k); ub[e] = U_(8 + j, k); b[e] = B_(j, k); rhb[e] = RH_(8 + j, k);
+        sd[e] = SD_(j, k); cq[e] = CQ_(j, k); lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; ox[e] = 0.0; oub[e] = 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        zd[t] = Z_(6 + t, k); ud[t] = U_(6 + t, k); rhd[t] = RH_(6 + t, k); bnd[t] = (k == 0) ? -x0p[6 + t] : 0.0; oud[t] = 0.0;
+        dsi[t] = DSI_(t, k); esd[t] = notfirst ? ESD_(t, k) : 0.0; esdn[t] = ESD_(t, kp); dgi[t] = DGI_(t, k);
+      }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2) og[c2] = OG_(c2, k);
+#pragma unroll
+      for (int o = 0; o < R; ++o) {
+        zo[o] = Z_(NBR + o, k); uo[o] = U_(NBR + o, k); rho_[o] = RH_(NBR + o, k); lob[o] = LO_(o, k); ouo[o] = 0.0;
+        g3[3 * o] = G3_(3 * o, k); g3[3 * o + 1] = G3_(3 * o + 1, k); g3[3 * o + 2] = G3_(3 * o + 2, k);
+        sl[o] = hasu ? SLK_(o, k) : 0;
+      }
+      for (int it = 0; it < niter; ++it) {
+        if (it == niter - 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { ox[e] = x[e]; oub[e] = ub[e]; }
+          oud[0] = ud[0]; oud[1] = ud[1];
+#pragma unroll
+          for (int o = 0; o < R; ++o) ouo[o] = uo[o];
+        }
+        // ---- leaf forward, slack part: eliminate s_{k+1,t} then sigma_{k,t}; what that does to the position rows
+        double r11[2];
+        {
+          double f[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const double bn = dn1(b[t]);
+            const double v = b[2 + t] - esdn[t] * bn;
+            r11[t] = hasu ? v : 0.0;
+            f[t] = dgi[t] * r11[t];
+          }
+          const double rs0 = og[0] - fs[0] * f[0] - fs[3] * f[1], rs1 = og[1] - fs[1] * f[0] - fs[4] * f[1],
+                       rs2 = og[2] - fs[2] * f[0] - fs[5] * f[1];
+          if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); }
+        }
+        bar_sync(kBarAll, 128);
+        bar_sync(kBarY, 128);
+        const double y0 = m.YB[k * 6], y1 = m.YB[k * 6 + 2], y2 = m.YB[k * 6 + 4];
+        // ---- leaf backward: slack inputs, then slack states
+        double xt[4], xp[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const double v = dgi[t] * (r11[t] - fs[3 * t] * y0 - fs[3 * t + 1] * y1 - fs[3 * t + 2] * y2);
+          xt[2 + t] = hasu ? v : 0.0;
+          const double q = up1(xt[2 + t]);
+          xp[t] = notfirst ? q : 0.0;
+          xt[t] = dsi[t] * b[t] - esd[t] * xp[t];
+        }
+        // ---- dynamics rows 6, 7:  sigma~_{k-1,t} - s~_{k,t}
+        double td[2], racc[4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const double zt = xp[t] - xt[t];
+          const double v = al * zt + om * zd[t] + ud[t];
+          zd[t] = bnd[t]; ud[t] = v - bnd[t];
+          td[t] = rhd[t] * (bnd[t] - ud[t]);
+          racc[t] = -td[t]; racc[2 + t] = 0.0;
+        }
+        // ---- box rows
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double v = al * xt[e] + om * zb[e] + ub[e];
+          const double zn = clampd(v, lo[e], hi[e]);
+          zb[e] = zn; ub[e] = v - zn;
+          racc[e] += rhb[e] * (zn - ub[e]);
+        }
+        // ---- obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low
+        og[0] = og[1] = og[2] = 0.0;
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+          const double zt = g3[3 * o] * y0 + g3[3 * o + 1] * y1 + g3[3 * o + 2] * y2 - (sl[o] ? xt[3] : xt[2]);
+          const double v = al * zt + om * zo[o] + uo[o];
+          const double zn = v > lob[o] ? v : lob[o];
+          zo[o] = zn; uo[o] = v - zn;
+          const double t = rho_[o] * (zn - uo[o]);
+          og[0] += g3[3 * o] * t; og[1] += g3[3 * o + 1] * t; og[2] += g3[3 * o + 2] * t;
+          if (sl[o]) racc[3] -= t; else racc[2] -= t;
+        }
+        // ---- x update, next right-hand side
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          x[e] = al * xt[e] + om * x[e];
+          b[e] = (e < 2 || hasu) ? racc[e] + sd[e] * x[e] - cq[e] : 0.0;
+        }
+        {
+          const double t6 = dn1(td[0]), t7 = dn1(td[1]);
+          if (hasu) { b[2] += t6; b[3] += t7; }
+        }
+      }
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = e < 2 ? 6 + e : 9 + e;
+          X_(j, k) = x[e]; Z_(8 + j, k) = zb[e]; U_(8 + j, k) = ub[e]; B_(j, k) = b[e];
+          WSDX_(j, k) = x[e] - ox[e]; WSDY_(8 + j, k) = rhb[e] * (ub[e] - oub[e]);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { Z_(6 + t, k) = zd[t]; U_(6 + t, k) = ud[t]; WSDY_(6 + t, k) = rhd[t] * (ud[t] - oud[t]); }
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2) OG_(c2, k) = og[c2];
+#pragma unroll
+        for (int o = 0; o < R; ++o) { Z_(NBR + o, k) = zo[o]; U_(NBR + o, k) = uo[o]; WSDY_(NBR + o, k) = rho_[o] * (uo[o] - ouo[o]); }
+      }
+    }
+  }
+
+  // osqp_solve for the CTA: warp 0 runs the single-warp phases (factor, info, termination, rho adaptation); its
+  // decisions reach the other warps through *flag.
+  MQ_HD void solve_cta(int warp, volatile int* flag) {
+    status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
+    int iter = 0;
+    bool refactor = true, last_checked = false, approx = false;
+    for (;;) {
+      bool do_info, do_check, do_adapt = false;
+      const bool final_pass = iter >= st.max_iter;
+      if (!final_pass) {
+        if (refactor) {
+          if (warp == 0) {
+            factor(); rows_phase<1>(); rhs_finish();
+            MQ_FOR_STAGES(k) { OG_(0, k) = 0.0; OG_(1, k) = 0.0; OG_(2, k) = 0.0; }   // B_ holds the whole rhs again
+          }
+          refactor = false;
+          __syncthreads();
+        }
+        int nb = st.max_iter;
+        if (st.check_termination) { int c2 = (iter / st.check_termination + 1) * st.check_termination; if (c2 < nb) nb = c2; }
+        if (st.adaptive_rho && st.adaptive_rho_interval) { int c2 = (iter / st.adaptive_rho_interval + 1) * st.adaptive_rho_interval; if (c2 < nb) nb = c2; }
+        burst_cta(nb - iter, warp);
+        __syncthreads();
+        iter = nb;
+        do_check = st.check_termination && (iter % st.check_termination == 0);
+        do_adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+        do_info = do_check || do_adapt;
+        last_checked = do_check;
+      } else if (!approx) {
+        do_info = !last_checked; do_check = !last_checked;
+      } else {
+        do_info = false; do_check = true;
+      }
+      if (warp == 0) {
+        if (do_info) update_info(iter);
+        const bool done = do_check && check_termination(approx);
+        int f = done ? 1 : 0;
+        if (!done && !final_pass && do_adapt && adapt_rho()) f |= 2;
+        if (lane == 0) *flag = f;
+      }
+      __syncthreads();
+      const int f = *flag;
+      __syncthreads();
+      if (f & 1) break;
+      if (final_pass) {
+        if (approx) { status = kMaxIter; break; }
+        approx = true;
+        continue;
+      }
+      if (f & 2) refactor = true;
+    }
+  }
+  MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag) {
+    x0p = bt.x0 + (size_t)b * 8;
+    if (warp == 0) load_and_scale(bt, b);
+    __syncthreads();
+    solve_cta(warp, flag);
+    if (warp == 0) store(bt, b);
+    __syncthreads();
+  }
+#endif
+
   // ---- osqp_solve (osqp.h:78) ---------------------------------------------------------------------
   // Written as one loop with a single call site per phase (factor, burst, update_info, check_termination,
   // adapt_rho) so that everything inlines into the kernel once: shared-memory addresses then fold to
@@ -1270,7 +1804,7 @@ template <int NST, int RT> struct Qp : DimsT<NST, RT> {
   MQ_HD Qp(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_)
       : Dm(shape.NS, shape.R), sh(shape), st(set) {
     lane = lane_;
-    map_memory(m, smem, ws, NS, R, kFast);
+    map_memory(m, smem, ws, NS, R, QMODE);
     pd = bt.pd; slack = bt.slack;
   }
   MQ_HD void run(const Batch& bt, int b) {

@@ -81,14 +81,42 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
   }
 }
 
+// CTA kernel: persistent, one 4-warp CTA per QP at a time (mode 2 of mpcqp_core.cuh), two CTAs per SM.
+template <int RT>
+__global__ void __launch_bounds__(128, 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+                                                                 const __grid_constant__ Batch bt, int ws_stride, int* counter) {
+  extern __shared__ double smem[];
+  __shared__ int s_next, s_flag;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Qp<30, RT, kModeCta> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+    __syncthreads();
+    const int b = s_next;
+    __syncthreads();
+    if (b >= bt.B) break;
+    qp.run_cta(bt, b, warp, &s_flag);
+  }
+}
+
 typedef void (*SolveKernel)(const Shape, const Settings, const Batch, int, int*);
 // Fast-path instantiations (compile-time dims, register-resident iterates); anything else runs the generic kernel.
 #ifndef MPCQP_FAST_R_LIST
 #define MPCQP_FAST_R_LIST X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #endif
-static SolveKernel pick_kernel(int NS, int R, bool* fast) {
-  *fast = true;
-  if (NS == 30) {
+// want: 2 = CTA kernel if available, 1 = warp-fast kernel if available, 0 = generic.  *mode returns what was picked.
+static SolveKernel pick_kernel(int NS, int R, int want, int* mode) {
+  if (NS == 30 && want == kModeCta) {
+    *mode = kModeCta;
+    switch (R) {
+#define X(r) case r: return mpcqp_solve_cta_kernel<r>;
+      MPCQP_FAST_R_LIST
+#undef X
+      default: break;
+    }
+  }
+  if (NS == 30 && want >= kModeWarp) {
+    *mode = kModeWarp;
     switch (R) {
 #define X(r) case r: return mpcqp_solve_kernel<30, r>;
       MPCQP_FAST_R_LIST
@@ -96,7 +124,7 @@ static SolveKernel pick_kernel(int NS, int R, bool* fast) {
       default: break;
     }
   }
-  *fast = false;
+  *mode = kModeGeneric;
   return mpcqp_solve_kernel<0, 0>;
 }
 
@@ -247,30 +275,32 @@ static int shape_from_params(mpcqp_engine* e, const mpcqp_mpc_params* p, int R, 
 
 // Launch the solve kernel on structured data already on the device.
 static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Batch bt) {
-  bool fast = false;
-  SolveKernel kern = pick_kernel(sh.NS, sh.R, &fast);
-  if (e->force_generic) { fast = false; kern = mpcqp_solve_kernel<0, 0>; }
-  const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, fast) * sizeof(double);
+  int mode = kModeGeneric;
+  // force_generic: 0 = best available (CTA kernel), 1 = generic kernel, 2 = warp-fast kernel
+  const int want = e->force_generic == 1 ? kModeGeneric : (e->force_generic == 2 ? kModeWarp : kModeCta);
+  SolveKernel kern = pick_kernel(sh.NS, sh.R, want, &mode);
+  const int threads = mode == kModeCta ? 128 : 32;
+  const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, mode) * sizeof(double);
   if ((long long)smem > (long long)e->max_smem_optin) {
     e->err = "problem does not fit shared memory: horizon/num_obs too large (" + std::to_string(smem) + " B needed)";
     return MPCQP_ERR_ARG;
   }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) { e->err = "solve kernel cannot be resident"; return MPCQP_ERR_CUDA; }
   long long grid = (long long)e->num_sms * occ;
   if (grid > bt.B) grid = bt.B;
-  const int wsd = ws_doubles(sh.NS, sh.R, fast);
+  const int wsd = ws_doubles(sh.NS, sh.R, mode);
   CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
   CK(e->counter.need(sizeof(int)));
   bt.ws = e->ws.as<double>();
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
   CK(cudaEventRecord(e->evs, e->stream));
-  kern<<<(unsigned)grid, 32, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+  kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
   CK(cudaGetLastError());
   e->last_launches += 1;
-  e->last_fast = fast ? 1 : 0;
+  e->last_fast = mode;
   return MPCQP_OK;
 }
 

@@ -136,11 +136,15 @@ class Engine:
 
     @property
     def last_path(self) -> str:
-        """'fast' (register-resident kernel, compile-time dims) or 'generic' (shared-memory kernel)."""
-        return "fast" if int(self.lib.mpcqp_engine_last_path(self.h)) == 1 else "generic"
+        """'cta' (4-warp CTA per QP, PCR solve), 'fast' (one warp per QP, register-resident) or 'generic'
+        (one warp per QP, shared-memory kernel for any shape)."""
+        return {2: "cta", 1: "fast"}.get(int(self.lib.mpcqp_engine_last_path(self.h)), "generic")
 
-    def force_generic(self, on: bool = True):
-        self._check(self.lib.mpcqp_engine_force_generic(self.h, C.c_int(1 if on else 0)))
+    def force_generic(self, on=True):
+        """True / 1 / 'generic': generic kernel; 2 / 'fast': one-warp register kernel; False / 0: default dispatch."""
+        names = {"generic": 1, "fast": 2, "cta": 0}
+        code = names[on] if isinstance(on, str) else (1 if on is True else int(on))
+        self._check(self.lib.mpcqp_engine_force_generic(self.h, C.c_int(code)))
 
     def fp64_fma_peak_tflops(self) -> float:
         tf = C.c_double()

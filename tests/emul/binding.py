@@ -50,7 +50,7 @@ def structured_inputs(mb):
                 low=np.ascontiguousarray(low), warm_x=np.ascontiguousarray(mb.warm_x))
 
 
-def solve(mb, want_y=True, **settings):
+def solve(mb, want_y=True, linsys=0, **settings):
     build()
     lib = C.CDLL(SO)
     s = structured_inputs(mb)
@@ -65,10 +65,12 @@ def solve(mb, want_y=True, **settings):
                pri_res=np.zeros(B), dua_res=np.zeros(B))
     D = C.POINTER(C.c_double); I = C.POINTER(C.c_int)
     def dp(a): return a.ctypes.data_as(D) if a is not None else None
-    lib.emul_solve_batch(C.c_int(s["NS"]), C.c_int(s["R"]), C.c_int(B), C.c_double(s["a_pv"]), C.c_double(s["b_pa"]),
+    rc = lib.emul_solve_batch(C.c_int(linsys), C.c_int(s["NS"]), C.c_int(s["R"]), C.c_int(B), C.c_double(s["a_pv"]), C.c_double(s["b_pa"]),
                          C.c_double(s["b_va"]), dp(s["blo"]), dp(s["bhi"]), dp(sdv), siv.ctypes.data_as(I),
                          dp(np.ascontiguousarray(s["pd"])), s["slack"].ctypes.data_as(C.POINTER(C.c_ubyte)),
                          dp(s["q"]), dp(s["x0"]), dp(s["g"]), dp(s["low"]), dp(s["warm_x"]),
                          dp(out["x"]), dp(out["y"]), out["status"].ctypes.data_as(I), out["iter"].ctypes.data_as(I),
                          out["rho_updates"].ctypes.data_as(I), dp(out["obj"]), dp(out["pri_res"]), dp(out["dua_res"]))
+    if rc != 0:
+        raise RuntimeError(f"emul_solve_batch(linsys={linsys}) -> {rc}")
     return out

@@ -6,7 +6,7 @@
 #include <vector>
 #include <cstring>
 
-extern "C" int emul_solve_batch(int NS, int R, int B, double a_pv, double b_pa, double b_va, const double* blo,
+extern "C" int emul_solve_batch(int linsys, int NS, int R, int B, double a_pv, double b_pa, double b_va, const double* blo,
                                 const double* bhi, const double* settings_d, const int* settings_i,
                                 const double* pd, const unsigned char* slack, const double* q, const double* x0,
                                 const double* g, const double* low, const double* warm_x, double* x, double* y,
@@ -26,8 +26,19 @@ extern "C" int emul_solve_batch(int NS, int R, int B, double a_pv, double b_pa, 
   bt.pd = pd; bt.slack = slack; bt.q = q; bt.x0 = x0; bt.g = g; bt.low = low; bt.warm_x = warm_x;
   bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates; bt.obj = obj;
   bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B;
-  std::vector<double> sm((size_t)smem_doubles(NS, R, false)), ws((size_t)ws_doubles(NS, R, false));
-  Qp<0, 0> qp(sm.data(), sh, st, bt, ws.data(), 0);
-  for (int b = 0; b < B; ++b) qp.run(bt, b);
-  return 0;
+  if (linsys == 0) {
+    std::vector<double> sm((size_t)smem_doubles(NS, R, kModeGeneric)), ws((size_t)ws_doubles(NS, R, kModeGeneric));
+    Qp<0, 0> qp(sm.data(), sh, st, bt, ws.data(), 0);
+    for (int b = 0; b < B; ++b) qp.run(bt, b);
+    return 0;
+  }
+  // linsys 1: the CTA path's linear algebra (PCR factor + plain-loop PCR solve) with the generic iteration around it
+  if (NS != 30) return -1;
+  std::vector<double> sm((size_t)smem_doubles(NS, R, kModeCta)), ws((size_t)ws_doubles(NS, R, kModeCta));
+  switch (R) {
+#define X(r) case r: { Qp<30, r, kModeCta> qp(sm.data(), sh, st, bt, ws.data(), 0); for (int b = 0; b < B; ++b) qp.run(bt, b); return 0; }
+    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+    default: return -2;
+  }
 }

@@ -25,3 +25,16 @@ def test_emulated_kernel_matches_reference_golden(name):
     assert (e["rho_updates"] == g[name + "_rho_updates"]).all()
     assert rel_inf(e["x"], g[name + "_x"]).max() < TOL
     assert np.abs((e["obj"] - g[name + "_obj"]) / g[name + "_obj"]).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["snapshot", "static4", "static0", "static8"])
+def test_emulated_pcr_linear_algebra_matches_reference_golden(name):
+    """The CTA kernel's linear algebra — leaf elimination + block parallel cyclic reduction (pcr_factor, with the
+    plain-loop pcr_solve_ref standing in for the three axis warps) — inside the same ADMM iteration."""
+    g = np.load(GOLD)
+    e = EM.solve(cases()[name], want_y=False, linsys=1)
+    assert (e["status"] == g[name + "_status"]).all()
+    assert (e["iter"] == g[name + "_iter"]).all()
+    assert (e["rho_updates"] == g[name + "_rho_updates"]).all()
+    assert rel_inf(e["x"], g[name + "_x"]).max() < TOL
+    assert np.abs((e["obj"] - g[name + "_obj"]) / g[name + "_obj"]).max() < TOL

@@ -34,15 +34,17 @@ def test_gpu_matches_reference_golden(eng, name):
     assert np.abs((out["obj"] - g[name + "_obj"]) / g[name + "_obj"]).max() < TOL
 
 
+@pytest.mark.parametrize("path", ["generic", "fast"])
 @pytest.mark.parametrize("name", ["snapshot", "static4", "static0", "static8"])
-def test_generic_kernel_matches_reference_golden(eng, name):
-    """The shared-memory kernel (used for horizons/obstacle counts without a compiled fast path) on the same
-    golden cases; the default dispatch above runs them on the register-resident fast path."""
+def test_other_kernels_match_reference_golden(eng, name, path):
+    """The one-warp kernels — generic shared-memory (used for horizons / obstacle counts without a compiled
+    specialisation) and register-resident — on the same golden cases; the default dispatch above runs them on the
+    CTA kernel."""
     g = np.load(GOLD)
-    eng.force_generic(True)
+    eng.force_generic(path)
     try:
         out = eng.solve_mpc_batch(cases()[name])
-        assert eng.last_path == "generic"
+        assert eng.last_path == path
     finally:
         eng.force_generic(False)
     assert (out["status"] == g[name + "_status"]).all()
@@ -53,7 +55,7 @@ def test_generic_kernel_matches_reference_golden(eng, name):
 
 def test_dispatch_uses_fast_path_for_default_shape(eng):
     eng.solve_mpc_batch(W.static_batch(4, num_obs=4))
-    assert eng.last_path == "fast"
+    assert eng.last_path == "cta"
     eng.solve_mpc_batch(W.static_batch(4, num_obs=2, params=W.MpcParams(horizon=60)))
     assert eng.last_path == "generic"
 
