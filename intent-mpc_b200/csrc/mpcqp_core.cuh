@@ -100,39 +100,50 @@ struct Mem {
   double *RH, *SD, *CQ, *G3, *LO, *W;                    // read-only per iteration + work vector
   double *SI, *GG, *DSI, *ESD, *DGI, *FS, *DAI, *CV, *PK; // factor (+ 72-double parking area)
   double *E, *D, *DY, *DX;                               // always in global scratch
-  double *PCR, *RA, *RS, *YB;                            // mode 2, shared: PCR matrices, r ping-pong, slack part of r, y
-  double *PD, *PL, *PI, *OG;                             // mode 2, global: PCR factor workspace (D, L x2, D^-1); parked obstacle part of the rhs
+  double *PCR, *WK, *RA, *RS, *YB;                          // mode 2, shared: PCR matrices, r ping-pong, slack part of r, y
+  double *PD, *PL, *PI, *OG, *OX, *OU;                           // mode 2, global: PCR factor workspace (D, L x2, D^-1); parked obstacle part of the rhs
 };
 MQ_HHD int hot_slots(int R, int mode) {
-  if (mode == kModeCta) return (NBR + R) + NV + NV + 3 * R + R;
   return (NBR + R) + NV + NV + 3 * R + R + (mode == kModeWarp ? 6 : NV) + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12;
 }
 MQ_HHD int iter_slots(int R) { return NV + 2 * (NBR + R) + NV + 8 + 3; }
+// mode 2: the "cold block" (scalings, rho vector, scaled cost, obstacle rows, parked iterates) is one contiguous run of
+// slots so that the setup phase can build it in shared memory (in the not-yet-used PCR region) and copy it out once.
+MQ_HHD int cold_slots(int R) { return 2 * (NBR + R) + 2 * NV + (NBR + R) + NV + NV + 3 * R + R + iter_slots(R); }
+constexpr int kWorkSlots = 108;             // PCR factor workspace: D / D^-1, L, next L (36 slots each); r / y exchange buffers alias it
 MQ_HHD int smem_doubles(int NS, int R, int mode) {
-  if (mode == kModeCta) return kPcrDoubles + 2 * 6 * NS + 4 * NS + 6 * NS + hot_slots(R, mode) * NS;
+  if (mode == kModeCta) return kPcrDoubles + kWorkSlots * NS;
   return (hot_slots(R, mode) + (mode == kModeWarp ? 0 : iter_slots(R))) * NS + 72;
 }
 MQ_HHD int ws_doubles(int NS, int R, int mode) {
   const int base = 2 * (NBR + R) + 2 * NV;
-  if (mode == kModeCta) return (base + iter_slots(R) + NV + 36 + 36 + 27 + 36 + 72 + 36 + 3) * NS;
+  if (mode == kModeCta) return (cold_slots(R) + NV + 36 + 36 + 27 + 36 + 72 + 36 + 3 + NV + (NBR + R)) * NS;
   return (base + (mode == kModeWarp ? iter_slots(R) : 0)) * NS;
+}
+// cold block at `g` (same order wherever it lives)
+MQ_HHD double* map_cold(Mem& m, double* g, int NS, int R) {
+  const int MK = NBR + R;
+  m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
+  m.RH = g; g += MK * NS; m.SD = g; g += NV * NS; m.CQ = g; g += NV * NS; m.G3 = g; g += 3 * R * NS; m.LO = g; g += R * NS;
+  m.X = g; g += NV * NS; m.Z = g; g += MK * NS; m.U = g; g += MK * NS; m.B = g; g += NV * NS; m.TD = g; g += 8 * NS; m.MA = g; g += 3 * NS;
+  return g;
 }
 MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) {
   const int MK = NBR + R;
   double* p = sm;
   double* g = ws;
-  m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
   if (mode == kModeCta) {
-    m.PCR = p; p += kPcrDoubles; m.RA = p; p += 2 * 6 * NS; m.RS = p; p += 4 * NS; m.YB = p; p += 6 * NS;
-    m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
-    m.X = g; g += NV * NS; m.Z = g; g += MK * NS; m.U = g; g += MK * NS; m.B = g; g += NV * NS; m.TD = g; g += 8 * NS; m.MA = g; g += 3 * NS;
+    m.PCR = p; p += kPcrDoubles;
+    m.WK = p; m.RA = p; m.RS = p + 2 * 6 * NS; m.YB = p + 2 * 6 * NS + 4 * NS;
+    g = map_cold(m, g, NS, R);
     m.W = g; g += NV * NS; m.SI = g; g += 36 * NS; m.GG = g; g += 36 * NS; m.DSI = g; g += 2 * NS; m.ESD = g; g += 2 * NS;
     m.DGI = g; g += 2 * NS; m.FS = g; g += 6 * NS; m.DAI = g; g += 3 * NS; m.CV = g; g += 12 * NS; m.PK = nullptr;
-    m.PD = g; g += 36 * NS; m.PL = g; g += 72 * NS; m.PI = g; g += 36 * NS; m.OG = g; g += 3 * NS;
+    m.PD = g; g += 36 * NS; m.PL = g; g += 72 * NS; m.PI = g; g += 36 * NS; m.OG = g; g += 3 * NS; m.OX = g; g += NV * NS; m.OU = g; g += MK * NS;
     return;
   }
+  m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
   const bool fast = mode == kModeWarp;
-  m.PCR = m.RA = m.RS = m.YB = m.PD = m.PL = m.PI = m.OG = nullptr;
+  m.PCR = m.WK = m.RA = m.RS = m.YB = m.PD = m.PL = m.PI = m.OG = m.OX = m.OU = nullptr;
   m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
   m.W = p; p += (fast ? 6 : NV) * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
   m.DGI = p; p += 2 * NS; m.FS = p; p += 6 * NS; m.DAI = p; p += 3 * NS; m.CV = p; p += 12 * NS; m.PK = p; p += 72;
@@ -226,6 +237,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
 #define PL_(buf, e, k) m.PL[((buf) * 36 + (e)) * NS + (k)]
 #define PI_(e, k) m.PI[(e) * NS + (k)]
 #define OG_(c, k) m.OG[(c) * NS + (k)]
+#define OX_(j, k) m.OX[(j) * NS + (k)]
+#define OU_(i, k) m.OU[(i) * NS + (k)]
 
   MQ_HD int nrows(int k) const { return k < N ? MK : 16; }
   // position of row i of stage k in the reference's constraint ordering (MP.cpp:989-1071)
@@ -521,7 +534,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       }
     }
     MQ_SYNC();
+#if MQ_DEV
+    if constexpr (kCta) return;                 // the whole CTA continues with pcr_factor_cta()
+#else
     if constexpr (kCta) { pcr_factor(); return; }
+#endif
     // pass 3: twisted recursion.  chain 0 walks k = 0..mid-1 upward, chain 1 walks k = N..mid+1 downward;
     // both run the same instruction stream on two lanes.  Their Schur corrections onto the middle block
     // are parked in the (idle during factorisation) B/W/TD/MA scratch columns mid and mid+1.
@@ -1411,7 +1428,185 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   static MQ_HD double clampd(double v, double lo, double hi) { double z = v > lo ? v : lo; return z < hi ? z : hi; }
   static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3;
 
-  MQ_HD void burst_cta(int niter, int warp) {
+  // PCR factorisation by the whole CTA (same recurrences as pcr_factor() above, which stays as the host-emulated
+  // specification).  Work split: axis warp w owns rows 2w, 2w+1 (axis-major) of every 6x6 product of its stage and
+  // keeps its two rows of D in registers across levels; warp 3 inverts the D blocks (lane = stage) while the axis
+  // warps wait.  Workspace in shared memory, [entry][stage]: DI (D, then D^-1 in place), LC (current L), LN (next L).
+  MQ_HD void pcr_factor_cta(const int warp) {
+    const int k = lane < NS ? lane : NS - 1;
+    const bool live = lane < NS;
+    double* DI = m.WK; double* LC = m.WK + 36 * NS; double* LN = m.WK + 72 * NS;
+    __syncthreads();                                      // warp 0 has written T (SI_) and the couplings (GG_)
+    // initial D = T (leaf elimination, (p,v)-major) and L = coupling of stages k-1, k, permuted to axis-major
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int e = warp * 9 + q, a = e / 6, b2 = e - 6 * a, oa = pcr_old(a), ob = pcr_old(b2);
+      double l = 0.0;
+      if (k > 0 && (oa % 3) == (ob % 3)) l = GG_(4 * (oa % 3) + (oa / 3) * 2 + (ob / 3), k - 1);
+      if (live) { DI[e * NS + k] = SI_(oa * 6 + ob, k); LC[e * NS + k] = l; }
+    }
+    double dr[12];
+    if (warp < 3) {
+#pragma unroll
+      for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dr[ar * 6 + j] = SI_(pcr_old(2 * warp + ar) * 6 + pcr_old(j), k);
+    }
+    for (int l = 0, s = 1; l < kPcrLevels; ++l, s <<= 1) {
+      const bool last = l == kPcrLevels - 1;
+      __syncthreads();                                    // DI = D of every stage, LC = L
+      if (warp == 3) {
+        double S[36];
+#pragma unroll
+        for (int e = 0; e < 36; ++e) S[e] = DI[e * NS + k];
+        inv6(S);
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 36; ++e) DI[e * NS + k] = S[e];
+        }
+      }
+      __syncthreads();                                    // DI = D^-1
+      const bool hm = k - s >= 0, hp = k + s <= N, hmm = k - 2 * s >= 0;
+      const int km = hm ? k - s : k, kp = hp ? k + s : k;
+      double2* const P2 = reinterpret_cast<double2*>(m.PCR) + l * (kPcrLevelDoubles / 2) + (warp * 12) * NS + k;
+      if (warp < 3) {
+        if (!last) {
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar) {
+            const int a = 2 * warp + ar;
+            double al_[6], ga_[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sa = 0.0, sg = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) {
+                sa = fma(LC[(a * 6 + t) * NS + k], DI[(t * 6 + j) * NS + km], sa);
+                sg = fma(LC[(t * 6 + a) * NS + kp], DI[(t * 6 + j) * NS + kp], sg);
+              }
+              al_[j] = hm ? sa : 0.0; ga_[j] = hp ? sg : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sd = dr[ar * 6 + j], sl = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) {
+                sd = fma(-al_[t], LC[(j * 6 + t) * NS + k], sd);
+                sd = fma(-ga_[t], LC[(t * 6 + j) * NS + kp], sd);
+                sl = fma(-al_[t], LC[(t * 6 + j) * NS + km], sl);
+              }
+              dr[ar * 6 + j] = sd;
+              if (live) LN[(a * 6 + j) * NS + k] = hmm ? sl : 0.0;
+            }
+            if (live) {
+#pragma unroll
+              for (int bp = 0; bp < 3; ++bp) {
+                P2[(ar * 3 + bp) * NS] = make_double2(al_[2 * bp], al_[2 * bp + 1]);
+                P2[(6 + ar * 3 + bp) * NS] = make_double2(ga_[2 * bp], ga_[2 * bp + 1]);
+              }
+            }
+          }
+        } else {
+          // single partner: M = alpha (partner k-s) or gamma (partner k+s);  D' = D - M (.)'
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar) {
+            const int a = 2 * warp + ar;
+            double mr[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sa = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t)
+                sa = fma(hm ? LC[(a * 6 + t) * NS + k] : LC[(t * 6 + a) * NS + kp], DI[(t * 6 + j) * NS + (hm ? km : kp)], sa);
+              mr[j] = (hm || hp) ? sa : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sd = dr[ar * 6 + j];
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sd = fma(-mr[t], hm ? LC[(j * 6 + t) * NS + k] : LC[(t * 6 + j) * NS + kp], sd);
+              dr[ar * 6 + j] = sd;
+              if (live) LN[(a * 6 + j) * NS + k] = mr[j];          // M, needed whole for D'^-1 M
+            }
+          }
+        }
+      }
+      __syncthreads();                                    // everyone is done with D^-1 and L of this level
+      if (warp < 3 && live) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) DI[((2 * warp) * 6 + e) * NS + k] = dr[e];
+      }
+      double* t_ = LC; LC = LN; LN = t_;
+    }
+    // D' of the last level is in DI, M in LC: invert, then rows of D'^-1 and D'^-1 M go to level 4 of the PCR store
+    __syncthreads();
+    if (warp == 3) {
+      double S[36];
+#pragma unroll
+      for (int e = 0; e < 36; ++e) S[e] = DI[e * NS + k];
+      inv6(S);
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < 36; ++e) DI[e * NS + k] = S[e];
+      }
+    }
+    __syncthreads();
+    if (warp < 3 && live) {
+      double2* const P2 = reinterpret_cast<double2*>(m.PCR) + (kPcrLevels - 1) * (kPcrLevelDoubles / 2) + (warp * 12) * NS + k;
+#pragma unroll
+      for (int ar = 0; ar < 2; ++ar) {
+        const int a = 2 * warp + ar;
+        double di[6], dm[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) di[j] = DI[(a * 6 + j) * NS + k];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          double sm = 0.0;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) sm = fma(di[t], LC[(t * 6 + j) * NS + k], sm);
+          dm[j] = sm;
+        }
+#pragma unroll
+        for (int bp = 0; bp < 3; ++bp) {
+          P2[(ar * 3 + bp) * NS] = make_double2(di[2 * bp], di[2 * bp + 1]);
+          P2[(6 + ar * 3 + bp) * NS] = make_double2(dm[2 * bp], dm[2 * bp + 1]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // CTA-wide reduction of NM maxima and NS_ sums; every thread ends with the same values (fixed combination order).
+  template <int NM, int NS_> MQ_HD void cta_reduce(double (&mx)[NM], double (&sm)[NS_], int warp) {
+    static_assert(4 * (NM + NS_) <= 6 * NST, "reduction scratch is the y buffer");
+#pragma unroll
+    for (int e = 0; e < NM; ++e) mx[e] = wmax(mx[e]);
+#pragma unroll
+    for (int e = 0; e < NS_; ++e) sm[e] = wsum(sm[e]);
+    double* red = m.YB;
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < NM; ++e) red[warp * (NM + NS_) + e] = mx[e];
+#pragma unroll
+      for (int e = 0; e < NS_; ++e) red[warp * (NM + NS_) + NM + e] = sm[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < NM; ++e) mx[e] = fmax(fmax(red[e], red[(NM + NS_) + e]), fmax(red[2 * (NM + NS_) + e], red[3 * (NM + NS_) + e]));
+#pragma unroll
+    for (int e = 0; e < NS_; ++e) sm[e] = (red[NM + e] + red[(NM + NS_) + NM + e]) + (red[2 * (NM + NS_) + NM + e] + red[3 * (NM + NS_) + NM + e]);
+    __syncthreads();
+  }
+
+  // The whole osqp_solve of one QP for one role (AX: axis warp `warp` in 0..2; !AX: slack/obstacle warp).  The
+  // iterates stay in registers from the first iteration to the last; residuals, termination and the rho estimate are
+  // evaluated from registers by all four warps (update_info / check_termination / compute_rho_estimate of auxil.h);
+  // only a rho change (re-factorisation) or a suspected infeasibility certificate parks the state and runs the
+  // single-warp array code on warp 0.
+  template <bool AX> MQ_HD void solve_role(const int warp, volatile int* flag) {
+    constexpr int NVR = AX ? 3 : 4;
+    constexpr int RO = AX ? 0 : R;
+    constexpr int RR = RO > 0 ? RO : 1;
+    const int cc = warp;
     const int k = lane < NS ? lane : NS - 1;            // ghost lanes shadow the last stage, never write
     const bool live = lane < NS, hasu = lane < N, notfirst = lane > 0 && live;
     const int kp = k < N ? k + 1 : k, km = k > 0 ? k - 1 : 0;
@@ -1419,270 +1614,363 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     double2* const RA2 = reinterpret_cast<double2*>(m.RA);      // [2][NS][3] pairs
     double2* const RS2 = reinterpret_cast<double2*>(m.RS);      // [NS][2] pairs: (x, y), (z, -)
     double2* const YB2 = reinterpret_cast<double2*>(m.YB);      // [NS][3] pairs
-    if (warp < 3) {
-      // ------------------------------------------------------------------------------------------
-      // axis warp
-      // ------------------------------------------------------------------------------------------
-      const int cc = warp;
-      double x[3], zb[3], ub[3], b[3], rhb[3], sd[3], cq[3], lo[3], hi[3], ox[3], oub[3];
-      double zd[2], ud[2], rhd[2], bnd[2], oud[2];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        const int j = e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc);
-        x[e] = X_(j, k); zb[e] = Z_(8 + j, k); ub[e] = U_(8 + j, k); b[e] = B_(j, k); rhb[e] = RH_(8 + j, k);
-        sd[e] = SD_(j, k); cq[e] = CQ_(j, k); lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; ox[e] = 0.0; oub[e] = 0.0;
-      }
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int i = cc + 3 * e;
-        zd[e] = Z_(i, k); ud[e] = U_(i, k); rhd[e] = RH_(i, k); bnd[e] = (k == 0) ? -x0p[i] : 0.0; oud[e] = 0.0;
-      }
-      const double dai = DAI_(cc, k), cv0 = CV_(4 * cc, k), cv1 = CV_(4 * cc + 1, k), cv2 = CV_(4 * cc + 2, k), cv3 = CV_(4 * cc + 3, k);
-      const double cv2m = notfirst ? CV_(4 * cc + 2, km) : 0.0, cv3m = notfirst ? CV_(4 * cc + 3, km) : 0.0;
-      const double2* const M = reinterpret_cast<const double2*>(m.PCR) + (cc * 12) * NS + k;
-      const int kq = k >= 16 ? k - 16 : (k + 16 <= N ? k + 16 : k);
+    const double2* const M = reinterpret_cast<const double2*>(m.PCR) + ((AX ? cc : 0) * 12) * NS + k;
+    const int kq = k >= 16 ? k - 16 : (k + 16 <= N ? k + 16 : k);
+    auto vj = [&](int e) { return AX ? (e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc)) : (e < 2 ? 6 + e : 9 + e); };
+    auto di = [&](int t) { return AX ? cc + 3 * t : 6 + t; };
 
-      for (int it = 0; it < niter; ++it) {
-        if (it == niter - 1) {
+    constexpr bool kObsRegs = R <= 4;                 // obstacle gradients / bounds in registers, else re-read from shared memory
+    double x[NVR], zb[NVR], ub[NVR], b[NVR], rhb[NVR], sd[NVR], cq[NVR], lo[AX ? 3 : 1], hi[AX ? 3 : 1];
+    double zd[2], ud[2], rhd[2], bnd[2];
+    // box bounds: the axis role's variable indices depend on the warp (registers); the slack role's are compile-time
+    auto blo = [&](int e) { if constexpr (AX) return lo[e]; else return sh.blo[e < 2 ? 6 + e : 9 + e]; };
+    auto bhi = [&](int e) { if constexpr (AX) return hi[e]; else return sh.bhi[e < 2 ? 6 + e : 9 + e]; };
+    double dai = 0, cv0 = 0, cv1 = 0, cv2 = 0, cv3 = 0, cv2m = 0, cv3m = 0;                 // AX
+    double dsi[2], esd[2], esdn[2], dgi[2], fs[6], og[3];                                       // !AX
+    double zo[RR], uo[RR], rho_[RR], g3r[kObsRegs ? 3 * RR : 1], lobr[kObsRegs ? RR : 1];
+    int sl[RR];
+    auto g3 = [&](int e) { if constexpr (kObsRegs) return g3r[e]; else return G3_(e, k); };
+    auto lob = [&](int o) { if constexpr (kObsRegs) return lobr[o]; else return LO_(o, k); };
+
+    auto load = [&]() {
 #pragma unroll
-          for (int e = 0; e < 3; ++e) { ox[e] = x[e]; oub[e] = ub[e]; }
-          oud[0] = ud[0]; oud[1] = ud[1];
-        }
-        // ---- leaf forward (this axis' acceleration): reduced rhs rows (p, v); the slack/obstacle part comes from warp 3
-        double r0, r1;
-        {
-          const double ma = dai * b[2];
-          const double mm = up1(ma);
-          r0 = b[0] - cv0 * ma; r1 = b[1] - cv1 * ma;
-          r0 -= cv2m * mm; r1 -= cv3m * mm;             // cv2m = cv3m = 0 on stage 0
-        }
-        if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
-        bar_sync(kBarAll, 128);
-        r0 += m.RS[k * 4 + cc];
-        // ---- PCR levels 0..3
-#pragma unroll
-        for (int l = 0; l < kPcrLevels - 1; ++l) {
-          const int s = 1 << l, cur = l & 1;
-          const int kmm = k - s >= 0 ? k - s : k, kpp = k + s <= N ? k + s : k;
-          const double2* ra = RA2 + cur * 3 * NS;
-          double2 a0 = ra[kmm * 3], a1 = ra[kmm * 3 + 1], a2 = ra[kmm * 3 + 2];
-          double2 c0 = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
-          if (l == 0) {
-            const double2 sm0 = RS2[kmm * 2], sm1 = RS2[kmm * 2 + 1], sp0 = RS2[kpp * 2], sp1 = RS2[kpp * 2 + 1];
-            a0.x += sm0.x; a1.x += sm0.y; a2.x += sm1.x;
-            c0.x += sp0.x; c1.x += sp0.y; c2.x += sp1.x;
-          }
-          const double2* ml = M + l * (kPcrLevelDoubles / 2);
-          const double2 m0 = ml[0], m1 = ml[NS], m2 = ml[2 * NS], m3 = ml[3 * NS], m4 = ml[4 * NS], m5 = ml[5 * NS];
-          const double2 m6 = ml[6 * NS], m7 = ml[7 * NS], m8 = ml[8 * NS], m9 = ml[9 * NS], m10 = ml[10 * NS], m11 = ml[11 * NS];
-          double sa0 = m0.x * a0.x, sa1 = m3.x * a0.x, sg0 = m6.x * c0.x, sg1 = m9.x * c0.x;
-          sa0 = fma(m0.y, a0.y, sa0); sa1 = fma(m3.y, a0.y, sa1); sg0 = fma(m6.y, c0.y, sg0); sg1 = fma(m9.y, c0.y, sg1);
-          sa0 = fma(m1.x, a1.x, sa0); sa1 = fma(m4.x, a1.x, sa1); sg0 = fma(m7.x, c1.x, sg0); sg1 = fma(m10.x, c1.x, sg1);
-          sa0 = fma(m1.y, a1.y, sa0); sa1 = fma(m4.y, a1.y, sa1); sg0 = fma(m7.y, c1.y, sg0); sg1 = fma(m10.y, c1.y, sg1);
-          sa0 = fma(m2.x, a2.x, sa0); sa1 = fma(m5.x, a2.x, sa1); sg0 = fma(m8.x, c2.x, sg0); sg1 = fma(m11.x, c2.x, sg1);
-          sa0 = fma(m2.y, a2.y, sa0); sa1 = fma(m5.y, a2.y, sa1); sg0 = fma(m8.y, c2.y, sg0); sg1 = fma(m11.y, c2.y, sg1);
-          r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
-          if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
-          bar_sync(kBarAxis, 96);
-        }
-        // ---- last level fused with D'^-1:  y = D'^-1 r_k - (D'^-1 M) r_partner   (buffer 0 holds the level-4 input)
-        double y0, y1;
-        {
-          const double2* ra = RA2;
-          const double2 a0 = ra[k * 3], a1 = ra[k * 3 + 1], a2 = ra[k * 3 + 2];
-          const double2 c0 = ra[kq * 3], c1 = ra[kq * 3 + 1], c2 = ra[kq * 3 + 2];
-          const double2* ml = M + (kPcrLevels - 1) * (kPcrLevelDoubles / 2);
-          const double2 m0 = ml[0], m1 = ml[NS], m2 = ml[2 * NS], m3 = ml[3 * NS], m4 = ml[4 * NS], m5 = ml[5 * NS];
-          const double2 m6 = ml[6 * NS], m7 = ml[7 * NS], m8 = ml[8 * NS], m9 = ml[9 * NS], m10 = ml[10 * NS], m11 = ml[11 * NS];
-          double sa0 = m0.x * a0.x, sa1 = m3.x * a0.x, sg0 = m6.x * c0.x, sg1 = m9.x * c0.x;
-          sa0 = fma(m0.y, a0.y, sa0); sa1 = fma(m3.y, a0.y, sa1); sg0 = fma(m6.y, c0.y, sg0); sg1 = fma(m9.y, c0.y, sg1);
-          sa0 = fma(m1.x, a1.x, sa0); sa1 = fma(m4.x, a1.x, sa1); sg0 = fma(m7.x, c1.x, sg0); sg1 = fma(m10.x, c1.x, sg1);
-          sa0 = fma(m1.y, a1.y, sa0); sa1 = fma(m4.y, a1.y, sa1); sg0 = fma(m7.y, c1.y, sg0); sg1 = fma(m10.y, c1.y, sg1);
-          sa0 = fma(m2.x, a2.x, sa0); sa1 = fma(m5.x, a2.x, sa1); sg0 = fma(m8.x, c2.x, sg0); sg1 = fma(m11.x, c2.x, sg1);
-          sa0 = fma(m2.y, a2.y, sa0); sa1 = fma(m5.y, a2.y, sa1); sg0 = fma(m8.y, c2.y, sg0); sg1 = fma(m11.y, c2.y, sg1);
-          y0 = sa0 - sg0; y1 = sa1 - sg1;
-        }
-        if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
-        bar_sync(kBarY, 128);
-        // ---- leaf backward: acceleration of this axis
-        double xt[3];
-        xt[0] = y0; xt[1] = y1;
-        {
-          const double yn0 = dn1(y0), yn1 = dn1(y1);
-          const double a = dai * (b[2] - cv0 * y0 - cv1 * y1 - cv2 * yn0 - cv3 * yn1);
-          xt[2] = hasu ? a : 0.0;
-        }
-        // ---- dynamics rows (p, v) of this stage: Ad x~_{k-1} + Bd u~_{k-1} - x~_k, projected onto the equality
-        double td0, td1, racc[3];
-        {
-          const double pp = up1(xt[0] + apv * xt[1] + bpa * xt[2]), pv = up1(xt[1] + bva * xt[2]);
-          const double zt0 = (notfirst ? pp : 0.0) - xt[0], zt1 = (notfirst ? pv : 0.0) - xt[1];
-          const double v0 = al * zt0 + om * zd[0] + ud[0], v1 = al * zt1 + om * zd[1] + ud[1];
-          zd[0] = bnd[0]; zd[1] = bnd[1];
-          ud[0] = v0 - bnd[0]; ud[1] = v1 - bnd[1];
-          td0 = rhd[0] * (bnd[0] - ud[0]); td1 = rhd[1] * (bnd[1] - ud[1]);
-          racc[0] = -td0; racc[1] = -td1; racc[2] = 0.0;
-        }
-        // ---- box rows
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const double v = al * xt[e] + om * zb[e] + ub[e];
-          const double zn = clampd(v, lo[e], hi[e]);
-          zb[e] = zn; ub[e] = v - zn;
-          racc[e] += rhb[e] * (zn - ub[e]);
-        }
-        // ---- x update, next right-hand side
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          x[e] = al * xt[e] + om * x[e];
-          b[e] = (e < 2 || hasu) ? racc[e] + sd[e] * x[e] - cq[e] : 0.0;
-        }
-        {
-          const double tp = dn1(td0), tv = dn1(td1);
-          if (hasu) { b[0] += tp; b[1] += apv * tp + tv; b[2] += bpa * tp + bva * tv; }
-        }
-      }
-      // ---- park
-      if (live) {
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const int j = e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc);
-          X_(j, k) = x[e]; Z_(8 + j, k) = zb[e]; U_(8 + j, k) = ub[e]; B_(j, k) = b[e];
-          WSDX_(j, k) = x[e] - ox[e]; WSDY_(8 + j, k) = rhb[e] * (ub[e] - oub[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = cc + 3 * e;
-          Z_(i, k) = zd[e]; U_(i, k) = ud[e]; WSDY_(i, k) = rhd[e] * (ud[e] - oud[e]);
-        }
-      }
-    } else {
-      // ------------------------------------------------------------------------------------------
-      // slack / obstacle warp: variables s_d, s_s (states 6, 7) and sigma_d, sigma_s (inputs 3, 4)
-      // ------------------------------------------------------------------------------------------
-      constexpr int RR = R > 0 ? R : 1;
-      double x[4], zb[4], ub[4], b[4], rhb[4], sd[4], cq[4], lo[4], hi[4], ox[4], oub[4];
-      double zd[2], ud[2], rhd[2], bnd[2], oud[2], dsi[2], esd[2], esdn[2], dgi[2], fs[6], og[3];
-      double zo[RR], uo[RR], rho_[RR], g3[3 * RR], lob[RR], ouo[RR];
-      int sl[RR];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = e < 2 ? 6 + e : 9 + e;
+      for (int e = 0; e < NVR; ++e) {
+        const int j = vj(e);
         x[e] = X_(j, k); zb[e] = Z_(8 + j, k); ub[e] = U_(8 + j, k); b[e] = B_(j, k); rhb[e] = RH_(8 + j, k);
-        sd[e] = SD_(j, k); cq[e] = CQ_(j, k); lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; ox[e] = 0.0; oub[e] = 0.0;
+        sd[e] = SD_(j, k); cq[e] = CQ_(j, k);
+        if constexpr (AX) { lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; }
+        if (live) { OX_(j, k) = x[e]; OU_(8 + j, k) = ub[e]; }
       }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        zd[t] = Z_(6 + t, k); ud[t] = U_(6 + t, k); rhd[t] = RH_(6 + t, k); bnd[t] = (k == 0) ? -x0p[6 + t] : 0.0; oud[t] = 0.0;
-        dsi[t] = DSI_(t, k); esd[t] = notfirst ? ESD_(t, k) : 0.0; esdn[t] = ESD_(t, kp); dgi[t] = DGI_(t, k);
+        const int i = di(t);
+        zd[t] = Z_(i, k); ud[t] = U_(i, k); rhd[t] = RH_(i, k); bnd[t] = (k == 0) ? -x0p[i] : 0.0;
+        if (live) OU_(i, k) = ud[t];
       }
+      if constexpr (AX) {
+        dai = DAI_(cc, k); cv0 = CV_(4 * cc, k); cv1 = CV_(4 * cc + 1, k); cv2 = CV_(4 * cc + 2, k); cv3 = CV_(4 * cc + 3, k);
+        cv2m = notfirst ? CV_(4 * cc + 2, km) : 0.0; cv3m = notfirst ? CV_(4 * cc + 3, km) : 0.0;
+      } else {
 #pragma unroll
-      for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
+        for (int t = 0; t < 2; ++t) { dsi[t] = DSI_(t, k); esd[t] = notfirst ? ESD_(t, k) : 0.0; esdn[t] = ESD_(t, kp); dgi[t] = DGI_(t, k); }
 #pragma unroll
-      for (int c2 = 0; c2 < 3; ++c2) og[c2] = OG_(c2, k);
+        for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
 #pragma unroll
-      for (int o = 0; o < R; ++o) {
-        zo[o] = Z_(NBR + o, k); uo[o] = U_(NBR + o, k); rho_[o] = RH_(NBR + o, k); lob[o] = LO_(o, k); ouo[o] = 0.0;
-        g3[3 * o] = G3_(3 * o, k); g3[3 * o + 1] = G3_(3 * o + 1, k); g3[3 * o + 2] = G3_(3 * o + 2, k);
-        sl[o] = hasu ? SLK_(o, k) : 0;
-      }
-      for (int it = 0; it < niter; ++it) {
-        if (it == niter - 1) {
+        for (int c2 = 0; c2 < 3; ++c2) og[c2] = OG_(c2, k);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { ox[e] = x[e]; oub[e] = ub[e]; }
-          oud[0] = ud[0]; oud[1] = ud[1];
-#pragma unroll
-          for (int o = 0; o < R; ++o) ouo[o] = uo[o];
+        for (int o = 0; o < RO; ++o) {
+          zo[o] = Z_(NBR + o, k); uo[o] = U_(NBR + o, k); rho_[o] = RH_(NBR + o, k);
+          if constexpr (kObsRegs) { lobr[o] = LO_(o, k); g3r[3 * o] = G3_(3 * o, k); g3r[3 * o + 1] = G3_(3 * o + 1, k); g3r[3 * o + 2] = G3_(3 * o + 2, k); }
+          sl[o] = hasu ? SLK_(o, k) : 0;
+          if (live) OU_(NBR + o, k) = uo[o];
         }
-        // ---- leaf forward, slack part: eliminate s_{k+1,t} then sigma_{k,t}; what that does to the position rows
-        double r11[2];
-        {
-          double f[2];
+      }
+    };
+    // iterates (+ the deltas of the last iteration) back to the arrays the single-warp code and store() read
+    auto park = [&]() {
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < NVR; ++e) {
+          const int j = vj(e);
+          X_(j, k) = x[e]; Z_(8 + j, k) = zb[e]; U_(8 + j, k) = ub[e]; B_(j, k) = b[e];
+          WSDX_(j, k) = x[e] - OX_(j, k); WSDY_(8 + j, k) = rhb[e] * (ub[e] - OU_(8 + j, k));
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { const int i = di(t); Z_(i, k) = zd[t]; U_(i, k) = ud[t]; WSDY_(i, k) = rhd[t] * (ud[t] - OU_(i, k)); }
+        if constexpr (!AX) {
+#pragma unroll
+          for (int c2 = 0; c2 < 3; ++c2) OG_(c2, k) = og[c2];
+#pragma unroll
+          for (int o = 0; o < RO; ++o) { Z_(NBR + o, k) = zo[o]; U_(NBR + o, k) = uo[o]; WSDY_(NBR + o, k) = rho_[o] * (uo[o] - OU_(NBR + o, k)); }
+        }
+      }
+    };
+
+    // ---- one burst of ADMM iterations (auxil.h:67-112) in registers; the last one records delta_x, delta_u
+    auto iterate = [&](const int niter) {
+      for (int it = 0; it < niter; ++it) {
+        const bool lastit = it == niter - 1;
+        if (lastit && live) {                       // iterate k-1 for the infeasibility certificates (delta_x, delta_y)
+#pragma unroll
+          for (int e = 0; e < NVR; ++e) { const int j = vj(e); OX_(j, k) = x[e]; OU_(8 + j, k) = ub[e]; }
+          OU_(di(0), k) = ud[0]; OU_(di(1), k) = ud[1];
+#pragma unroll
+          for (int o = 0; o < RO; ++o) OU_(NBR + o, k) = uo[o];
+        }
+        double xt[NVR], td[2], racc[NVR];
+        if constexpr (AX) {
+          // level-0 matrices are fetched before anything else so that they are in flight across the first barrier
+          double2 mt[12];
+#pragma unroll
+          for (int h = 0; h < 12; ++h) mt[h] = M[h * NS];
+          // ---- leaf forward (this axis' acceleration): reduced rhs rows (p, v); the slack/obstacle part comes from warp 3
+          double r0, r1;
+          {
+            const double ma = dai * b[2];
+            const double mm = up1(ma);
+            r0 = b[0] - cv0 * ma; r1 = b[1] - cv1 * ma;
+            r0 -= cv2m * mm; r1 -= cv3m * mm;             // cv2m = cv3m = 0 on stage 0
+          }
+          if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
+          bar_sync(kBarAll, 128);
+          r0 += m.RS[k * 4 + cc];
+          // ---- PCR levels 0..3
+#pragma unroll
+          for (int l = 0; l < kPcrLevels - 1; ++l) {
+            const int s = 1 << l, cur = l & 1;
+            const int kmm = k - s >= 0 ? k - s : k, kpp = k + s <= N ? k + s : k;
+            const double2* ra = RA2 + cur * 3 * NS;
+            double2 a0 = ra[kmm * 3], a1 = ra[kmm * 3 + 1], a2 = ra[kmm * 3 + 2];
+            double2 c0 = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
+            if (l == 0) {
+              const double2 sm0 = RS2[kmm * 2], sm1 = RS2[kmm * 2 + 1], sp0 = RS2[kpp * 2], sp1 = RS2[kpp * 2 + 1];
+              a0.x += sm0.x; a1.x += sm0.y; a2.x += sm1.x;
+              c0.x += sp0.x; c1.x += sp0.y; c2.x += sp1.x;
+            }
+            double sa0 = mt[0].x * a0.x, sa1 = mt[3].x * a0.x, sg0 = mt[6].x * c0.x, sg1 = mt[9].x * c0.x;
+            sa0 = fma(mt[0].y, a0.y, sa0); sa1 = fma(mt[3].y, a0.y, sa1); sg0 = fma(mt[6].y, c0.y, sg0); sg1 = fma(mt[9].y, c0.y, sg1);
+            sa0 = fma(mt[1].x, a1.x, sa0); sa1 = fma(mt[4].x, a1.x, sa1); sg0 = fma(mt[7].x, c1.x, sg0); sg1 = fma(mt[10].x, c1.x, sg1);
+            sa0 = fma(mt[1].y, a1.y, sa0); sa1 = fma(mt[4].y, a1.y, sa1); sg0 = fma(mt[7].y, c1.y, sg0); sg1 = fma(mt[10].y, c1.y, sg1);
+            sa0 = fma(mt[2].x, a2.x, sa0); sa1 = fma(mt[5].x, a2.x, sa1); sg0 = fma(mt[8].x, c2.x, sg0); sg1 = fma(mt[11].x, c2.x, sg1);
+            sa0 = fma(mt[2].y, a2.y, sa0); sa1 = fma(mt[5].y, a2.y, sa1); sg0 = fma(mt[8].y, c2.y, sg0); sg1 = fma(mt[11].y, c2.y, sg1);
+            // next level's matrices: issued before the barrier, consumed after it
+            const double2* mn = M + (l + 1) * (kPcrLevelDoubles / 2);
+#pragma unroll
+            for (int h = 0; h < 12; ++h) mt[h] = mn[h * NS];
+            r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
+            if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
+            bar_sync(kBarAxis, 96);
+          }
+          // ---- last level fused with D'^-1:  y = D'^-1 r_k - (D'^-1 M) r_partner   (buffer 0 holds the level-4 input)
+          double y0, y1;
+          {
+            const double2 a0 = RA2[k * 3], a1 = RA2[k * 3 + 1], a2 = RA2[k * 3 + 2];
+            const double2 c0 = RA2[kq * 3], c1 = RA2[kq * 3 + 1], c2 = RA2[kq * 3 + 2];
+            double sa0 = mt[0].x * a0.x, sa1 = mt[3].x * a0.x, sg0 = mt[6].x * c0.x, sg1 = mt[9].x * c0.x;
+            sa0 = fma(mt[0].y, a0.y, sa0); sa1 = fma(mt[3].y, a0.y, sa1); sg0 = fma(mt[6].y, c0.y, sg0); sg1 = fma(mt[9].y, c0.y, sg1);
+            sa0 = fma(mt[1].x, a1.x, sa0); sa1 = fma(mt[4].x, a1.x, sa1); sg0 = fma(mt[7].x, c1.x, sg0); sg1 = fma(mt[10].x, c1.x, sg1);
+            sa0 = fma(mt[1].y, a1.y, sa0); sa1 = fma(mt[4].y, a1.y, sa1); sg0 = fma(mt[7].y, c1.y, sg0); sg1 = fma(mt[10].y, c1.y, sg1);
+            sa0 = fma(mt[2].x, a2.x, sa0); sa1 = fma(mt[5].x, a2.x, sa1); sg0 = fma(mt[8].x, c2.x, sg0); sg1 = fma(mt[11].x, c2.x, sg1);
+            sa0 = fma(mt[2].y, a2.y, sa0); sa1 = fma(mt[5].y, a2.y, sa1); sg0 = fma(mt[8].y, c2.y, sg0); sg1 = fma(mt[11].y, c2.y, sg1);
+            y0 = sa0 - sg0; y1 = sa1 - sg1;
+          }
+          if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
+          bar_sync(kBarY, 128);
+          // ---- leaf backward: acceleration of this axis
+          xt[0] = y0; xt[1] = y1;
+          {
+            const double yn0 = dn1(y0), yn1 = dn1(y1);
+            const double a = dai * (b[2] - cv0 * y0 - cv1 * y1 - cv2 * yn0 - cv3 * yn1);
+            xt[2] = hasu ? a : 0.0;
+          }
+          // ---- dynamics rows (p, v) of this stage: Ad x~_{k-1} + Bd u~_{k-1} - x~_k, projected onto the equality
+          {
+            const double pp = up1(xt[0] + apv * xt[1] + bpa * xt[2]), pv = up1(xt[1] + bva * xt[2]);
+            const double zt0 = (notfirst ? pp : 0.0) - xt[0], zt1 = (notfirst ? pv : 0.0) - xt[1];
+            const double v0 = al * zt0 + om * zd[0] + ud[0], v1 = al * zt1 + om * zd[1] + ud[1];
+            zd[0] = bnd[0]; zd[1] = bnd[1];
+            ud[0] = v0 - bnd[0]; ud[1] = v1 - bnd[1];
+            td[0] = rhd[0] * (bnd[0] - ud[0]); td[1] = rhd[1] * (bnd[1] - ud[1]);
+            racc[0] = -td[0]; racc[1] = -td[1]; racc[2] = 0.0;
+          }
+        } else {
+          // ---- leaf forward, slack part: eliminate s_{k+1,t} then sigma_{k,t}; what that does to the position rows
+          double r11[2];
+          {
+            double f[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const double bn = dn1(b[t]);
+              const double v = b[2 + t] - esdn[t] * bn;
+              r11[t] = hasu ? v : 0.0;
+              f[t] = dgi[t] * r11[t];
+            }
+            const double rs0 = og[0] - fs[0] * f[0] - fs[3] * f[1], rs1 = og[1] - fs[1] * f[0] - fs[4] * f[1],
+                         rs2 = og[2] - fs[2] * f[0] - fs[5] * f[1];
+            if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); }
+          }
+          bar_sync(kBarAll, 128);
+          bar_sync(kBarY, 128);
+          const double y0 = m.YB[k * 6], y1 = m.YB[k * 6 + 2], y2 = m.YB[k * 6 + 4];
+          // ---- leaf backward: slack inputs, then slack states
+          double xp[2];
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const double bn = dn1(b[t]);
-            const double v = b[2 + t] - esdn[t] * bn;
-            r11[t] = hasu ? v : 0.0;
-            f[t] = dgi[t] * r11[t];
+            const double v = dgi[t] * (r11[t] - fs[3 * t] * y0 - fs[3 * t + 1] * y1 - fs[3 * t + 2] * y2);
+            xt[2 + t] = hasu ? v : 0.0;
+            const double q = up1(xt[2 + t]);
+            xp[t] = notfirst ? q : 0.0;
+            xt[t] = dsi[t] * b[t] - esd[t] * xp[t];
           }
-          const double rs0 = og[0] - fs[0] * f[0] - fs[3] * f[1], rs1 = og[1] - fs[1] * f[0] - fs[4] * f[1],
-                       rs2 = og[2] - fs[2] * f[0] - fs[5] * f[1];
-          if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); }
-        }
-        bar_sync(kBarAll, 128);
-        bar_sync(kBarY, 128);
-        const double y0 = m.YB[k * 6], y1 = m.YB[k * 6 + 2], y2 = m.YB[k * 6 + 4];
-        // ---- leaf backward: slack inputs, then slack states
-        double xt[4], xp[2];
+          // ---- dynamics rows 6, 7:  sigma~_{k-1,t} - s~_{k,t}
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const double v = dgi[t] * (r11[t] - fs[3 * t] * y0 - fs[3 * t + 1] * y1 - fs[3 * t + 2] * y2);
-          xt[2 + t] = hasu ? v : 0.0;
-          const double q = up1(xt[2 + t]);
-          xp[t] = notfirst ? q : 0.0;
-          xt[t] = dsi[t] * b[t] - esd[t] * xp[t];
-        }
-        // ---- dynamics rows 6, 7:  sigma~_{k-1,t} - s~_{k,t}
-        double td[2], racc[4];
+          for (int t = 0; t < 2; ++t) {
+            const double zt = xp[t] - xt[t];
+            const double v = al * zt + om * zd[t] + ud[t];
+            zd[t] = bnd[t]; ud[t] = v - bnd[t];
+            td[t] = rhd[t] * (bnd[t] - ud[t]);
+            racc[t] = -td[t]; racc[2 + t] = 0.0;
+          }
+          // ---- obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low
+          og[0] = og[1] = og[2] = 0.0;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const double zt = xp[t] - xt[t];
-          const double v = al * zt + om * zd[t] + ud[t];
-          zd[t] = bnd[t]; ud[t] = v - bnd[t];
-          td[t] = rhd[t] * (bnd[t] - ud[t]);
-          racc[t] = -td[t]; racc[2 + t] = 0.0;
+          for (int o = 0; o < RO; ++o) {
+            const double ga = g3(3 * o), gb = g3(3 * o + 1), gc = g3(3 * o + 2), lw = lob(o);
+            const double zt = ga * y0 + gb * y1 + gc * y2 - (sl[o] ? xt[3] : xt[2]);
+            const double v = al * zt + om * zo[o] + uo[o];
+            const double zn = v > lw ? v : lw;
+            zo[o] = zn; uo[o] = v - zn;
+            const double t = rho_[o] * (zn - uo[o]);
+            og[0] += ga * t; og[1] += gb * t; og[2] += gc * t;
+            if (sl[o]) racc[3] -= t; else racc[2] -= t;
+          }
         }
         // ---- box rows
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < NVR; ++e) {
           const double v = al * xt[e] + om * zb[e] + ub[e];
-          const double zn = clampd(v, lo[e], hi[e]);
+          const double zn = clampd(v, blo(e), bhi(e));
           zb[e] = zn; ub[e] = v - zn;
           racc[e] += rhb[e] * (zn - ub[e]);
         }
-        // ---- obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low
-        og[0] = og[1] = og[2] = 0.0;
+        // ---- x update (auxil.h:83), next right-hand side
 #pragma unroll
-        for (int o = 0; o < R; ++o) {
-          const double zt = g3[3 * o] * y0 + g3[3 * o + 1] * y1 + g3[3 * o + 2] * y2 - (sl[o] ? xt[3] : xt[2]);
-          const double v = al * zt + om * zo[o] + uo[o];
-          const double zn = v > lob[o] ? v : lob[o];
-          zo[o] = zn; uo[o] = v - zn;
-          const double t = rho_[o] * (zn - uo[o]);
-          og[0] += g3[3 * o] * t; og[1] += g3[3 * o + 1] * t; og[2] += g3[3 * o + 2] * t;
-          if (sl[o]) racc[3] -= t; else racc[2] -= t;
-        }
-        // ---- x update, next right-hand side
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < NVR; ++e) {
           x[e] = al * xt[e] + om * x[e];
           b[e] = (e < 2 || hasu) ? racc[e] + sd[e] * x[e] - cq[e] : 0.0;
         }
         {
-          const double t6 = dn1(td[0]), t7 = dn1(td[1]);
-          if (hasu) { b[2] += t6; b[3] += t7; }
+          const double t0 = dn1(td[0]), t1 = dn1(td[1]);
+          if (hasu) {
+            if constexpr (AX) { b[0] += t0; b[1] += apv * t0 + t1; b[2] += bpa * t0 + bva * t1; }
+            else { b[2] += t0; b[3] += t1; }
+          }
         }
       }
-      if (live) {
+    };
+
+    // screening values for the infeasibility certificates (filled by info())
+    double s_ndy = 0.0, s_lhs = 0.0, s_ndx = 0.0, s_qd = 0.0, s_pm = 0.0;
+    // ---- update_info (auxil.h:154) from registers, all warps; every thread ends with identical scalars
+    auto info = [&](const int iter) {
+      // exchange: positions for the obstacle rows' A x, obstacle multipliers for the position columns' A' y
+      if constexpr (AX) { if (live) RA2[k * 3 + cc] = make_double2(x[0], x[1]); }
+      else {
+        double oy[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int o = 0; o < RO; ++o) { const double yo = rho_[o] * uo[o]; oy[0] += g3(3 * o) * yo; oy[1] += g3(3 * o + 1) * yo; oy[2] += g3(3 * o + 2) * yo; }
+        if (live) { RS2[k * 2] = make_double2(oy[0], oy[1]); RS2[k * 2 + 1] = make_double2(oy[2], 0.0); }
+      }
+      __syncthreads();
+      double mx[15], sm[3];
+#pragma unroll
+      for (int e = 0; e < 15; ++e) mx[e] = 0.0;
+      sm[0] = sm[1] = sm[2] = 0.0;
+      auto row = [&](double ax, double z, double e) {
+        const double d = fabs(ax - z);
+        mx[0] = fmax(mx[0], d); mx[1] = fmax(mx[1], fabs(ax)); mx[2] = fmax(mx[2], fabs(z));
+        mx[3] = fmax(mx[3], e * d); mx[4] = fmax(mx[4], e * fabs(ax)); mx[5] = fmax(mx[5], e * fabs(z));
+      };
+      auto var = [&](double xv, double p, double cqv, double aty, double dj, double dxv) {
+        const double px = c * p * xv;
+        const double d = fabs(px + cqv + aty);
+        mx[6] = fmax(mx[6], d); mx[7] = fmax(mx[7], fabs(px)); mx[8] = fmax(mx[8], fabs(aty));
+        mx[9] = fmax(mx[9], dj * d); mx[10] = fmax(mx[10], dj * fabs(px)); mx[11] = fmax(mx[11], dj * fabs(aty));
+        if (live) sm[0] += (0.5 * p * xv + cqv * cinv) * xv;
+        // is_dual_infeasible screening (auxil.h:148): |dx|_inf, q'dx, |P dx|_inf
+        mx[13] = fmax(mx[13], fabs(dxv)); mx[14] = fmax(mx[14], fabs(c * p * dxv));
+        if (live) sm[2] += cqv * dxv;
+      };
+      // is_primal_infeasible screening (auxil.h:137): projected delta_y, its norm and the support-function value
+      auto cert = [&](double dy, double e, double lo_, double hi_) {
+        const double ls = e * lo_, us = e * hi_;
+        if (us > kInfty * kMinScaling) { if (ls < -kInfty * kMinScaling) dy = 0.0; else dy = fmin(dy, 0.0); }
+        else if (ls < -kInfty * kMinScaling) dy = fmax(dy, 0.0);
+        mx[12] = fmax(mx[12], fabs(dy));
+        if (live) sm[1] += hi_ * fmax(dy, 0.0) + lo_ * fmin(dy, 0.0);
+      };
+      const double yd0 = rhd[0] * ud[0], yd1 = rhd[1] * ud[1];
+      const double yn0 = dn1(yd0), yn1 = dn1(yd1);
+      if constexpr (AX) {
+        const double pp = up1(x[0] + apv * x[1] + bpa * x[2]), pv = up1(x[1] + bva * x[2]);
+        const double e0 = WSE_(cc, k), e1 = WSE_(3 + cc, k);
+        row((notfirst ? pp : 0.0) - x[0], zd[0], e0); row((notfirst ? pv : 0.0) - x[1], zd[1], e1);
+        cert(rhd[0] * (ud[0] - OU_(cc, k)), e0, bnd[0], bnd[0]); cert(rhd[1] * (ud[1] - OU_(3 + cc, k)), e1, bnd[1], bnd[1]);
+        double aty[3];
+        aty[0] = rhb[0] * ub[0] - yd0; aty[1] = rhb[1] * ub[1] - yd1; aty[2] = rhb[2] * ub[2];
+        if (hasu) { aty[0] += yn0 + m.RS[k * 4 + cc]; aty[1] += apv * yn0 + yn1; aty[2] += bpa * yn0 + bva * yn1; }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const int j = vj(e);
+          if (e < 2 || hasu) {
+            const double ee = WSE_(8 + j, k);
+            row(x[e], zb[e], ee); cert(rhb[e] * (ub[e] - OU_(8 + j, k)), ee, blo(e), bhi(e));
+            var(x[e], pd[k * NV + j], cq[e], aty[e], WSD_(j, k), x[e] - OX_(j, k));
+          }
+        }
+      } else {
+        const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4];
+        const double q0 = up1(x[2]), q1 = up1(x[3]);
+        const double e0 = WSE_(6, k), e1 = WSE_(7, k);
+        row((notfirst ? q0 : 0.0) - x[0], zd[0], e0); row((notfirst ? q1 : 0.0) - x[1], zd[1], e1);
+        cert(rhd[0] * (ud[0] - OU_(6, k)), e0, bnd[0], bnd[0]); cert(rhd[1] * (ud[1] - OU_(7, k)), e1, bnd[1], bnd[1]);
+        double aty[4];
+        aty[0] = rhb[0] * ub[0] - yd0; aty[1] = rhb[1] * ub[1] - yd1; aty[2] = rhb[2] * ub[2]; aty[3] = rhb[3] * ub[3];
+        if (hasu) { aty[2] += yn0; aty[3] += yn1; }
+#pragma unroll
+        for (int o = 0; o < RO; ++o) {
+          if (hasu) {
+            const double ee = WSE_(NBR + o, k), yo = rho_[o] * uo[o];
+            row(g3(3 * o) * x0v + g3(3 * o + 1) * x1v + g3(3 * o + 2) * x2v - (sl[o] ? x[3] : x[2]), zo[o], ee);
+            cert(rho_[o] * (uo[o] - OU_(NBR + o, k)), ee, lob(o), INFINITY);
+            if (sl[o]) aty[3] -= yo; else aty[2] -= yo;
+          }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int j = e < 2 ? 6 + e : 9 + e;
-          X_(j, k) = x[e]; Z_(8 + j, k) = zb[e]; U_(8 + j, k) = ub[e]; B_(j, k) = b[e];
-          WSDX_(j, k) = x[e] - ox[e]; WSDY_(8 + j, k) = rhb[e] * (ub[e] - oub[e]);
+          const int j = vj(e);
+          if (e < 2 || hasu) {
+            const double ee = WSE_(8 + j, k);
+            row(x[e], zb[e], ee); cert(rhb[e] * (ub[e] - OU_(8 + j, k)), ee, blo(e), bhi(e));
+            var(x[e], pd[k * NV + j], cq[e], aty[e], WSD_(j, k), x[e] - OX_(j, k));
+          }
         }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) { Z_(6 + t, k) = zd[t]; U_(6 + t, k) = ud[t]; WSDY_(6 + t, k) = rhd[t] * (ud[t] - oud[t]); }
-#pragma unroll
-        for (int c2 = 0; c2 < 3; ++c2) OG_(c2, k) = og[c2];
-#pragma unroll
-        for (int o = 0; o < R; ++o) { Z_(NBR + o, k) = zo[o]; U_(NBR + o, k) = uo[o]; WSDY_(NBR + o, k) = rho_[o] * (uo[o] - ouo[o]); }
       }
-    }
-  }
+      if (!live) {                                // ghost lanes carry a meaningless copy of the last stage
+#pragma unroll
+        for (int e = 0; e < 15; ++e) mx[e] = 0.0;
+      }
+      cta_reduce(mx, sm, warp);
+      obj = sm[0];
+      pri_res = mx[0]; nAx = mx[1]; nZ = mx[2]; pri_s = mx[3]; nAx_s = mx[4]; nZ_s = mx[5];
+      dua_res = mx[6] * cinv; nPx = mx[7] * cinv; nAty = mx[8] * cinv; dua_s = mx[9]; nPx_s = mx[10]; nAty_s = mx[11];
+      s_ndy = mx[12]; s_lhs = sm[1]; s_ndx = mx[13]; s_pm = mx[14]; s_qd = sm[2];
+      info_iter = iter;
+    };
+    // check_termination (auxil.h:133).  The residual tests are exact; the infeasibility certificates are screened
+    // with their first (necessary) conditions and only evaluated in full, by warp 0 from the parked arrays, when
+    // the screening passes.
+    auto check = [&](const bool approx) -> bool {
+      double ea = st.eps_abs, er = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+      if (pri_res > kInfty || dua_res > kInfty) { status = kNonCvx; obj = kOsqpNan; return true; }
+      if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+      const bool pr = sh.m == 0 || pri_res < ea + er * fmax(nZ, nAx);
+      const bool dr = dua_res < ea + er * fmax(nq, fmax(nAty, nPx));
+      if (pr && dr) { status = approx ? kSolvedInacc : kSolved; return true; }
+      bool maybe = false;
+      if (!pr) maybe = maybe || ((s_ndy > epi) && (s_lhs < -epi * s_ndy));
+      if (!dr) maybe = maybe || ((s_ndx > edi) && (s_qd < -c * edi * s_ndx) && (s_pm < c * edi * s_ndx));
+      if (!maybe) return false;
+      park();
+      __syncthreads();
+      if (warp == 0) { const bool d = check_termination(approx); if (lane == 0) *flag = d ? 1 : 0; }
+      __syncthreads();
+      const int f = *flag;
+      __syncthreads();
+      return f != 0;
+    };
 
-  // osqp_solve for the CTA: warp 0 runs the single-warp phases (factor, info, termination, rho adaptation); its
-  // decisions reach the other warps through *flag.
-  MQ_HD void solve_cta(int warp, volatile int* flag) {
+    // ---- osqp_solve (osqp.h:78): same control flow as solve() below
     status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
     int iter = 0;
     bool refactor = true, last_checked = false, approx = false;
@@ -1692,17 +1980,17 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       if (!final_pass) {
         if (refactor) {
           if (warp == 0) {
-            factor(); rows_phase<1>(); rhs_finish();
-            MQ_FOR_STAGES(k) { OG_(0, k) = 0.0; OG_(1, k) = 0.0; OG_(2, k) = 0.0; }   // B_ holds the whole rhs again
+            factor(); rows_phase<1>(); rhs_finish();      // leaf elimination + T blocks; whole right-hand side into B_
+            MQ_FOR_STAGES(kk) { OG_(0, kk) = 0.0; OG_(1, kk) = 0.0; OG_(2, kk) = 0.0; }
           }
+          pcr_factor_cta(warp);                           // starts and ends with a CTA barrier
+          load();
           refactor = false;
-          __syncthreads();
         }
         int nb = st.max_iter;
         if (st.check_termination) { int c2 = (iter / st.check_termination + 1) * st.check_termination; if (c2 < nb) nb = c2; }
         if (st.adaptive_rho && st.adaptive_rho_interval) { int c2 = (iter / st.adaptive_rho_interval + 1) * st.adaptive_rho_interval; if (c2 < nb) nb = c2; }
-        burst_cta(nb - iter, warp);
-        __syncthreads();
+        iterate(nb - iter);
         iter = nb;
         do_check = st.check_termination && (iter % st.check_termination == 0);
         do_adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
@@ -1713,30 +2001,47 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       } else {
         do_info = false; do_check = true;
       }
-      if (warp == 0) {
-        if (do_info) update_info(iter);
-        const bool done = do_check && check_termination(approx);
-        int f = done ? 1 : 0;
-        if (!done && !final_pass && do_adapt && adapt_rho()) f |= 2;
-        if (lane == 0) *flag = f;
-      }
-      __syncthreads();
-      const int f = *flag;
-      __syncthreads();
-      if (f & 1) break;
+      if (do_info) info(iter);
+      if (do_check && check(approx)) break;
       if (final_pass) {
         if (approx) { status = kMaxIter; break; }
         approx = true;
         continue;
       }
-      if (f & 2) refactor = true;
+      if (do_adapt) {
+        // compute_rho_estimate / adapt_rho (auxil.h:21-38): the decision is taken by every thread on identical scalars
+        const double pn = pri_s / (fmax(nZ_s, nAx_s) + 1e-10);
+        const double dn = dua_s / (fmax(nq_s, fmax(nAty_s, nPx_s)) + 1e-10);
+        double rn = rho * sqrt(pn / (dn + 1e-10));
+        rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+        if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
+          park();
+          __syncthreads();
+          if (warp == 0) adapt_rho(); else rho = rn;       // warp 0 re-derives the same rho and rescales RH_, U_
+          refactor = true;
+        }
+      }
     }
+    park();
   }
+
   MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag) {
     x0p = bt.x0 + (size_t)b * 8;
-    if (warp == 0) load_and_scale(bt, b);
+    // setup (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) builds the cold block in the still unused PCR
+    // region of shared memory; the CTA then copies it to its global home in one pass
+    if (warp == 0) {
+      const Mem keep = m;
+      map_cold(m, keep.PCR, NS, R);
+      load_and_scale(bt, b);
+      m = keep;
+      if (lane == 0) { m.YB[0] = c; m.YB[1] = rho; m.YB[2] = nq; m.YB[3] = nq_s; }
+    }
     __syncthreads();
-    solve_cta(warp, flag);
+    c = m.YB[0]; cinv = 1.0 / c; rho = m.YB[1]; nq = m.YB[2]; nq_s = m.YB[3];
+    for (int i = threadIdx.x; i < cold_slots(R) * NS; i += blockDim.x) m.E[i] = m.PCR[i];
+    __syncthreads();
+    if (warp < 3) solve_role<true>(warp, flag); else solve_role<false>(warp, flag);
+    __syncthreads();
     if (warp == 0) store(bt, b);
     __syncthreads();
   }
