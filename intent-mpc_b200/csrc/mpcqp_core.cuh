@@ -80,6 +80,7 @@ struct Batch {              // device pointers
   int* status; int* iter; int* rho_updates;
   double* obj; double* pri_res; double* dua_res;
   double* ws;                   // per-warp scratch, ws_doubles(shape) each
+  const int* order;             // [B] processing order (longest-first hint) or nullptr
   int B;
 };
 
@@ -1579,9 +1580,12 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   template <int NM, int NS_> MQ_HD void cta_reduce(double (&mx)[NM], double (&sm)[NS_], int warp) {
     static_assert(4 * (NM + NS_) <= 6 * NST, "reduction scratch is the y buffer");
 #pragma unroll
-    for (int e = 0; e < NM; ++e) mx[e] = wmax(mx[e]);
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int e = 0; e < NS_; ++e) sm[e] = wsum(sm[e]);
+      for (int e = 0; e < NM; ++e) { const double v = __shfl_xor_sync(0xffffffffu, mx[e], o); mx[e] = v > mx[e] ? v : mx[e]; }
+#pragma unroll
+      for (int e = 0; e < NS_; ++e) sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], o);
+    }
     double* red = m.YB;
     if (lane == 0) {
 #pragma unroll
@@ -1591,7 +1595,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     }
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < NM; ++e) mx[e] = fmax(fmax(red[e], red[(NM + NS_) + e]), fmax(red[2 * (NM + NS_) + e], red[3 * (NM + NS_) + e]));
+    for (int e = 0; e < NM; ++e) {
+      const double a0 = red[e], a1 = red[(NM + NS_) + e], a2 = red[2 * (NM + NS_) + e], a3 = red[3 * (NM + NS_) + e];
+      const double b0 = a0 > a1 ? a0 : a1, b1 = a2 > a3 ? a2 : a3;
+      mx[e] = b0 > b1 ? b0 : b1;
+    }
 #pragma unroll
     for (int e = 0; e < NS_; ++e) sm[e] = (red[NM + e] + red[(NM + NS_) + NM + e]) + (red[2 * (NM + NS_) + NM + e] + red[3 * (NM + NS_) + NM + e]);
     __syncthreads();
@@ -1604,8 +1612,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   // single-warp array code on warp 0.
   template <bool AX> MQ_HD void solve_role(const int warp, volatile int* flag) {
     constexpr int NVR = AX ? 3 : 4;
-    constexpr int RO = AX ? 0 : R;
-    constexpr int RR = RO > 0 ? RO : 1;
+    constexpr int NOW = (R + 3) / 4;                    // obstacle rows owned per warp: row o belongs to warp o % 4
+    constexpr int RW = NOW > 0 ? NOW : 1;
     const int cc = warp;
     const int k = lane < NS ? lane : NS - 1;            // ghost lanes shadow the last stage, never write
     const bool live = lane < NS, hasu = lane < N, notfirst = lane > 0 && live;
@@ -1614,23 +1622,24 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     double2* const RA2 = reinterpret_cast<double2*>(m.RA);      // [2][NS][3] pairs
     double2* const RS2 = reinterpret_cast<double2*>(m.RS);      // [NS][2] pairs: (x, y), (z, -)
     double2* const YB2 = reinterpret_cast<double2*>(m.YB);      // [NS][3] pairs
+    double* const XR = m.YB + 6 * NS;                           // [2][NS]   r11 of the slack-input elimination
+    double* const T4 = XR + 2 * NS;                             // [R][4][NS] obstacle rows: (g0 t, g1 t, g2 t, t)
     const double2* const M = reinterpret_cast<const double2*>(m.PCR) + ((AX ? cc : 0) * 12) * NS + k;
     const int kq = k >= 16 ? k - 16 : (k + 16 <= N ? k + 16 : k);
     auto vj = [&](int e) { return AX ? (e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc)) : (e < 2 ? 6 + e : 9 + e); };
     auto di = [&](int t) { return AX ? cc + 3 * t : 6 + t; };
 
-    constexpr bool kObsRegs = R <= 4;                 // obstacle gradients / bounds in registers, else re-read from shared memory
     double x[NVR], zb[NVR], ub[NVR], b[NVR], rhb[NVR], sd[NVR], cq[NVR], lo[AX ? 3 : 1], hi[AX ? 3 : 1];
     double zd[2], ud[2], rhd[2], bnd[2];
     // box bounds: the axis role's variable indices depend on the warp (registers); the slack role's are compile-time
     auto blo = [&](int e) { if constexpr (AX) return lo[e]; else return sh.blo[e < 2 ? 6 + e : 9 + e]; };
     auto bhi = [&](int e) { if constexpr (AX) return hi[e]; else return sh.bhi[e < 2 ? 6 + e : 9 + e]; };
-    double dai = 0, cv0 = 0, cv1 = 0, cv2 = 0, cv3 = 0, cv2m = 0, cv3m = 0;                 // AX
-    double dsi[2], esd[2], esdn[2], dgi[2], fs[6], og[3];                                       // !AX
-    double zo[RR], uo[RR], rho_[RR], g3r[kObsRegs ? 3 * RR : 1], lobr[kObsRegs ? RR : 1];
-    int sl[RR];
-    auto g3 = [&](int e) { if constexpr (kObsRegs) return g3r[e]; else return G3_(e, k); };
-    auto lob = [&](int o) { if constexpr (kObsRegs) return lobr[o]; else return LO_(o, k); };
+    double dai = 0, cv0 = 0, cv1 = 0, cv2 = 0, cv3 = 0, cv2m = 0, cv3m = 0, ogp = 0;        // AX (ogp: parked obstacle part of b_p)
+    double dsi[2], esd[2], esdn[2], dgi[2], fs[6];                                              // !AX
+    unsigned slmask = 0;                                // !AX: bit o set when row o is softened by sigma_s (slack input 4)
+    // owned obstacle rows (both roles): row o = 4 q + warp
+    double zo[RW], uo[RW], orh[RW], og3[3 * RW], olo[RW], odg[RW], ofs[3 * RW];
+    int osl[RW]; bool oex[RW];
 
     auto load = [&]() {
 #pragma unroll
@@ -1639,31 +1648,34 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         x[e] = X_(j, k); zb[e] = Z_(8 + j, k); ub[e] = U_(8 + j, k); b[e] = B_(j, k); rhb[e] = RH_(8 + j, k);
         sd[e] = SD_(j, k); cq[e] = CQ_(j, k);
         if constexpr (AX) { lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; }
-        if (live) { OX_(j, k) = x[e]; OU_(8 + j, k) = ub[e]; }
       }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int i = di(t);
         zd[t] = Z_(i, k); ud[t] = U_(i, k); rhd[t] = RH_(i, k); bnd[t] = (k == 0) ? -x0p[i] : 0.0;
-        if (live) OU_(i, k) = ud[t];
       }
       if constexpr (AX) {
         dai = DAI_(cc, k); cv0 = CV_(4 * cc, k); cv1 = CV_(4 * cc + 1, k); cv2 = CV_(4 * cc + 2, k); cv3 = CV_(4 * cc + 3, k);
         cv2m = notfirst ? CV_(4 * cc + 2, km) : 0.0; cv3m = notfirst ? CV_(4 * cc + 3, km) : 0.0;
+        ogp = OG_(cc, k);
       } else {
 #pragma unroll
         for (int t = 0; t < 2; ++t) { dsi[t] = DSI_(t, k); esd[t] = notfirst ? ESD_(t, k) : 0.0; esdn[t] = ESD_(t, kp); dgi[t] = DGI_(t, k); }
 #pragma unroll
         for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
+        slmask = 0;
 #pragma unroll
-        for (int c2 = 0; c2 < 3; ++c2) og[c2] = OG_(c2, k);
+        for (int o = 0; o < R; ++o) slmask |= (hasu && SLK_(o, k)) ? (1u << o) : 0u;
+      }
 #pragma unroll
-        for (int o = 0; o < RO; ++o) {
-          zo[o] = Z_(NBR + o, k); uo[o] = U_(NBR + o, k); rho_[o] = RH_(NBR + o, k);
-          if constexpr (kObsRegs) { lobr[o] = LO_(o, k); g3r[3 * o] = G3_(3 * o, k); g3r[3 * o + 1] = G3_(3 * o + 1, k); g3r[3 * o + 2] = G3_(3 * o + 2, k); }
-          sl[o] = hasu ? SLK_(o, k) : 0;
-          if (live) OU_(NBR + o, k) = uo[o];
-        }
+      for (int q = 0; q < NOW; ++q) {
+        const int o = 4 * q + warp;
+        oex[q] = o < R && hasu;
+        const int oo = o < R ? o : 0;
+        zo[q] = Z_(NBR + oo, k); uo[q] = U_(NBR + oo, k); orh[q] = RH_(NBR + oo, k); olo[q] = LO_(oo, k);
+        og3[3 * q] = G3_(3 * oo, k); og3[3 * q + 1] = G3_(3 * oo + 1, k); og3[3 * q + 2] = G3_(3 * oo + 2, k);
+        osl[q] = hasu ? SLK_(oo, k) : 0;
+        odg[q] = DGI_(osl[q], k); ofs[3 * q] = FS_(3 * osl[q], k); ofs[3 * q + 1] = FS_(3 * osl[q] + 1, k); ofs[3 * q + 2] = FS_(3 * osl[q] + 2, k);
       }
     };
     // iterates (+ the deltas of the last iteration) back to the arrays the single-warp code and store() read
@@ -1677,11 +1689,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         }
 #pragma unroll
         for (int t = 0; t < 2; ++t) { const int i = di(t); Z_(i, k) = zd[t]; U_(i, k) = ud[t]; WSDY_(i, k) = rhd[t] * (ud[t] - OU_(i, k)); }
-        if constexpr (!AX) {
+        if constexpr (AX) OG_(cc, k) = ogp;
 #pragma unroll
-          for (int c2 = 0; c2 < 3; ++c2) OG_(c2, k) = og[c2];
-#pragma unroll
-          for (int o = 0; o < RO; ++o) { Z_(NBR + o, k) = zo[o]; U_(NBR + o, k) = uo[o]; WSDY_(NBR + o, k) = rho_[o] * (uo[o] - OU_(NBR + o, k)); }
+        for (int q = 0; q < NOW; ++q) {
+          const int o = 4 * q + warp;
+          if (o < R) { Z_(NBR + o, k) = zo[q]; U_(NBR + o, k) = uo[q]; WSDY_(NBR + o, k) = orh[q] * (uo[q] - OU_(NBR + o, k)); }
         }
       }
     };
@@ -1695,20 +1707,20 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           for (int e = 0; e < NVR; ++e) { const int j = vj(e); OX_(j, k) = x[e]; OU_(8 + j, k) = ub[e]; }
           OU_(di(0), k) = ud[0]; OU_(di(1), k) = ud[1];
 #pragma unroll
-          for (int o = 0; o < RO; ++o) OU_(NBR + o, k) = uo[o];
+          for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R) OU_(NBR + o, k) = uo[q]; }
         }
-        double xt[NVR], td[2], racc[NVR];
+        double xt[NVR], td[2], racc[NVR], yp0, yp1, yp2;
         if constexpr (AX) {
           // level-0 matrices are fetched before anything else so that they are in flight across the first barrier
           double2 mt[12];
 #pragma unroll
           for (int h = 0; h < 12; ++h) mt[h] = M[h * NS];
-          // ---- leaf forward (this axis' acceleration): reduced rhs rows (p, v); the slack/obstacle part comes from warp 3
+          // ---- leaf forward (this axis' acceleration): reduced rhs rows (p, v); the slack-input part comes from warp 3
           double r0, r1;
           {
             const double ma = dai * b[2];
             const double mm = up1(ma);
-            r0 = b[0] - cv0 * ma; r1 = b[1] - cv1 * ma;
+            r0 = (b[0] + ogp) - cv0 * ma; r1 = b[1] - cv1 * ma;
             r0 -= cv2m * mm; r1 -= cv3m * mm;             // cv2m = cv3m = 0 on stage 0
           }
           if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
@@ -1756,6 +1768,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           }
           if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
           bar_sync(kBarY, 128);
+          if constexpr (NOW > 0) { yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4]; }
           // ---- leaf backward: acceleration of this axis
           xt[0] = y0; xt[1] = y1;
           {
@@ -1785,18 +1798,17 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
               r11[t] = hasu ? v : 0.0;
               f[t] = dgi[t] * r11[t];
             }
-            const double rs0 = og[0] - fs[0] * f[0] - fs[3] * f[1], rs1 = og[1] - fs[1] * f[0] - fs[4] * f[1],
-                         rs2 = og[2] - fs[2] * f[0] - fs[5] * f[1];
-            if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); }
+            const double rs0 = -fs[0] * f[0] - fs[3] * f[1], rs1 = -fs[1] * f[0] - fs[4] * f[1], rs2 = -fs[2] * f[0] - fs[5] * f[1];
+            if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); XR[k] = r11[0]; XR[NS + k] = r11[1]; }
           }
           bar_sync(kBarAll, 128);
           bar_sync(kBarY, 128);
-          const double y0 = m.YB[k * 6], y1 = m.YB[k * 6 + 2], y2 = m.YB[k * 6 + 4];
+          yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4];
           // ---- leaf backward: slack inputs, then slack states
           double xp[2];
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const double v = dgi[t] * (r11[t] - fs[3 * t] * y0 - fs[3 * t + 1] * y1 - fs[3 * t + 2] * y2);
+            const double v = dgi[t] * (r11[t] - fs[3 * t] * yp0 - fs[3 * t + 1] * yp1 - fs[3 * t + 2] * yp2);
             xt[2 + t] = hasu ? v : 0.0;
             const double q = up1(xt[2 + t]);
             xp[t] = notfirst ? q : 0.0;
@@ -1811,18 +1823,21 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             td[t] = rhd[t] * (bnd[t] - ud[t]);
             racc[t] = -td[t]; racc[2 + t] = 0.0;
           }
-          // ---- obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low
-          og[0] = og[1] = og[2] = 0.0;
+        }
+        // ---- owned obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low.  The slack input of the row's type is
+        // re-derived from r11 (4 flops) instead of being fetched from warp 3.
 #pragma unroll
-          for (int o = 0; o < RO; ++o) {
-            const double ga = g3(3 * o), gb = g3(3 * o + 1), gc = g3(3 * o + 2), lw = lob(o);
-            const double zt = ga * y0 + gb * y1 + gc * y2 - (sl[o] ? xt[3] : xt[2]);
-            const double v = al * zt + om * zo[o] + uo[o];
-            const double zn = v > lw ? v : lw;
-            zo[o] = zn; uo[o] = v - zn;
-            const double t = rho_[o] * (zn - uo[o]);
-            og[0] += ga * t; og[1] += gb * t; og[2] += gc * t;
-            if (sl[o]) racc[3] -= t; else racc[2] -= t;
+        for (int q = 0; q < NOW; ++q) {
+          const int o = 4 * q + warp;
+          if (o < R) {
+            const double r11s = XR[osl[q] * NS + k];
+            const double sg = oex[q] ? odg[q] * (r11s - ofs[3 * q] * yp0 - ofs[3 * q + 1] * yp1 - ofs[3 * q + 2] * yp2) : 0.0;
+            const double zt = og3[3 * q] * yp0 + og3[3 * q + 1] * yp1 + og3[3 * q + 2] * yp2 - sg;
+            const double v = al * zt + om * zo[q] + uo[q];
+            const double zn = v > olo[q] ? v : olo[q];
+            zo[q] = zn; uo[q] = v - zn;
+            const double t = orh[q] * (zn - uo[q]);
+            if (live) { T4[(4 * o) * NS + k] = og3[3 * q] * t; T4[(4 * o + 1) * NS + k] = og3[3 * q + 1] * t; T4[(4 * o + 2) * NS + k] = og3[3 * q + 2] * t; T4[(4 * o + 3) * NS + k] = t; }
           }
         }
         // ---- box rows
@@ -1846,6 +1861,21 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             else { b[2] += t0; b[3] += t1; }
           }
         }
+        // ---- obstacle rows' contributions to the next right-hand side: positions (axis warps), slack inputs (warp 3)
+        if constexpr (R > 0) {
+          __syncthreads();
+          if constexpr (AX) {
+            double sgo = 0.0;
+#pragma unroll
+            for (int o = 0; o < R; ++o) sgo += T4[(4 * o + cc) * NS + k];
+            ogp = hasu ? sgo : 0.0;
+          } else {
+            double s0 = 0.0, s1 = 0.0;             // sum of t over the rows softened by sigma_d / sigma_s
+#pragma unroll
+            for (int o = 0; o < R; ++o) { const double t = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) s1 += t; else s0 += t; }
+            if (hasu) { b[2] -= s0; b[3] -= s1; }
+          }
+        }
       }
     };
 
@@ -1853,92 +1883,102 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     double s_ndy = 0.0, s_lhs = 0.0, s_ndx = 0.0, s_qd = 0.0, s_pm = 0.0;
     // ---- update_info (auxil.h:154) from registers, all warps; every thread ends with identical scalars
     auto info = [&](const int iter) {
-      // exchange: positions for the obstacle rows' A x, obstacle multipliers for the position columns' A' y
-      if constexpr (AX) { if (live) RA2[k * 3 + cc] = make_double2(x[0], x[1]); }
-      else {
-        double oy[3] = {0.0, 0.0, 0.0};
+      // cold per-row / per-variable data (E, D, P, previous iterate) first, so that the loads overlap the exchange
+      double er_[NVR], ed_[2], eo_[RW], dv_[NVR], pv_[NVR], oxv[NVR], oub_[NVR], oud_[2], ouo_[RW];
 #pragma unroll
-        for (int o = 0; o < RO; ++o) { const double yo = rho_[o] * uo[o]; oy[0] += g3(3 * o) * yo; oy[1] += g3(3 * o + 1) * yo; oy[2] += g3(3 * o + 2) * yo; }
-        if (live) { RS2[k * 2] = make_double2(oy[0], oy[1]); RS2[k * 2 + 1] = make_double2(oy[2], 0.0); }
+      for (int e = 0; e < NVR; ++e) {
+        const int j = vj(e);
+        er_[e] = WSE_(8 + j, k); dv_[e] = WSD_(j, k); pv_[e] = pd[k * NV + j]; oxv[e] = OX_(j, k); oub_[e] = OU_(8 + j, k);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) { ed_[t] = WSE_(di(t), k); oud_[t] = OU_(di(t), k); }
+#pragma unroll
+      for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp, oo = o < R ? o : 0; eo_[q] = WSE_(NBR + oo, k); ouo_[q] = OU_(NBR + oo, k); }
+      // exchange: positions for the obstacle rows' A x; obstacle multipliers for the position / slack-input columns' A' y
+      if constexpr (AX) { if (live) RA2[k * 3 + cc] = make_double2(x[0], x[1]); }
+      else { if (live) { XR[k] = x[2]; XR[NS + k] = x[3]; } }
+#pragma unroll
+      for (int q = 0; q < NOW; ++q) {
+        const int o = 4 * q + warp;
+        if (o < R && live) {
+          const double yo = orh[q] * uo[q];
+          T4[(4 * o) * NS + k] = og3[3 * q] * yo; T4[(4 * o + 1) * NS + k] = og3[3 * q + 1] * yo; T4[(4 * o + 2) * NS + k] = og3[3 * q + 2] * yo;
+          T4[(4 * o + 3) * NS + k] = yo;
+        }
       }
       __syncthreads();
       double mx[15], sm[3];
 #pragma unroll
       for (int e = 0; e < 15; ++e) mx[e] = 0.0;
       sm[0] = sm[1] = sm[2] = 0.0;
+      auto up = [&](double& mref, double v) { mref = v > mref ? v : mref; };      // max of non-negative, non-NaN values
       auto row = [&](double ax, double z, double e) {
         const double d = fabs(ax - z);
-        mx[0] = fmax(mx[0], d); mx[1] = fmax(mx[1], fabs(ax)); mx[2] = fmax(mx[2], fabs(z));
-        mx[3] = fmax(mx[3], e * d); mx[4] = fmax(mx[4], e * fabs(ax)); mx[5] = fmax(mx[5], e * fabs(z));
+        up(mx[0], d); up(mx[1], fabs(ax)); up(mx[2], fabs(z));
+        up(mx[3], e * d); up(mx[4], e * fabs(ax)); up(mx[5], e * fabs(z));
       };
       auto var = [&](double xv, double p, double cqv, double aty, double dj, double dxv) {
         const double px = c * p * xv;
         const double d = fabs(px + cqv + aty);
-        mx[6] = fmax(mx[6], d); mx[7] = fmax(mx[7], fabs(px)); mx[8] = fmax(mx[8], fabs(aty));
-        mx[9] = fmax(mx[9], dj * d); mx[10] = fmax(mx[10], dj * fabs(px)); mx[11] = fmax(mx[11], dj * fabs(aty));
-        if (live) sm[0] += (0.5 * p * xv + cqv * cinv) * xv;
+        up(mx[6], d); up(mx[7], fabs(px)); up(mx[8], fabs(aty));
+        up(mx[9], dj * d); up(mx[10], dj * fabs(px)); up(mx[11], dj * fabs(aty));
+        sm[0] += (0.5 * p * xv + cqv * cinv) * xv;
         // is_dual_infeasible screening (auxil.h:148): |dx|_inf, q'dx, |P dx|_inf
-        mx[13] = fmax(mx[13], fabs(dxv)); mx[14] = fmax(mx[14], fabs(c * p * dxv));
-        if (live) sm[2] += cqv * dxv;
+        up(mx[13], fabs(dxv)); up(mx[14], fabs(c * p * dxv));
+        sm[2] += cqv * dxv;
       };
       // is_primal_infeasible screening (auxil.h:137): projected delta_y, its norm and the support-function value
       auto cert = [&](double dy, double e, double lo_, double hi_) {
         const double ls = e * lo_, us = e * hi_;
-        if (us > kInfty * kMinScaling) { if (ls < -kInfty * kMinScaling) dy = 0.0; else dy = fmin(dy, 0.0); }
-        else if (ls < -kInfty * kMinScaling) dy = fmax(dy, 0.0);
-        mx[12] = fmax(mx[12], fabs(dy));
-        if (live) sm[1] += hi_ * fmax(dy, 0.0) + lo_ * fmin(dy, 0.0);
+        if (us > kInfty * kMinScaling) { if (ls < -kInfty * kMinScaling) dy = 0.0; else dy = dy < 0.0 ? dy : 0.0; }
+        else if (ls < -kInfty * kMinScaling) dy = dy > 0.0 ? dy : 0.0;
+        up(mx[12], fabs(dy));
+        sm[1] += hi_ * (dy > 0.0 ? dy : 0.0) + lo_ * (dy < 0.0 ? dy : 0.0);
       };
       const double yd0 = rhd[0] * ud[0], yd1 = rhd[1] * ud[1];
       const double yn0 = dn1(yd0), yn1 = dn1(yd1);
+      double aty[NVR];
       if constexpr (AX) {
         const double pp = up1(x[0] + apv * x[1] + bpa * x[2]), pv = up1(x[1] + bva * x[2]);
-        const double e0 = WSE_(cc, k), e1 = WSE_(3 + cc, k);
-        row((notfirst ? pp : 0.0) - x[0], zd[0], e0); row((notfirst ? pv : 0.0) - x[1], zd[1], e1);
-        cert(rhd[0] * (ud[0] - OU_(cc, k)), e0, bnd[0], bnd[0]); cert(rhd[1] * (ud[1] - OU_(3 + cc, k)), e1, bnd[1], bnd[1]);
-        double aty[3];
+        row((notfirst ? pp : 0.0) - x[0], zd[0], ed_[0]); row((notfirst ? pv : 0.0) - x[1], zd[1], ed_[1]);
         aty[0] = rhb[0] * ub[0] - yd0; aty[1] = rhb[1] * ub[1] - yd1; aty[2] = rhb[2] * ub[2];
-        if (hasu) { aty[0] += yn0 + m.RS[k * 4 + cc]; aty[1] += apv * yn0 + yn1; aty[2] += bpa * yn0 + bva * yn1; }
+        if (hasu) {
+          double gy = 0.0;
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const int j = vj(e);
-          if (e < 2 || hasu) {
-            const double ee = WSE_(8 + j, k);
-            row(x[e], zb[e], ee); cert(rhb[e] * (ub[e] - OU_(8 + j, k)), ee, blo(e), bhi(e));
-            var(x[e], pd[k * NV + j], cq[e], aty[e], WSD_(j, k), x[e] - OX_(j, k));
-          }
+          for (int o = 0; o < R; ++o) gy += T4[(4 * o + cc) * NS + k];
+          aty[0] += yn0 + gy; aty[1] += apv * yn0 + yn1; aty[2] += bpa * yn0 + bva * yn1;
         }
       } else {
-        const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4];
         const double q0 = up1(x[2]), q1 = up1(x[3]);
-        const double e0 = WSE_(6, k), e1 = WSE_(7, k);
-        row((notfirst ? q0 : 0.0) - x[0], zd[0], e0); row((notfirst ? q1 : 0.0) - x[1], zd[1], e1);
-        cert(rhd[0] * (ud[0] - OU_(6, k)), e0, bnd[0], bnd[0]); cert(rhd[1] * (ud[1] - OU_(7, k)), e1, bnd[1], bnd[1]);
-        double aty[4];
+        row((notfirst ? q0 : 0.0) - x[0], zd[0], ed_[0]); row((notfirst ? q1 : 0.0) - x[1], zd[1], ed_[1]);
         aty[0] = rhb[0] * ub[0] - yd0; aty[1] = rhb[1] * ub[1] - yd1; aty[2] = rhb[2] * ub[2]; aty[3] = rhb[3] * ub[3];
-        if (hasu) { aty[2] += yn0; aty[3] += yn1; }
+        if (hasu) {
+          aty[2] += yn0; aty[3] += yn1;
 #pragma unroll
-        for (int o = 0; o < RO; ++o) {
-          if (hasu) {
-            const double ee = WSE_(NBR + o, k), yo = rho_[o] * uo[o];
-            row(g3(3 * o) * x0v + g3(3 * o + 1) * x1v + g3(3 * o + 2) * x2v - (sl[o] ? x[3] : x[2]), zo[o], ee);
-            cert(rho_[o] * (uo[o] - OU_(NBR + o, k)), ee, lob(o), INFINITY);
-            if (sl[o]) aty[3] -= yo; else aty[2] -= yo;
-          }
+          for (int o = 0; o < R; ++o) { const double yo = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) aty[3] -= yo; else aty[2] -= yo; }
         }
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = vj(e);
-          if (e < 2 || hasu) {
-            const double ee = WSE_(8 + j, k);
-            row(x[e], zb[e], ee); cert(rhb[e] * (ub[e] - OU_(8 + j, k)), ee, blo(e), bhi(e));
-            var(x[e], pd[k * NV + j], cq[e], aty[e], WSD_(j, k), x[e] - OX_(j, k));
-          }
+      for (int q = 0; q < NOW; ++q) {
+        const int o = 4 * q + warp;
+        if (o < R && hasu) {
+          const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4], xs = XR[osl[q] * NS + k];
+          row(og3[3 * q] * x0v + og3[3 * q + 1] * x1v + og3[3 * q + 2] * x2v - xs, zo[q], eo_[q]);
+          cert(orh[q] * (uo[q] - ouo_[q]), eo_[q], olo[q], INFINITY);
+        }
+      }
+      cert(rhd[0] * (ud[0] - oud_[0]), ed_[0], bnd[0], bnd[0]); cert(rhd[1] * (ud[1] - oud_[1]), ed_[1], bnd[1], bnd[1]);
+#pragma unroll
+      for (int e = 0; e < NVR; ++e) {
+        if (e < 2 || hasu) {
+          row(x[e], zb[e], er_[e]); cert(rhb[e] * (ub[e] - oub_[e]), er_[e], blo(e), bhi(e));
+          var(x[e], pv_[e], cq[e], aty[e], dv_[e], x[e] - oxv[e]);
         }
       }
       if (!live) {                                // ghost lanes carry a meaningless copy of the last stage
 #pragma unroll
         for (int e = 0; e < 15; ++e) mx[e] = 0.0;
+        sm[0] = sm[1] = sm[2] = 0.0;
       }
       cta_reduce(mx, sm, warp);
       obj = sm[0];

@@ -29,6 +29,7 @@ struct AsmArgs {
   const double* obs_c; const double* obs_semi; const double* obs_yaw;   // [B][N][R][3], [B][N][R][3], [B][N][R]
   const double* lin_pt;         // [B][N][3]
   double* q; double* x0s; double* g; double* low;
+  int* hard;                    // [B] set when a stage-0 obstacle row is violated by the (fixed) current position
 };
 
 __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
@@ -58,8 +59,24 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
       const double fyy = 2 * xi / (sx * sx) * sn + 2 * eta / (sy * sy) * cs;
       const double fzz = 2 * (cz - oz) / (sz * sz);
       a.g[u * 3] = fxx; a.g[u * 3 + 1] = fyy; a.g[u * 3 + 2] = fzz;
-      a.low[u] = 1 - fxyz + fxx * cx + fyy * cy + fzz * cz;
+      const double lw = 1 - fxyz + fxx * cx + fyy * cy + fzz * cz;
+      a.low[u] = lw;
+      // Scheduling hint only (results do not depend on it): x_0 is pinned by the stage-0 equality, so a stage-0 obstacle
+      // row that the current position violates makes the QP infeasible; OSQP then runs to max_iter.  Such
+      // instances are started first so that they do not form the tail of the batch.
+      const int N_ = a.NS - 1;
+      if (bk % N_ == 0) {
+        const long long b = bk / N_;
+        if (fxx * a.x0[b * 6] + fyy * a.x0[b * 6 + 1] + fzz * a.x0[b * 6 + 2] < lw) a.hard[b] = 1;
+      }
     }
+  }
+}
+
+// Longest-first launch order: instances flagged `hard` take the front of the queue, the rest fill it from the back.
+__global__ void mpc_order_kernel(int B, const int* hard, int* order, int* cnt) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    if (hard[b]) order[atomicAdd(&cnt[0], 1)] = b; else order[B - 1 - atomicAdd(&cnt[1], 1)] = b;
   }
 }
 
@@ -77,7 +94,7 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
     if (lane == 0) b = atomicAdd(counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= bt.B) break;
-    qp.run(bt, b);
+    qp.run(bt, bt.order ? bt.order[b] : b);
   }
 }
 
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(128, 2) mpcqp_solve_cta_kernel(const __grid_co
     const int b = s_next;
     __syncthreads();
     if (b >= bt.B) break;
-    qp.run_cta(bt, b, warp, &s_flag);
+    qp.run_cta(bt, bt.order ? bt.order[b] : b, warp, &s_flag);
   }
 }
 
@@ -157,7 +174,7 @@ struct mpcqp_engine {
   std::string err;
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order;
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
 };
@@ -204,7 +221,7 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
 extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
   if (!e) return MPCQP_ERR_ARG;
   cudaSetDevice(e->device);
-  DevBuf* bufs[] = { &e->pd, &e->slack, &e->q, &e->x0s, &e->g, &e->low, &e->ws, &e->counter, &e->in_x0, &e->in_xref, &e->in_c,
+  DevBuf* bufs[] = { &e->pd, &e->slack, &e->q, &e->x0s, &e->g, &e->low, &e->ws, &e->counter, &e->hard, &e->order, &e->in_x0, &e->in_xref, &e->in_c,
                      &e->in_semi, &e->in_yaw, &e->in_lin, &e->in_warm, &e->out_x, &e->out_y, &e->out_i, &e->out_d };
   for (DevBuf* b : bufs) b->release();
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -293,7 +310,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   if (grid > bt.B) grid = bt.B;
   const int wsd = ws_doubles(sh.NS, sh.R, mode);
   CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
-  CK(e->counter.need(sizeof(int)));
+  CK(e->counter.need(4 * sizeof(int)));
   bt.ws = e->ws.as<double>();
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
   CK(cudaEventRecord(e->evs, e->stream));
@@ -328,6 +345,9 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   CK(e->x0s.need((size_t)B * 8 * sizeof(double)));
   CK(e->g.need((size_t)B * N * (R > 0 ? R : 1) * 3 * sizeof(double)));
   CK(e->low.need((size_t)B * N * (R > 0 ? R : 1) * sizeof(double)));
+  CK(e->hard.need((size_t)B * sizeof(int)));
+  CK(e->order.need((size_t)B * sizeof(int)));
+  CK(e->counter.need(4 * sizeof(int)));
   e->last_launches = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
   AsmArgs a;
@@ -335,6 +355,9 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   a.Qp[0] = a.Qp[1] = a.Qp[2] = p->position_weight;
   a.x0 = x0; a.xref = xref; a.obs_c = obs_c; a.obs_semi = obs_semi; a.obs_yaw = obs_yaw; a.lin_pt = lin_pt;
   a.q = e->q.as<double>(); a.x0s = e->x0s.as<double>(); a.g = e->g.as<double>(); a.low = e->low.as<double>();
+  a.hard = e->hard.as<int>();
+  CK(cudaMemsetAsync(e->hard.p, 0, (size_t)B * sizeof(int), e->stream));
+  CK(cudaMemsetAsync(e->counter.p, 0, 4 * sizeof(int), e->stream));
   {
     long long total = (long long)B * sh.n + (long long)B * 8 + (long long)B * N * R;
     long long blocks = (total + 255) / 256;
@@ -342,12 +365,14 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
     if (blocks > cap) blocks = cap;
     mpc_assemble_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(a);
     CK(cudaGetLastError());
-    e->last_launches += 1;
+    mpc_order_kernel<<<(unsigned)((B + 255) / 256 < cap ? (B + 255) / 256 : cap), 256, 0, e->stream>>>(B, a.hard, e->order.as<int>(), e->counter.as<int>() + 1);
+    CK(cudaGetLastError());
+    e->last_launches += 2;
   }
   Batch bt; memset(&bt, 0, sizeof bt);
   bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
   bt.warm_x = warm_x; bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates;
-  bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B;
+  bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>();
   rc = launch_solve(e, sh, st, bt); if (rc) return rc;
   CK(cudaEventRecord(e->ev1, e->stream));
   return MPCQP_OK;
