@@ -80,7 +80,10 @@ struct Batch {              // device pointers
   int* status; int* iter; int* rho_updates;
   double* obj; double* pri_res; double* dua_res;
   double* ws;                   // per-warp scratch, ws_doubles(shape) each
-  const int* order;             // [B] processing order (longest-first hint) or nullptr
+  const int* order;             // [nhard] indices of the instances flagged hard, or nullptr
+  const int* hard;              // [B] hard flags, or nullptr
+  const int* nhard;             // number of hard instances (device scalar), or nullptr
+  int queue;                    // 0: one queue over all B; 1: hard instances only; 2: the others only
   int B;
 };
 

@@ -73,10 +73,10 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
   }
 }
 
-// Longest-first launch order: instances flagged `hard` take the front of the queue, the rest fill it from the back.
+// Compacts the indices of the instances flagged `hard` into order[0 .. cnt[0]).
 __global__ void mpc_order_kernel(int B, const int* hard, int* order, int* cnt) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-    if (hard[b]) order[atomicAdd(&cnt[0], 1)] = b; else order[B - 1 - atomicAdd(&cnt[1], 1)] = b;
+    if (hard[b]) order[atomicAdd(&cnt[0], 1)] = b;
   }
 }
 
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
     if (lane == 0) b = atomicAdd(counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= bt.B) break;
-    qp.run(bt, bt.order ? bt.order[b] : b);
+    qp.run(bt, b);
   }
 }
 
@@ -107,12 +107,17 @@ __global__ void __launch_bounds__(128, 2) mpcqp_solve_cta_kernel(const __grid_co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Qp<30, RT, kModeCta> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
   for (;;) {
-    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+    if (threadIdx.x == 0) s_next = atomicAdd(counter + (bt.queue == 2 ? 3 : 0), 1);
     __syncthreads();
-    const int b = s_next;
+    const int idx = s_next;
     __syncthreads();
-    if (b >= bt.B) break;
-    qp.run_cta(bt, bt.order ? bt.order[b] : b, warp, &s_flag);
+    int b = idx;
+    if (bt.queue == 1) { if (idx >= *bt.nhard) break; b = bt.order[idx]; }
+    else {
+      if (idx >= bt.B) break;
+      if (bt.queue == 2 && bt.hard[idx]) continue;       // solved by the other launch
+    }
+    qp.run_cta(bt, b, warp, &s_flag);
   }
 }
 
@@ -169,8 +174,9 @@ struct DevBuf {
 
 struct mpcqp_engine {
   int device = 0, num_sms = 0, max_smem_optin = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;          // main stream; side stream for the second solve launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
+  cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
   // structured-problem buffers (device)
@@ -213,6 +219,8 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
   e->num_sms = pr.multiProcessorCount;
   e->max_smem_optin = (int)pr.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->evf, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->evj, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreate(&e->evs) != cudaSuccess) { delete e; return MPCQP_ERR_CUDA; }
   *out = e;
   return MPCQP_OK;
@@ -227,6 +235,9 @@ extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs) cudaEventDestroy(e->evs);
+  if (e->evf) cudaEventDestroy(e->evf);
+  if (e->evj) cudaEventDestroy(e->evj);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return MPCQP_OK;
@@ -309,15 +320,51 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   long long grid = (long long)e->num_sms * occ;
   if (grid > bt.B) grid = bt.B;
   const int wsd = ws_doubles(sh.NS, sh.R, mode);
-  CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
   CK(e->counter.need(4 * sizeof(int)));
-  bt.ws = e->ws.as<double>();
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
+  e->last_fast = mode;
+  bt.queue = 0; bt.nhard = nullptr;
+  if (mode != kModeCta) { bt.order = nullptr; bt.hard = nullptr; }
+  if (mode == kModeCta) {
+    // A CTA that has an SM to itself iterates ~1.5x faster than two sharing one.  Small batches therefore run one CTA
+    // per SM (the launch asks for the whole shared memory of the SM).  Larger batches run as two concurrent launches:
+    // the instances flagged hard (they run to max_iter and would otherwise form the tail of the batch) one per SM on
+    // the main stream, everything else two per SM on the side stream, on whatever SMs the first launch leaves free.
+    const size_t smem_solo = (size_t)e->max_smem_optin - 2048;   // more than half an SM: nothing else fits beside it
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
+    if (bt.B <= e->num_sms || !bt.order) {
+      const bool solo = bt.B <= e->num_sms;
+      CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
+      bt.ws = e->ws.as<double>();
+      CK(cudaEventRecord(e->evs, e->stream));
+      kern<<<(unsigned)grid, threads, solo ? smem_solo : smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+      CK(cudaGetLastError());
+      e->last_launches += 1;
+      return MPCQP_OK;
+    }
+    const long long gh = e->num_sms < bt.B ? e->num_sms : bt.B;
+    CK(e->ws.need((size_t)(grid + gh) * wsd * sizeof(double)));
+    bt.nhard = e->counter.as<int>() + 1;
+    CK(cudaEventRecord(e->evs, e->stream));
+    CK(cudaEventRecord(e->evf, e->stream));
+    CK(cudaStreamWaitEvent(e->stream2, e->evf, 0));
+    Batch bh = bt; bh.queue = 1; bh.ws = e->ws.as<double>();
+    kern<<<(unsigned)gh, threads, smem_solo, e->stream>>>(sh, st, bh, wsd, e->counter.as<int>());
+    CK(cudaGetLastError());
+    Batch bn = bt; bn.queue = 2; bn.ws = e->ws.as<double>() + (size_t)gh * wsd;
+    kern<<<(unsigned)grid, threads, smem, e->stream2>>>(sh, st, bn, wsd, e->counter.as<int>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->evj, e->stream2));
+    CK(cudaStreamWaitEvent(e->stream, e->evj, 0));
+    e->last_launches += 2;
+    return MPCQP_OK;
+  }
+  CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
+  bt.ws = e->ws.as<double>();
   CK(cudaEventRecord(e->evs, e->stream));
   kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
   CK(cudaGetLastError());
   e->last_launches += 1;
-  e->last_fast = mode;
   return MPCQP_OK;
 }
 
@@ -372,7 +419,7 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   Batch bt; memset(&bt, 0, sizeof bt);
   bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
   bt.warm_x = warm_x; bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates;
-  bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>();
+  bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>(); bt.hard = e->hard.as<int>();
   rc = launch_solve(e, sh, st, bt); if (rc) return rc;
   CK(cudaEventRecord(e->ev1, e->stream));
   return MPCQP_OK;
