@@ -528,3 +528,263 @@ extern "C" int mpcqp_fp64_fma_peak(mpcqp_engine* e, double* tflops) {
   *tflops = best;
   return MPCQP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// (3) OSQP-shaped single problem with explicit CSC data (what OsqpEigen::Solver hands to osqp_setup,
+// OsqpEigen/Data.tpp:38-39,77; osqp.h:58).  The problem must have the mpcPlanner stage structure
+// (mpcPlanner.cpp:932-1146); it is parsed on the host into the structured form the kernels take and solved
+// by the same kernels as a batch of one.  There is no generic (unstructured) kernel and no host solve.
+// ------------------------------------------------------------------------------------------------
+struct mpcqp_problem {
+  mpcqp_engine* e = nullptr;
+  Shape sh; Settings st; mpcqp_settings user;
+  std::vector<double> pd, q, x0, g, low, warm_x, warm_y, sol_x, sol_y;
+  std::vector<unsigned char> slack;
+  bool has_wx = false, has_wy = false, solved = false;
+  mpcqp_info info;
+  DevBuf d_pd, d_slack, d_q, d_x0, d_g, d_low, d_wx, d_wy, d_x, d_y, d_i, d_d;
+};
+
+namespace {
+const double kBoundInf = 1e20;     // OSQP_INFTY is 1e30 (constants.h:78); IEEE inf is what the reference passes
+
+// l / u of the stage structure -> x0, stage-uniform box, obstacle lower bounds.  Returns 0 or an error code.
+int parse_bounds(const Shape& sh, const double* l, const double* u, double* x0, double* blo, double* bhi, double* low, std::string* err) {
+  const int NS = sh.NS, N = NS - 1, R = sh.R;
+  for (int i = 0; i < sh.m; ++i) if (l[i] > u[i]) { *err = "lower bound > upper bound at row " + std::to_string(i); return MPCQP_ERR_DATA; }
+  for (int i = 0; i < 8 * NS; ++i) {
+    if (l[i] != u[i]) { *err = "dynamics row " + std::to_string(i) + " is not an equality"; return MPCQP_ERR_STRUCTURE; }
+    if (i < 8) x0[i] = -l[i]; else if (l[i] != 0.0) { *err = "dynamics row " + std::to_string(i) + " has a non-zero right-hand side"; return MPCQP_ERR_STRUCTURE; }
+  }
+  for (int k = 0; k < NS; ++k) for (int j = 0; j < 8; ++j) {
+    const int i = 8 * NS + 8 * k + j;
+    if (k == 0) { blo[j] = l[i]; bhi[j] = u[i]; }
+    else if (l[i] != blo[j] || u[i] != bhi[j]) { *err = "state box is not stage-uniform (row " + std::to_string(i) + ")"; return MPCQP_ERR_STRUCTURE; }
+  }
+  for (int k = 0; k < N; ++k) for (int j = 0; j < 5; ++j) {
+    const int i = 16 * NS + 5 * k + j;
+    if (k == 0) { blo[8 + j] = l[i]; bhi[8 + j] = u[i]; }
+    else if (l[i] != blo[8 + j] || u[i] != bhi[8 + j]) { *err = "input box is not stage-uniform (row " + std::to_string(i) + ")"; return MPCQP_ERR_STRUCTURE; }
+  }
+  for (int k = 0; k < N; ++k) for (int o = 0; o < R; ++o) {
+    const int i = 16 * NS + 5 * N + k * R + o;
+    if (!(u[i] >= kBoundInf)) { *err = "obstacle row " + std::to_string(i) + " has a finite upper bound"; return MPCQP_ERR_STRUCTURE; }
+    low[k * R + o] = l[i];
+  }
+  return MPCQP_OK;
+}
+
+bool set_coef(double* slot, bool* seen, double v) { if (!*seen) { *slot = v; *seen = true; return true; } return *slot == v; }
+
+int parse_structure(int64_t n, int64_t m, const int64_t* Pp, const int64_t* Pi, const double* Px, const int64_t* Ap, const int64_t* Ai,
+                    const double* Ax, Shape* sh, std::vector<double>* pd, std::vector<unsigned char>* slack, std::vector<double>* g,
+                    std::string* err) {
+  if (n < 34 || (n + 5) % 13 != 0) { *err = "n is not 8*horizon + 5*(horizon-1)"; return MPCQP_ERR_STRUCTURE; }
+  const int NS = (int)((n + 5) / 13), N = NS - 1;
+  const int64_t mr = m - 16 * NS - 5 * N;
+  if (mr < 0 || mr % N != 0) { *err = "m is not 16*horizon + 5*(horizon-1) + num_obs*(horizon-1) (field-of-view half-space rows are not supported)"; return MPCQP_ERR_STRUCTURE; }
+  const int R = (int)(mr / N);
+  sh->NS = NS; sh->R = R; sh->n = (int)n; sh->m = (int)m;
+  pd->assign((size_t)NS * 13, 0.0);
+  auto stage_slot = [&](int64_t v) { return v < 8 * NS ? (int)(v / 8) * 13 + (int)(v % 8) : (int)((v - 8 * NS) / 5) * 13 + 8 + (int)((v - 8 * NS) % 5); };
+  for (int64_t j = 0; j < n; ++j) for (int64_t t = Pp[j]; t < Pp[j + 1]; ++t) {
+    if (Pi[t] != j) { if (Px[t] == 0.0) continue; *err = "P is not diagonal"; return MPCQP_ERR_STRUCTURE; }
+    if (Px[t] < 0.0) { *err = "P has a negative diagonal entry"; return MPCQP_ERR_DATA; }
+    (*pd)[stage_slot(j)] = Px[t];
+  }
+  slack->assign((size_t)N * (R > 0 ? R : 1), 255);
+  g->assign((size_t)N * (R > 0 ? R : 1) * 3, 0.0);
+  bool s_apv = false, s_bpa = false, s_bva = false;
+  const int64_t base = 16 * NS + 5 * N;
+  std::vector<char> have_neg((size_t)8 * NS, 0), have_id((size_t)n, 0);
+  auto bad = [&](int64_t j, int64_t r) { *err = "A(" + std::to_string(r) + "," + std::to_string(j) + ") does not belong to the mpcPlanner constraint structure"; return MPCQP_ERR_STRUCTURE; };
+  for (int64_t j = 0; j < n; ++j) {
+    const bool is_state = j < 8 * NS;
+    const int k = is_state ? (int)(j / 8) : (int)((j - 8 * NS) / 5), c = is_state ? (int)(j % 8) : (int)((j - 8 * NS) % 5);
+    for (int64_t t = Ap[j]; t < Ap[j + 1]; ++t) {
+      const int64_t r = Ai[t]; const double v = Ax[t];
+      if (r < 0 || r >= m) { *err = "row index out of range"; return MPCQP_ERR_DATA; }
+      if (v == 0.0) continue;
+      if (r == 8 * NS + j) { if (v != 1.0) return bad(j, r); have_id[j] = 1; continue; }
+      if (r >= base) {                                   // obstacle row of stage k only
+        const int64_t kk = (r - base) / (R > 0 ? R : 1), o = (r - base) % (R > 0 ? R : 1);
+        if (R == 0 || kk != k || k >= N) return bad(j, r);
+        if (is_state) { if (c > 2) return bad(j, r); (*g)[(kk * R + o) * 3 + c] = v; }
+        else { if (c < 3 || v != -1.0 || (*slack)[kk * R + o] != 255) return bad(j, r); (*slack)[kk * R + o] = (unsigned char)(c - 3); }
+        continue;
+      }
+      if (r >= 8 * NS) return bad(j, r);
+      const int rk = (int)(r / 8), ri = (int)(r % 8);
+      if (is_state) {
+        if (rk == k) { if (ri != c || v != -1.0) return bad(j, r); have_neg[r] = 1; continue; }
+        if (rk != k + 1) return bad(j, r);
+        if (c < 6 && ri == c) { if (v != 1.0) return bad(j, r); continue; }                 // Ad diagonal
+        if (c >= 3 && c < 6 && ri == c - 3) { if (!set_coef(&sh->a_pv, &s_apv, v)) return bad(j, r); continue; }
+        return bad(j, r);
+      }
+      if (rk != k + 1) return bad(j, r);
+      if (c < 3 && ri == c) { if (!set_coef(&sh->b_pa, &s_bpa, v)) return bad(j, r); continue; }
+      if (c < 3 && ri == 3 + c) { if (!set_coef(&sh->b_va, &s_bva, v)) return bad(j, r); continue; }
+      if (c >= 3 && ri == 3 + c) { if (v != 1.0) return bad(j, r); continue; }
+      return bad(j, r);
+    }
+  }
+  for (size_t i = 0; i < have_neg.size(); ++i) if (!have_neg[i]) { *err = "dynamics row " + std::to_string(i) + " lacks its -1 entry"; return MPCQP_ERR_STRUCTURE; }
+  for (int64_t j = 0; j < n; ++j) if (!have_id[j]) { *err = "box row of variable " + std::to_string(j) + " is missing"; return MPCQP_ERR_STRUCTURE; }
+  for (int i = 0; i < N * R; ++i) if ((*slack)[i] == 255) { *err = "obstacle row " + std::to_string(i) + " has no slack entry"; return MPCQP_ERR_STRUCTURE; }
+  if (!s_apv) sh->a_pv = 0.0;
+  if (!s_bpa) sh->b_pa = 0.0;
+  if (!s_bva) sh->b_va = 0.0;
+  return MPCQP_OK;
+}
+}  // namespace
+
+extern "C" int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int64_t m, const int64_t* P_colptr,
+                           const int64_t* P_rowidx, const double* P_val, const double* q, const int64_t* A_colptr,
+                           const int64_t* A_rowidx, const double* A_val, const double* l, const double* u,
+                           const mpcqp_settings* s) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (!out) { e->err = "null out pointer"; return MPCQP_ERR_ARG; }
+  *out = nullptr;
+  if (n <= 0 || m < 0 || !P_colptr || !q || !A_colptr || (m > 0 && (!l || !u))) { e->err = "null array or non-positive size"; return MPCQP_ERR_DATA; }
+  const auto t0 = std::chrono::steady_clock::now();
+  mpcqp_problem* pr = new mpcqp_problem();
+  pr->e = e;
+  int rc = check_settings(e, s, &pr->st);
+  if (rc) { delete pr; return rc; }
+  pr->user = *s;
+  rc = parse_structure(n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, A_val, &pr->sh, &pr->pd, &pr->slack, &pr->g, &e->err);
+  if (rc) { delete pr; return rc; }
+  const int NS = pr->sh.NS, N = NS - 1, R = pr->sh.R;
+  pr->x0.assign(8, 0.0); pr->low.assign((size_t)N * (R > 0 ? R : 1), 0.0);
+  rc = parse_bounds(pr->sh, l, u, pr->x0.data(), pr->sh.blo, pr->sh.bhi, pr->low.data(), &e->err);
+  if (rc) { delete pr; return rc; }
+  pr->q.assign(q, q + n);
+  pr->sol_x.assign((size_t)n, 0.0); pr->sol_y.assign((size_t)m, 0.0);
+  memset(&pr->info, 0, sizeof pr->info);
+  pr->info.status_val = MPCQP_UNSOLVED;
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t r = b.need(bytes ? bytes : 8); if (r != cudaSuccess) return r;
+    return bytes ? cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream) : cudaSuccess;
+  };
+  cudaError_t ce = cudaSetDevice(e->device);
+  if (ce == cudaSuccess) ce = up(pr->d_pd, pr->pd.data(), pr->pd.size() * sizeof(double));
+  if (ce == cudaSuccess) ce = up(pr->d_slack, pr->slack.data(), pr->slack.size());
+  if (ce == cudaSuccess) ce = up(pr->d_q, pr->q.data(), pr->q.size() * sizeof(double));
+  if (ce == cudaSuccess) ce = up(pr->d_x0, pr->x0.data(), 8 * sizeof(double));
+  if (ce == cudaSuccess) ce = up(pr->d_g, pr->g.data(), pr->g.size() * sizeof(double));
+  if (ce == cudaSuccess) ce = up(pr->d_low, pr->low.data(), pr->low.size() * sizeof(double));
+  if (ce == cudaSuccess) ce = pr->d_x.need((size_t)n * sizeof(double));
+  if (ce == cudaSuccess) ce = pr->d_y.need((size_t)(m > 0 ? m : 1) * sizeof(double));
+  if (ce == cudaSuccess) ce = pr->d_i.need(3 * sizeof(int32_t));
+  if (ce == cudaSuccess) ce = pr->d_d.need(3 * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) { e->err = std::string("mpcqp_setup: ") + cudaGetErrorString(ce); mpcqp_cleanup(pr); return MPCQP_ERR_CUDA; }
+  pr->info.setup_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *out = pr;
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_warm_start(mpcqp_problem* pr, const double* x, const double* y) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  if (!x || !y) { pr->e->err = "null warm start"; return MPCQP_ERR_ARG; }
+  pr->warm_x.assign(x, x + pr->sh.n); pr->warm_y.assign(y, y + pr->sh.m);
+  pr->has_wx = pr->has_wy = true;
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_warm_start_x(mpcqp_problem* pr, const double* x) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  if (!x) { pr->e->err = "null warm start"; return MPCQP_ERR_ARG; }
+  pr->warm_x.assign(x, x + pr->sh.n);
+  pr->has_wx = true;
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_update_lin_cost(mpcqp_problem* pr, const double* q_new) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  mpcqp_engine* e = pr->e;
+  if (!q_new) { e->err = "null q"; return MPCQP_ERR_ARG; }
+  pr->q.assign(q_new, q_new + pr->sh.n);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(pr->d_q.p, pr->q.data(), pr->q.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_update_bounds(mpcqp_problem* pr, const double* l_new, const double* u_new) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  mpcqp_engine* e = pr->e;
+  if (!l_new || !u_new) { e->err = "null bounds"; return MPCQP_ERR_ARG; }
+  Shape sh = pr->sh; std::vector<double> x0(8), low(pr->low.size());
+  int rc = parse_bounds(sh, l_new, u_new, x0.data(), sh.blo, sh.bhi, low.data(), &e->err);
+  if (rc) return rc;
+  pr->sh = sh; pr->x0 = x0; pr->low = low;
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(pr->d_x0.p, pr->x0.data(), 8 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  if (!pr->low.empty() && pr->sh.R > 0) CK(cudaMemcpyAsync(pr->d_low.p, pr->low.data(), pr->low.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_solve(mpcqp_problem* pr) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  mpcqp_engine* e = pr->e;
+  const int n = pr->sh.n, m = pr->sh.m;
+  const auto t0 = std::chrono::steady_clock::now();
+  CK(cudaSetDevice(e->device));
+  // osqp_solve starts from the workspace iterates: an explicit warm start if one was given, else the previous
+  // solution (OSQP keeps its iterates between solves when settings->warm_start is on), else zeros.
+  const bool ws = pr->st.warm_start != 0;
+  const double* wx = nullptr; const double* wy = nullptr;
+  if (ws && pr->has_wx) wx = pr->warm_x.data(); else if (ws && pr->solved) wx = pr->sol_x.data();
+  if (ws && pr->has_wy) wy = pr->warm_y.data(); else if (ws && pr->solved && !pr->has_wx) wy = pr->sol_y.data();
+  if (wx) { CK(pr->d_wx.need((size_t)n * sizeof(double))); CK(cudaMemcpyAsync(pr->d_wx.p, wx, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream)); }
+  if (wy && m > 0) { CK(pr->d_wy.need((size_t)m * sizeof(double))); CK(cudaMemcpyAsync(pr->d_wy.p, wy, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, e->stream)); }
+  Batch bt; memset(&bt, 0, sizeof bt);
+  bt.pd = pr->d_pd.as<double>(); bt.slack = pr->d_slack.as<unsigned char>(); bt.q = pr->d_q.as<double>(); bt.x0 = pr->d_x0.as<double>();
+  bt.g = pr->d_g.as<double>(); bt.low = pr->d_low.as<double>();
+  bt.warm_x = wx ? pr->d_wx.as<double>() : nullptr; bt.warm_y = (wy && m > 0) ? pr->d_wy.as<double>() : nullptr;
+  bt.x = pr->d_x.as<double>(); bt.y = pr->d_y.as<double>();
+  int32_t* di = pr->d_i.as<int32_t>(); double* dd = pr->d_d.as<double>();
+  bt.status = di; bt.iter = di + 1; bt.rho_updates = di + 2; bt.obj = dd; bt.pri_res = dd + 1; bt.dua_res = dd + 2; bt.B = 1;
+  e->last_launches = 0;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  int rc = launch_solve(e, pr->sh, pr->st, bt); if (rc) return rc;
+  CK(cudaEventRecord(e->ev1, e->stream));
+  int32_t hi[3]; double hd[3];
+  CK(cudaMemcpyAsync(pr->sol_x.data(), pr->d_x.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (m > 0) CK(cudaMemcpyAsync(pr->sol_y.data(), pr->d_y.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(hi, di, sizeof hi, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(hd, dd, sizeof hd, cudaMemcpyDeviceToHost, e->stream));
+  rc = mpcqp_engine_sync(e); if (rc) return rc;
+  pr->info.status_val = hi[0]; pr->info.iter = hi[1]; pr->info.rho_updates = hi[2];
+  pr->info.obj_val = hd[0]; pr->info.pri_res = hd[1]; pr->info.dua_res = hd[2];
+  pr->info.solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  pr->solved = true; pr->has_wx = pr->has_wy = false;
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_get_info(const mpcqp_problem* pr, mpcqp_info* info) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  if (!info) return MPCQP_ERR_ARG;
+  *info = pr->info;
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_get_solution(const mpcqp_problem* pr, double* x, double* y) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  if (!pr->solved) { pr->e->err = "no solution yet: call mpcqp_solve first"; return MPCQP_ERR_NOT_INIT; }
+  if (x) memcpy(x, pr->sol_x.data(), pr->sol_x.size() * sizeof(double));
+  if (y) memcpy(y, pr->sol_y.data(), pr->sol_y.size() * sizeof(double));
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_cleanup(mpcqp_problem* pr) {
+  if (!pr) return MPCQP_ERR_NOT_INIT;
+  cudaSetDevice(pr->e->device);
+  DevBuf* bufs[] = { &pr->d_pd, &pr->d_slack, &pr->d_q, &pr->d_x0, &pr->d_g, &pr->d_low, &pr->d_wx, &pr->d_wy, &pr->d_x, &pr->d_y, &pr->d_i, &pr->d_d };
+  for (DevBuf* b : bufs) b->release();
+  delete pr;
+  return MPCQP_OK;
+}
