@@ -175,6 +175,7 @@ def run_b200(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     solve_ms = []
+    launches = 0
     for a, b in evs:
         with torch.cuda.stream(stream):
             flush.zero_()                                  # L2 flush, outside the timed pair
@@ -184,6 +185,7 @@ def run_b200(args, rank, world, local_rank):
             b.record(stream)
         eng.sync()
         solve_ms.append(eng.last_solve_kernel_ms)
+        launches += eng.last_launches
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -215,7 +217,10 @@ def run_b200(args, rank, world, local_rank):
     e2e_s = float(t.item())
     h2d = sum(v.numel() * v.element_size() for v in pin.values())
     d2h = sum(v.numel() * v.element_size() for v in pout.values())
-    assert np.array_equal(pout["iter"].numpy(), iters), "host and device entry points disagree"
+    if not np.array_equal(pout["iter"].numpy(), iters):
+        bad = np.where(pout["iter"].numpy() != iters)[0]
+        raise SystemExit(f"bench.py: host and device entry points disagree on {len(bad)} instances, e.g. {bad[:8]}: "
+                         f"host {pout['iter'].numpy()[bad[:8]]} device {iters[bad[:8]]}")
 
     # ---- verification gather (NCCL over NVLink; not on the solve path, not timed into `value`) ------------
     gather_ms = None
@@ -254,6 +259,37 @@ def run_b200(args, rank, world, local_rank):
     except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU number
         parity = {"error": repr(ex)}
 
+    # ---- explanatory extras (device-resident inputs, untimed above): throughput on a batch large enough to fill the GPU,
+    # and the latency of single QPs (B = 1: one CTA on an otherwise idle GPU), the "p50 per-QP latency" of the metric
+    extras = {}
+    try:
+        # the headline again with the iteration-count history switched off (what a first, cold call gets)
+        eng.use_history(False)
+        msc = []
+        for _ in range(min(K, 5)):
+            step_device(); eng.sync(); msc.append(eng.last_kernel_ms)
+        eng.use_history(True)
+        extras["headline_without_history"] = {"value": B / (float(np.mean(msc)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(msc)),
+                                              "note": "same batch, scheduling hint from the previous call disabled"}
+        Bl = 16384
+        ml = W.static_batch(Bl, num_obs=R, seed0=100000 + rank * Bl)
+        outl = eng.solve_mpc_batch(ml)
+        msl = []
+        for _ in range(3):
+            eng.solve_mpc_batch(ml, out=outl); msl.append(eng.last_kernel_ms)
+        extras["large_batch"] = {"batch_per_gpu": Bl, "value": Bl / (min(msl) * 1e-3), "unit": UNIT, "ms_per_batch": min(msl),
+                                 "iterations_total": int(outl["iter"].sum()),
+                                 "fp64_tflops": float(algorithmic_flops(N, R, outl["iter"], outl["rho_updates"]).sum()) / (min(msl) * 1e-3) / 1e12,
+                                 "note": "device kernels only (assembly + solve), one GPU, not the headline"}
+        lat = []
+        for i in range(48):
+            m1 = mb.slice(i, i + 1)
+            eng.solve_mpc_batch(m1); lat.append(eng.last_kernel_ms)
+        lat = np.sort(np.array(lat))
+        extras["single_qp_latency_ms"] = {"p50": float(lat[len(lat) // 2]), "p90": float(lat[int(0.9 * len(lat))]), "max": float(lat[-1]), "samples": len(lat)}
+    except Exception as ex:
+        extras["error"] = repr(ex)
+
     flops = float(algorithmic_flops(N, R, iters, rhou).sum())
     solve_avg_ms = float(np.mean(solve_ms))
     ach_tf = flops / (solve_avg_ms * 1e-3) / 1e12
@@ -270,10 +306,11 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(B, R), "batch_per_gpu": B, "num_obs": R, "horizon": p.horizon,
                    "pins": "adaptive_rho_interval=25,time_limit=0", "l2": "flushed between steps (256 MiB write)",
+                   "schedule": "slots that ran >= 500 iterations in the previous call start first, one per SM (receding-horizon hint; results do not depend on it)",
                    "kernel_path": eng.last_path, "iterations_total": int(iters.sum()), "iterations_max": int(iters.max())},
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / K},
-        "gpu_launches": 2 * K,
+        "gpu_launches": int(launches),
         "p50_latency_ms": float(np.median(solve_ms)),
         "status_hist": _hist(status),
         "roofline": {"bound": "fp64_fma", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
@@ -282,7 +319,7 @@ def run_b200(args, rank, world, local_rank):
                      "algorithmic_flops_per_launch": flops,
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"}},
-        "cpu_baseline": cpu, "parity": parity, "clocks": sampler.summary(),
+        "cpu_baseline": cpu, "parity": parity, "clocks": sampler.summary(), "extras": extras,
     }
     if gather_ms is not None:
         line["verification_gather_ms"] = gather_ms

@@ -88,6 +88,10 @@ int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
  * one-warp register kernel, (0) restores the default dispatch (used by the tests to cover all three). */
 int mpcqp_engine_last_path(const mpcqp_engine* e);
 int mpcqp_engine_force_generic(mpcqp_engine* e, int on);
+/* Scheduling hint (default on): the batched entry point remembers how many iterations each batch slot took and, when
+ * the next call has the same batch size and num_obs (a receding-horizon loop: slot b is the same scenario one control
+ * step later), starts the slots that ran long first, one per SM.  Results never depend on it.  0 switches it off. */
+int mpcqp_engine_use_history(mpcqp_engine* e, int on);
 /* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */
 int mpcqp_engine_sync(mpcqp_engine* e);
 /* FP64 FMA-pipe microbenchmark (all SMs, 8 independent DFMA chains per thread): the measured roofline

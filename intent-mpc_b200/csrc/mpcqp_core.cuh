@@ -1897,7 +1897,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       for (int t = 0; t < 2; ++t) { ed_[t] = WSE_(di(t), k); oud_[t] = OU_(di(t), k); }
 #pragma unroll
       for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp, oo = o < R ? o : 0; eo_[q] = WSE_(NBR + oo, k); ouo_[q] = OU_(NBR + oo, k); }
-      // exchange: positions for the obstacle rows' A x; obstacle multipliers for the position / slack-input columns' A' y
+      // exchange: positions for the obstacle rows' A x; obstacle multipliers for the position / slack-input columns' A' y.
+      // The buffers are the iteration's: wait until every warp has consumed the last iteration's obstacle terms.
+      __syncthreads();
       if constexpr (AX) { if (live) RA2[k * 3 + cc] = make_double2(x[0], x[1]); }
       else { if (live) { XR[k] = x[2]; XR[NS + k] = x[3]; } }
 #pragma unroll

@@ -30,6 +30,7 @@ struct AsmArgs {
   const double* lin_pt;         // [B][N][3]
   double* q; double* x0s; double* g; double* low;
   int* hard;                    // [B] set when a stage-0 obstacle row is violated by the (fixed) current position
+  const int* hist; int hist_thresh;   // iterations each slot took in the previous call (or null): >= thresh -> hard
 };
 
 __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
@@ -45,6 +46,9 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
     } else if (t < nq + n0) {                       // x0 = [pos, vel, 0, 0]           (MP.cpp:401-408)
       const long long u = t - nq; const int b = (int)(u >> 3), j = (int)(u & 7);
       a.x0s[u] = j < 6 ? a.x0[(long long)b * 6 + j] : 0.0;
+      // Scheduling hint only: in receding-horizon use slot b of consecutive calls is the same scenario one control
+      // step later, so a slot that ran long last time very likely runs long again.
+      if (j == 0 && a.hist && a.hist[b] >= a.hist_thresh) a.hard[b] = 1;
     } else {                                        // obstacle rows                   (MP.cpp:1040-1071, 1114-1139)
       const long long u = t - nq - n0;
       const long long bk = u / a.R;                 // b*N + k
@@ -106,16 +110,21 @@ __global__ void __launch_bounds__(128, 2) mpcqp_solve_cta_kernel(const __grid_co
   __shared__ int s_next, s_flag;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Qp<30, RT, kModeCta> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  // queue 0: all instances in natural order.  queue 1: the hard list only.  queue 2: everything not flagged hard, then
+  // whatever is left of the hard list (so an over-long hard list does not serialise on the one-per-SM launch).
+  bool natural = bt.queue != 1;
   for (;;) {
-    if (threadIdx.x == 0) s_next = atomicAdd(counter + (bt.queue == 2 ? 3 : 0), 1);
+    if (threadIdx.x == 0) s_next = atomicAdd(counter + ((natural && bt.queue == 2) ? 3 : 0), 1);
     __syncthreads();
     const int idx = s_next;
     __syncthreads();
     int b = idx;
-    if (bt.queue == 1) { if (idx >= *bt.nhard) break; b = bt.order[idx]; }
-    else {
-      if (idx >= bt.B) break;
-      if (bt.queue == 2 && bt.hard[idx]) continue;       // solved by the other launch
+    if (natural) {
+      if (idx >= bt.B) { if (bt.queue == 2) { natural = false; continue; } break; }
+      if (bt.queue == 2 && bt.hard[idx]) continue;       // on the hard list
+    } else {
+      if (idx >= *bt.nhard) break;
+      b = bt.order[idx];
     }
     qp.run_cta(bt, b, warp, &s_flag);
   }
@@ -180,7 +189,8 @@ struct mpcqp_engine {
   std::string err;
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist;
+  int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
 };
@@ -229,7 +239,7 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
 extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
   if (!e) return MPCQP_ERR_ARG;
   cudaSetDevice(e->device);
-  DevBuf* bufs[] = { &e->pd, &e->slack, &e->q, &e->x0s, &e->g, &e->low, &e->ws, &e->counter, &e->hard, &e->order, &e->in_x0, &e->in_xref, &e->in_c,
+  DevBuf* bufs[] = { &e->pd, &e->slack, &e->q, &e->x0s, &e->g, &e->low, &e->ws, &e->counter, &e->hard, &e->order, &e->hist, &e->in_x0, &e->in_xref, &e->in_c,
                      &e->in_semi, &e->in_yaw, &e->in_lin, &e->in_warm, &e->out_x, &e->out_y, &e->out_i, &e->out_d };
   for (DevBuf* b : bufs) b->release();
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -249,6 +259,7 @@ extern "C" double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e) { ret
 extern "C" int64_t mpcqp_engine_last_launches(const mpcqp_engine* e) { return e ? e->last_launches : 0; }
 extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->last_fast : -1; }
 extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
+extern "C" int mpcqp_engine_use_history(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->use_history = on ? 1 : 0; if (!on) e->hist_B = 0; return MPCQP_OK; }
 extern "C" void* mpcqp_engine_stream(const mpcqp_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 static int check_settings(mpcqp_engine* e, const mpcqp_settings* s, Settings* o) {
@@ -403,6 +414,8 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   a.x0 = x0; a.xref = xref; a.obs_c = obs_c; a.obs_semi = obs_semi; a.obs_yaw = obs_yaw; a.lin_pt = lin_pt;
   a.q = e->q.as<double>(); a.x0s = e->x0s.as<double>(); a.g = e->g.as<double>(); a.low = e->low.as<double>();
   a.hard = e->hard.as<int>();
+  a.hist = (e->use_history && e->hist_B == B && e->hist_R == R) ? e->hist.as<int>() : nullptr;
+  a.hist_thresh = 500;
   CK(cudaMemsetAsync(e->hard.p, 0, (size_t)B * sizeof(int), e->stream));
   CK(cudaMemsetAsync(e->counter.p, 0, 4 * sizeof(int), e->stream));
   {
@@ -422,6 +435,11 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>(); bt.hard = e->hard.as<int>();
   rc = launch_solve(e, sh, st, bt); if (rc) return rc;
   CK(cudaEventRecord(e->ev1, e->stream));
+  if (e->use_history) {
+    CK(e->hist.need((size_t)B * sizeof(int)));
+    CK(cudaMemcpyAsync(e->hist.p, iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+    e->hist_B = B; e->hist_R = R;
+  }
   return MPCQP_OK;
 }
 

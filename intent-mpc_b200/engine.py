@@ -146,6 +146,10 @@ class Engine:
         code = names[on] if isinstance(on, str) else (1 if on is True else int(on))
         self._check(self.lib.mpcqp_engine_force_generic(self.h, C.c_int(code)))
 
+    def use_history(self, on: bool = True):
+        """Scheduling hint from the previous call's iteration counts (mpcqp_engine_use_history)."""
+        self._check(self.lib.mpcqp_engine_use_history(self.h, C.c_int(1 if on else 0)))
+
     def fp64_fma_peak_tflops(self) -> float:
         tf = C.c_double()
         self._check(self.lib.mpcqp_fp64_fma_peak(self.h, C.byref(tf)))

@@ -118,3 +118,28 @@ def test_solution_properties_at_full_size(eng):
     assert np.abs(vel_pred - st[:, 1:, 3:6]).max() < 10 * scale
     assert np.abs(st[:, 0, 0:6] - mb.x0[ok]).max() < 10 * scale
     assert np.abs(u[:, :, 0:3]).max() <= p.max_acc + 0.1
+
+
+def test_bitwise_determinism_under_cold_caches_and_scheduling(eng):
+    """Results must not depend on timing or on the scheduling hints: the same batch solved repeatedly — cold L2
+    (256 MiB flush on the engine's stream before each call), history hint on and off, and single-QP launches — is
+    bit-identical.  (Guards the shared-memory hand-offs between the four warps of a CTA.)"""
+    import torch
+    mb = W.static_batch(512, num_obs=4, seed0=0)
+    eng.use_history(False)
+    ref = eng.solve_mpc_batch(mb)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda:0")
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", 0))
+    eng.use_history(True)
+    try:
+        for rep in range(12):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            out = eng.solve_mpc_batch(mb)
+            assert np.array_equal(out["iter"], ref["iter"]) and np.array_equal(out["x"], ref["x"]), f"repeat {rep} differs"
+    finally:
+        eng.use_history(True)
+    long_ones = np.argsort(ref["iter"])[-3:]
+    for i in list(long_ones) + [0, 1]:
+        one = eng.solve_mpc_batch(mb.slice(int(i), int(i) + 1))
+        assert np.array_equal(one["x"][0], ref["x"][i])
