@@ -1,0 +1,83 @@
+"""BASELINE.json configs[2] at test size: intent-predicted dynamic obstacles, six candidates per scenario per control
+step, warm-started receding-horizon loop (intent-mpc_b200/receding.py).  CPU tier: the host logic runs end to end on the
+oracle.  GPU tier: the loop is driven by the CUDA engine and every QP of every step is checked against the oracle on the
+identical inputs (status, iterations, 1e-5 on x and objective); then the full-size batch (65,536 QPs) for two steps,
+checked through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from intent_mpc_b200 import receding
+from oracle import bindings as OB
+from tests.helpers import to_qp_batch, rel_inf
+
+TOL = 1e-5
+
+
+def _oracle():
+    return OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
+
+
+def _oracle_solve(mb):
+    return _oracle().solve_batch(to_qp_batch(mb), want_y=False, nthreads=os.cpu_count() or 1)
+
+
+def test_receding_horizon_host_logic_on_oracle():
+    sw = receding.IntentSweep(S=6, D=3, seed0=3)
+    x_start = sw.pos[:, 0].copy()
+    for step in range(4):
+        r = sw.step(_oracle_solve)
+        if step == 0:
+            assert len(r["batches"]) == 1 and r["batches"][0].num_obs == 0
+        else:
+            assert [b.num_obs for b in r["batches"]] == [3, 4] and [b.B for b in r["batches"]] == [24, 12]
+            assert set(np.unique(r["status"])) <= {1, 2, -2}
+            assert (r["best"] >= 0).all() and (r["best"] < 6).all()
+    assert (sw.pos[:, 0] > x_start).all() and np.isfinite(sw.states).all()
+
+
+@pytest.mark.gpu
+def test_receding_horizon_gpu_matches_oracle_every_step():
+    from intent_mpc_b200 import engine
+    eng = engine.Engine(0)
+    sw = receding.IntentSweep(S=16, D=4, seed0=11)
+    n_checked = 0
+    for step in range(6):
+        r = sw.step(lambda mb: eng.solve_mpc_batch(mb))
+        for mb, out in zip(r["batches"], r["outs"]):
+            ref = _oracle_solve(mb)
+            assert (out["status"] == ref["status"]).all(), f"step {step}"
+            assert (out["iter"] == ref["iter"]).all(), f"step {step}"
+            assert (out["rho_updates"] == ref["rho_updates"]).all()
+            assert rel_inf(out["x"], ref["x"]).max() < TOL
+            assert np.abs((out["obj"] - ref["obj"]) / ref["obj"]).max() < TOL
+            n_checked += mb.B
+    assert n_checked == 16 + 5 * 96
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_receding_horizon_full_size_properties():
+    """65,536 candidate QPs per control step (10,923 scenarios x 6, BASELINE.json configs[2]); two control steps."""
+    from intent_mpc_b200 import engine
+    eng = engine.Engine(0)
+    S = 10923
+    sw = receding.IntentSweep(S=S, D=4, seed0=5)
+    sw.step(lambda mb: eng.solve_mpc_batch(mb))
+    r = sw.step(lambda mb: eng.solve_mpc_batch(mb))
+    assert sum(b.B for b in r["batches"]) == 6 * S >= 65536
+    p = sw.p
+    ts = float(np.float32(p.ts)); h = float(np.float32(0.5 * p.ts ** 2))
+    for mb, out in zip(r["batches"], r["outs"]):
+        again = eng.solve_mpc_batch(mb)
+        assert np.array_equal(again["x"], out["x"])                     # deterministic at full size
+        ok = out["status"] == 1
+        assert ok.mean() > 0.8
+        X = out["x"][ok]; NS = p.N + 1
+        st = X[:, : 8 * NS].reshape(-1, NS, 8); u = X[:, 8 * NS:].reshape(-1, p.N, 5)
+        scale = 1e-2 * (1 + np.abs(st[:, :, 0:3]).max())
+        assert np.abs(st[:, :-1, 0:3] + ts * st[:, :-1, 3:6] + h * u[:, :, 0:3] - st[:, 1:, 0:3]).max() < scale
+        assert np.abs(st[:, 0, 0:6] - np.concatenate([mb.x0[ok, 0:3], mb.x0[ok, 3:6]], axis=1)).max() < scale
+        assert np.abs(u[:, :, 0:3]).max() <= p.max_acc + 0.2 and (u[:, :, 3:5] > -1e-2).all()
+    eng.close()
