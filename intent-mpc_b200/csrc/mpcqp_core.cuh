@@ -318,36 +318,64 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   }
 
   // ---- setup: load, Ruiz equilibration (scaling.h: scale_data), rho vector, warm start --------
-  MQ_NOINL void load_and_scale(const Batch& bt, int b) {
+  // `wi` of `nw` cooperating warps (mode 2: the four warps of the CTA; otherwise one): the per-variable / per-row loops
+  // of every stage are dealt round-robin to the warps, lane = stage in each of them.
+  MQ_HD void setup_sync(int nw) const {
+#if MQ_DEV
+    if (nw > 1) __syncthreads(); else __syncwarp();
+#else
+    (void)nw;
+#endif
+  }
+  // sum and max over all cooperating warps; every thread gets the same values
+  MQ_HD void setup_reduce(double& sm, double& mx, int wi, int nw) const {
+    sm = wsum(sm); mx = wmax(mx);
+#if MQ_DEV
+    if (nw > 1) {
+      double* red = m.YB;                       // exchange buffer outside the (aliased) PCR region
+      if (lane == 0) { red[2 * wi] = sm; red[2 * wi + 1] = mx; }
+      __syncthreads();
+      double s2 = 0.0, m2 = 0.0;
+      for (int w = 0; w < nw; ++w) { s2 += red[2 * w]; m2 = fmax(m2, red[2 * w + 1]); }
+      __syncthreads();
+      sm = s2; mx = m2;
+    }
+#else
+    (void)wi; (void)nw;
+#endif
+  }
+  MQ_NOINL void load_and_scale(const Batch& bt, int b, const int wi = 0, const int nw = 1) {
     const double* q = bt.q + (size_t)b * sh.n;
     const double* gp = bt.g + (size_t)b * N * R * 3;
     const double* lp = bt.low + (size_t)b * N * R;
     MQ_FOR_STAGES(k) {
-      for (int j = 0; j < NV; ++j) {
+      for (int j = wi; j < NV; j += nw) {
         bool ex = j < nvars(k);
         CQ_(j, k) = ex ? (j < 8 ? q[8 * k + j] : q[8 * NS + 5 * k + (j - 8)]) : 0.0;
         SD_(j, k) = 1.0;  // D during Ruiz
         B_(j, k) = 0.0; X_(j, k) = 0.0;
       }
-      for (int i = 0; i < MK; ++i) { RH_(i, k) = 1.0; Z_(i, k) = 0.0; U_(i, k) = 0.0; }  // RH holds E during Ruiz
-      for (int o = 0; o < R; ++o) {
+      for (int i = wi; i < MK; i += nw) { RH_(i, k) = 1.0; Z_(i, k) = 0.0; U_(i, k) = 0.0; }  // RH holds E during Ruiz
+      for (int o = wi; o < R; o += nw) {
         bool ex = k < N;
         G3_(3 * o, k) = ex ? gp[(k * R + o) * 3] : 0.0;
         G3_(3 * o + 1, k) = ex ? gp[(k * R + o) * 3 + 1] : 0.0;
         G3_(3 * o + 2, k) = ex ? gp[(k * R + o) * 3 + 2] : 0.0;
         LO_(o, k) = ex ? lp[k * R + o] : 0.0;
       }
-      for (int r = 0; r < 8; ++r) TD_(r, k) = 0.0;
-      for (int cc = 0; cc < 3; ++cc) MA_(cc, k) = 0.0;
+      if (wi == 0) {
+        for (int r = 0; r < 8; ++r) TD_(r, k) = 0.0;
+        for (int cc = 0; cc < 3; ++cc) MA_(cc, k) = 0.0;
+      }
     }
     c = 1.0;
-    MQ_SYNC();
+    setup_sync(nw);
     const double apv = fabs(sh.a_pv), bpa = fabs(sh.b_pa), bva = fabs(sh.b_va);
     for (int pass = 0; pass < st.scaling; ++pass) {
       // column norms of [P A'; A 0] -> B (Dt), row norms of A -> Z (Et); D lives in SD, E in RH
       MQ_FOR_STAGES(k) {
         const int nv = nvars(k), nr = nrows(k);
-        for (int j = 0; j < nv; ++j) {
+        for (int j = wi; j < nv; j += nw) {
           double dj = SD_(j, k);
           double an = RH_(8 + j, k);
           if (j < 8) an = fmax(an, RH_(j, k));
@@ -361,7 +389,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           double pn = fabs(c * pd[k * NV + j]) * dj * dj;
           B_(j, k) = 1.0 / sqrt(limit_scaling(fmax(pn, an * dj)));
         }
-        for (int i = 0; i < nr; ++i) {
+        for (int i = wi; i < nr; i += nw) {
           double rn;
           if (i < 8) {
             rn = SD_(i, k);
@@ -379,32 +407,32 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           Z_(i, k) = 1.0 / sqrt(limit_scaling(rn * RH_(i, k)));
         }
       }
-      MQ_SYNC();
+      setup_sync(nw);
       double psum = 0.0, qmax = 0.0;
       MQ_FOR_STAGES(k) {
         const int nv = nvars(k), nr = nrows(k);
-        for (int j = 0; j < nv; ++j) {
+        for (int j = wi; j < nv; j += nw) {
           double dj = SD_(j, k) * B_(j, k);
           SD_(j, k) = dj;
           psum += fabs(c * pd[k * NV + j]) * dj * dj;
           qmax = fmax(qmax, fabs(c * CQ_(j, k) * dj));
         }
-        for (int i = 0; i < nr; ++i) RH_(i, k) *= Z_(i, k);
+        for (int i = wi; i < nr; i += nw) RH_(i, k) *= Z_(i, k);
       }
-      psum = wsum(psum); qmax = wmax(qmax);
+      setup_reduce(psum, qmax, wi, nw);
       double ct = psum / (double)sh.n;
       double nqv = limit_scaling(qmax);
       if (nqv > ct) ct = nqv;
       ct = limit_scaling(ct);
       c *= 1.0 / ct;
-      MQ_SYNC();
+      setup_sync(nw);
     }
     cinv = 1.0 / c;
     // finalise: stash E, D (needed for rho estimates / rho updates), form Rh, sigma/D^2, c q
     rho = fmin(fmax(st.rho, kRhoMin), kRhoMax);
     double nq0 = 0.0, nq1 = 0.0;
     MQ_FOR_STAGES(k) {
-      for (int j = 0; j < NV; ++j) {
+      for (int j = wi; j < NV; j += nw) {
         double dj = SD_(j, k);
         WSD_(j, k) = dj;
         double cq = c * CQ_(j, k);
@@ -415,29 +443,34 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         B_(j, k) = 0.0; WSDX_(j, k) = 0.0;
       }
       const int nr = nrows(k);
-      for (int i = 0; i < MK; ++i) {
+      for (int i = wi; i < MK; i += nw) {
         double e = RH_(i, k);
         WSE_(i, k) = e; WSDY_(i, k) = 0.0; Z_(i, k) = 0.0;
         if (i < nr) { double lo, hi; row_bounds(k, i, lo, hi); RH_(i, k) = rho_of_type(row_type(e, lo, hi)) * e * e; }
         else RH_(i, k) = 0.0;
       }
     }
-    nq = wmax(nq0); nq_s = wmax(nq1);
+    {
+      double dummy = 0.0;
+      setup_reduce(dummy, nq0, wi, nw); nq = nq0;
+      dummy = 0.0;
+      setup_reduce(dummy, nq1, wi, nw); nq_s = nq1;
+    }
     // warm start (osqp.h:157): x given, y = 0 (MP.cpp:487), z = A x
     if (bt.warm_x && st.warm_start) {
       const double* wx = bt.warm_x + (size_t)b * sh.n;
-      MQ_FOR_STAGES(k) { const int nv = nvars(k); for (int j = 0; j < nv; ++j) X_(j, k) = j < 8 ? wx[8 * k + j] : wx[8 * NS + 5 * k + (j - 8)]; }
+      MQ_FOR_STAGES(k) { const int nv = nvars(k); for (int j = wi; j < nv; j += nw) X_(j, k) = j < 8 ? wx[8 * k + j] : wx[8 * NS + 5 * k + (j - 8)]; }
     }
-    MQ_SYNC();
-    MQ_FOR_STAGES(k) { const int nr = nrows(k); for (int i = 0; i < nr; ++i) Z_(i, k) = row_ax(k, i, [&](int j, int kk) { return X_(j, kk); }); }
+    setup_sync(nw);
+    MQ_FOR_STAGES(k) { const int nr = nrows(k); for (int i = wi; i < nr; i += nw) Z_(i, k) = row_ax(k, i, [&](int j, int kk) { return X_(j, kk); }); }
     if (bt.warm_y && st.warm_start) {   // y_s = c E^-1 y  =>  u = E^-1 y_s / rho = c y / Rh
       const double* wy = bt.warm_y + (size_t)b * sh.m;
       MQ_FOR_STAGES(k) {
         const int nr = nrows(k);
-        for (int i = 0; i < nr; ++i) U_(i, k) = c * wy[row_index(k, i)] / RH_(i, k);
+        for (int i = wi; i < nr; i += nw) U_(i, k) = c * wy[row_index(k, i)] / RH_(i, k);
       }
     }
-    MQ_SYNC();
+    setup_sync(nw);
   }
 
   // ---- factorisation of the reduced KKT matrix ---------------------------------------------
@@ -2074,15 +2107,12 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     x0p = bt.x0 + (size_t)b * 8;
     // setup (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) builds the cold block in the still unused PCR
     // region of shared memory; the CTA then copies it to its global home in one pass
-    if (warp == 0) {
+    {
       const Mem keep = m;
       map_cold(m, keep.PCR, NS, R);
-      load_and_scale(bt, b);
+      load_and_scale(bt, b, warp, 4);           // all four warps; every thread ends with the same c, rho, |q| norms
       m = keep;
-      if (lane == 0) { m.YB[0] = c; m.YB[1] = rho; m.YB[2] = nq; m.YB[3] = nq_s; }
     }
-    __syncthreads();
-    c = m.YB[0]; cinv = 1.0 / c; rho = m.YB[1]; nq = m.YB[2]; nq_s = m.YB[3];
     for (int i = threadIdx.x; i < cold_slots(R) * NS; i += blockDim.x) m.E[i] = m.PCR[i];
     __syncthreads();
     if (warp < 3) solve_role<true>(warp, flag); else solve_role<false>(warp, flag);
