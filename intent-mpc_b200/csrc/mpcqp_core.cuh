@@ -84,6 +84,7 @@ struct Batch {              // device pointers
   const int* hard;              // [B] hard flags, or nullptr
   const int* nhard;             // number of hard instances (device scalar), or nullptr
   int queue;                    // 0: one queue over all B; 1: hard instances only; 2: the others only
+  long long* dbg;               // [B][8] per-phase clock64 totals (only with MPCQP_PHASE_TIMING), or nullptr
   int B;
 };
 
@@ -140,7 +141,8 @@ MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) 
     m.PCR = p; p += kPcrDoubles;
     m.WK = p; m.RA = p; m.RS = p + 2 * 6 * NS; m.YB = p + 2 * 6 * NS + 4 * NS;
     g = map_cold(m, g, NS, R);
-    m.W = g; g += NV * NS; m.SI = g; g += 36 * NS; m.GG = g; g += 36 * NS; m.DSI = g; g += 2 * NS; m.ESD = g; g += 2 * NS;
+    // T blocks (SI) and couplings (GG, 12 slots used) are staged in the factor workspace: LN slots / tail of the LC slots
+    m.W = g; g += NV * NS; m.SI = m.WK + 72 * NS; m.GG = m.WK + 60 * NS; m.DSI = g; g += 2 * NS; m.ESD = g; g += 2 * NS;
     m.DGI = g; g += 2 * NS; m.FS = g; g += 6 * NS; m.DAI = g; g += 3 * NS; m.CV = g; g += 12 * NS; m.PK = nullptr;
     m.PD = g; g += 36 * NS; m.PL = g; g += 72 * NS; m.PI = g; g += 36 * NS; m.OG = g; g += 3 * NS; m.OX = g; g += NV * NS; m.OU = g; g += MK * NS;
     return;
@@ -174,6 +176,8 @@ template <> struct DimsT<0, 0> {
 #endif
 
 MQ_HD double limit_scaling(double v) { v = v < kMinScaling ? 1.0 : v; return v > kMaxScaling ? kMaxScaling : v; }
+// 1/sqrt(v) of scaling.h's scale_data (sqrt then reciprocal, as OSQP computes it)
+MQ_HD double rsqrt_scaling(double v) { return 1.0 / sqrt(v); }
 
 // In-place inverse of a symmetric positive definite 6x6 (Gauss-Jordan, no pivoting).
 MQ_HD void inv6(double* a) {
@@ -210,6 +214,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   double c, cinv, rho, nq, nq_s;                 // cost scaling, current rho, |q|_inf norms (unscaled / scaled)
   double pri_res, dua_res, obj, nAx, nZ, nPx, nAty, pri_s, dua_s, nAx_s, nZ_s, nPx_s, nAty_s;
   int status, info_iter, rho_updates;
+#ifdef MPCQP_PHASE_TIMING
+  long long dbg_ruiz = 0;
+#endif
 
 #define X_(j, k) m.X[(j) * NS + (k)]
 #define Z_(i, k) m.Z[(i) * NS + (k)]
@@ -344,7 +351,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     (void)wi; (void)nw;
 #endif
   }
-  MQ_NOINL void load_and_scale(const Batch& bt, int b, const int wi = 0, const int nw = 1) {
+  // NW = number of cooperating warps (compile time, so that the dealt-out loops unroll and their sqrt / divide chains
+  // interleave); wi = this warp's index.
+  template <int NW = 1> MQ_NOINL void load_and_scale(const Batch& bt, int b, const int wi = 0) {
+    constexpr int nw = NW;
     const double* q = bt.q + (size_t)b * sh.n;
     const double* gp = bt.g + (size_t)b * N * R * 3;
     const double* lp = bt.low + (size_t)b * N * R;
@@ -370,12 +380,18 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     }
     c = 1.0;
     setup_sync(nw);
+#ifdef MPCQP_PHASE_TIMING
+    long long ts0 = clock64();
+#endif
     const double apv = fabs(sh.a_pv), bpa = fabs(sh.b_pa), bva = fabs(sh.b_va);
     for (int pass = 0; pass < st.scaling; ++pass) {
       // column norms of [P A'; A 0] -> B (Dt), row norms of A -> Z (Et); D lives in SD, E in RH
       MQ_FOR_STAGES(k) {
         const int nv = nvars(k), nr = nrows(k);
-        for (int j = wi; j < nv; j += nw) {
+#pragma unroll
+        for (int jj = 0; jj < (NW > 1 ? (NV + NW - 1) / NW : NV); ++jj) {
+          const int j = wi + nw * jj;
+          if (j >= nv) continue;
           double dj = SD_(j, k);
           double an = RH_(8 + j, k);
           if (j < 8) an = fmax(an, RH_(j, k));
@@ -387,8 +403,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             else { an = fmax(an, RH_(j - 5, k + 1)); for (int o = 0; o < R; ++o) if (SLK_(o, k) == j - 11) an = fmax(an, RH_(NBR + o, k)); }
           }
           double pn = fabs(c * pd[k * NV + j]) * dj * dj;
-          B_(j, k) = 1.0 / sqrt(limit_scaling(fmax(pn, an * dj)));
+          B_(j, k) = rsqrt_scaling(limit_scaling(fmax(pn, an * dj)));
         }
+#pragma unroll 4
         for (int i = wi; i < nr; i += nw) {
           double rn;
           if (i < 8) {
@@ -404,7 +421,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             rn = SD_(11 + SLK_(o, k), k);
             for (int cc = 0; cc < 3; ++cc) rn = fmax(rn, fabs(G3_(3 * o + cc, k)) * SD_(cc, k));
           }
-          Z_(i, k) = 1.0 / sqrt(limit_scaling(rn * RH_(i, k)));
+          Z_(i, k) = rsqrt_scaling(limit_scaling(rn * RH_(i, k)));
         }
       }
       setup_sync(nw);
@@ -427,6 +444,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       c *= 1.0 / ct;
       setup_sync(nw);
     }
+#ifdef MPCQP_PHASE_TIMING
+    dbg_ruiz = clock64() - ts0;
+#endif
     cinv = 1.0 / c;
     // finalise: stash E, D (needed for rho estimates / rho updates), form Rh, sigma/D^2, c q
     rho = fmin(fmax(st.rho, kRhoMin), kRhoMax);
@@ -1465,6 +1485,14 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   static MQ_HD double clampd(double v, double lo, double hi) { double z = v > lo ? v : lo; return z < hi ? z : hi; }
   static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3;
 
+#ifdef MPCQP_PHASE_TIMING
+  long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // setup, leaf, pcr factor, load, iterate, info+check, park/adapt, store
+#define MQ_T0() long long t0_ = clock64()
+#define MQ_T(i) do { long long t1_ = clock64(); tacc[i] += t1_ - t0_; t0_ = t1_; } while (0)
+#else
+#define MQ_T0() ((void)0)
+#define MQ_T(i) ((void)0)
+#endif
   // PCR factorisation by the whole CTA (same recurrences as pcr_factor() above, which stays as the host-emulated
   // specification).  Work split: axis warp w owns rows 2w, 2w+1 (axis-major) of every 6x6 product of its stage and
   // keeps its two rows of D in registers across levels; warp 3 inverts the D blocks (lane = stage) while the axis
@@ -1474,24 +1502,34 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     const bool live = lane < NS;
     double* DI = m.WK; double* LC = m.WK + 36 * NS; double* LN = m.WK + 72 * NS;
     __syncthreads();                                      // warp 0 has written T (SI_) and the couplings (GG_)
-    // initial D = T (leaf elimination, (p,v)-major) and L = coupling of stages k-1, k, permuted to axis-major
-#pragma unroll
-    for (int q = 0; q < 9; ++q) {
-      const int e = warp * 9 + q, a = e / 6, b2 = e - 6 * a, oa = pcr_old(a), ob = pcr_old(b2);
-      double l = 0.0;
-      if (k > 0 && (oa % 3) == (ob % 3)) l = GG_(4 * (oa % 3) + (oa / 3) * 2 + (ob / 3), k - 1);
-      if (live) { DI[e * NS + k] = SI_(oa * 6 + ob, k); LC[e * NS + k] = l; }
-    }
+    MQ_T0();
+    // initial D = T (leaf elimination, (p,v)-major) and L = coupling of stages k-1, k, permuted to axis-major.  T and
+    // the couplings are staged in the workspace itself (SI_ in the LN slots, GG_ in the tail of LC): read, then write.
     double dr[12];
-    if (warp < 3) {
+    {
+      double dv[9], lv[9];
 #pragma unroll
-      for (int ar = 0; ar < 2; ++ar)
+      for (int q = 0; q < 9; ++q) {
+        const int e = warp * 9 + q, a = e / 6, b2 = e - 6 * a, oa = pcr_old(a), ob = pcr_old(b2);
+        dv[q] = SI_(oa * 6 + ob, k);
+        lv[q] = (k > 0 && (oa % 3) == (ob % 3)) ? GG_(4 * (oa % 3) + (oa / 3) * 2 + (ob / 3), k - 1) : 0.0;
+      }
+      if (warp < 3) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) dr[ar * 6 + j] = SI_(pcr_old(2 * warp + ar) * 6 + pcr_old(j), k);
+        for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) dr[ar * 6 + j] = SI_(pcr_old(2 * warp + ar) * 6 + pcr_old(j), k);
+      }
+      __syncthreads();
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { const int e = warp * 9 + q; DI[e * NS + k] = dv[q]; LC[e * NS + k] = lv[q]; }
+      }
     }
     for (int l = 0, s = 1; l < kPcrLevels; ++l, s <<= 1) {
       const bool last = l == kPcrLevels - 1;
       __syncthreads();                                    // DI = D of every stage, LC = L
+      MQ_T(l == 0 ? 8 : 10);
       if (warp == 3) {
         double S[36];
 #pragma unroll
@@ -1503,68 +1541,126 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         }
       }
       __syncthreads();                                    // DI = D^-1
+      MQ_T(9);
       const bool hm = k - s >= 0, hp = k + s <= N, hmm = k - 2 * s >= 0;
       const int km = hm ? k - s : k, kp = hp ? k + s : k;
       double2* const P2 = reinterpret_cast<double2*>(m.PCR) + l * (kPcrLevelDoubles / 2) + (warp * 12) * NS + k;
+      double out_l[12];                                   // what goes to LN: next L rows (or M rows on the last level)
       if (warp < 3) {
+        const int a0 = 2 * warp;
+        double al_[12], ga_[12], M[36];
+        // every product reads its operands into registers first: nothing below is stored until all loads are done
         if (!last) {
+          // alpha rows = L_k rows . D_{k-s}^-1
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = DI[e * NS + km];
 #pragma unroll
           for (int ar = 0; ar < 2; ++ar) {
-            const int a = 2 * warp + ar;
-            double al_[6], ga_[6];
+            double lr[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              double sa = 0.0, sg = 0.0;
-#pragma unroll
-              for (int t = 0; t < 6; ++t) {
-                sa = fma(LC[(a * 6 + t) * NS + k], DI[(t * 6 + j) * NS + km], sa);
-                sg = fma(LC[(t * 6 + a) * NS + kp], DI[(t * 6 + j) * NS + kp], sg);
-              }
-              al_[j] = hm ? sa : 0.0; ga_[j] = hp ? sg : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              double sd = dr[ar * 6 + j], sl = 0.0;
-#pragma unroll
-              for (int t = 0; t < 6; ++t) {
-                sd = fma(-al_[t], LC[(j * 6 + t) * NS + k], sd);
-                sd = fma(-ga_[t], LC[(t * 6 + j) * NS + kp], sd);
-                sl = fma(-al_[t], LC[(t * 6 + j) * NS + km], sl);
-              }
-              dr[ar * 6 + j] = sd;
-              if (live) LN[(a * 6 + j) * NS + k] = hmm ? sl : 0.0;
-            }
-            if (live) {
-#pragma unroll
-              for (int bp = 0; bp < 3; ++bp) {
-                P2[(ar * 3 + bp) * NS] = make_double2(al_[2 * bp], al_[2 * bp + 1]);
-                P2[(6 + ar * 3 + bp) * NS] = make_double2(ga_[2 * bp], ga_[2 * bp + 1]);
-              }
-            }
-          }
-        } else {
-          // single partner: M = alpha (partner k-s) or gamma (partner k+s);  D' = D - M (.)'
-#pragma unroll
-          for (int ar = 0; ar < 2; ++ar) {
-            const int a = 2 * warp + ar;
-            double mr[6];
+            for (int t = 0; t < 6; ++t) lr[t] = LC[((a0 + ar) * 6 + t) * NS + k];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
               double sa = 0.0;
 #pragma unroll
-              for (int t = 0; t < 6; ++t)
-                sa = fma(hm ? LC[(a * 6 + t) * NS + k] : LC[(t * 6 + a) * NS + kp], DI[(t * 6 + j) * NS + (hm ? km : kp)], sa);
-              mr[j] = (hm || hp) ? sa : 0.0;
+              for (int t = 0; t < 6; ++t) sa = fma(lr[t], M[t * 6 + j], sa);
+              al_[ar * 6 + j] = hm ? sa : 0.0;
             }
+          }
+          // gamma rows = (L_{k+s}')rows . D_{k+s}^-1
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = DI[e * NS + kp];
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar) {
+            double lc[6];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) lc[t] = LC[(t * 6 + a0 + ar) * NS + kp];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sg = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sg = fma(lc[t], M[t * 6 + j], sg);
+              ga_[ar * 6 + j] = hp ? sg : 0.0;
+            }
+          }
+          // D' rows -= alpha L_k'
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = LC[e * NS + k];
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar)
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
               double sd = dr[ar * 6 + j];
 #pragma unroll
-              for (int t = 0; t < 6; ++t) sd = fma(-mr[t], hm ? LC[(j * 6 + t) * NS + k] : LC[(t * 6 + j) * NS + kp], sd);
+              for (int t = 0; t < 6; ++t) sd = fma(-al_[ar * 6 + t], M[j * 6 + t], sd);
               dr[ar * 6 + j] = sd;
-              if (live) LN[(a * 6 + j) * NS + k] = mr[j];          // M, needed whole for D'^-1 M
+            }
+          // D' rows -= gamma L_{k+s}
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = LC[e * NS + kp];
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sd = dr[ar * 6 + j];
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sd = fma(-ga_[ar * 6 + t], M[t * 6 + j], sd);
+              dr[ar * 6 + j] = sd;
+            }
+          // next L rows = -alpha L_{k-s}
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = LC[e * NS + km];
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sl = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sl = fma(-al_[ar * 6 + t], M[t * 6 + j], sl);
+              out_l[ar * 6 + j] = hmm ? sl : 0.0;
+            }
+          if (live) {
+#pragma unroll
+            for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+              for (int bp = 0; bp < 3; ++bp) {
+                P2[(ar * 3 + bp) * NS] = make_double2(al_[ar * 6 + 2 * bp], al_[ar * 6 + 2 * bp + 1]);
+                P2[(6 + ar * 3 + bp) * NS] = make_double2(ga_[ar * 6 + 2 * bp], ga_[ar * 6 + 2 * bp + 1]);
+              }
+          }
+        } else {
+          // single partner: M = alpha (partner k-s) or gamma (partner k+s);  D' = D - M (.)'
+          const int kq2 = hm ? km : kp;
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = DI[e * NS + kq2];
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar) {
+            double lr[6];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) lr[t] = hm ? LC[((a0 + ar) * 6 + t) * NS + k] : LC[(t * 6 + a0 + ar) * NS + kp];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sa = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sa = fma(lr[t], M[t * 6 + j], sa);
+              out_l[ar * 6 + j] = (hm || hp) ? sa : 0.0;      // M rows
             }
           }
+#pragma unroll
+          for (int e = 0; e < 36; ++e) M[e] = hm ? LC[e * NS + k] : LC[e * NS + kp];
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double sd = dr[ar * 6 + j];
+#pragma unroll
+              for (int t = 0; t < 6; ++t) sd = fma(-out_l[ar * 6 + t], hm ? M[j * 6 + t] : M[t * 6 + j], sd);
+              dr[ar * 6 + j] = sd;
+            }
+        }
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) LN[(a0 * 6 + e) * NS + k] = out_l[e];
         }
       }
       __syncthreads();                                    // everyone is done with D^-1 and L of this level
@@ -1576,6 +1672,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     }
     // D' of the last level is in DI, M in LC: invert, then rows of D'^-1 and D'^-1 M go to level 4 of the PCR store
     __syncthreads();
+    MQ_T(10);
     if (warp == 3) {
       double S[36];
 #pragma unroll
@@ -1589,6 +1686,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     __syncthreads();
     if (warp < 3 && live) {
       double2* const P2 = reinterpret_cast<double2*>(m.PCR) + (kPcrLevels - 1) * (kPcrLevelDoubles / 2) + (warp * 12) * NS + k;
+      double M[36];
+#pragma unroll
+      for (int e = 0; e < 36; ++e) M[e] = LC[e * NS + k];
 #pragma unroll
       for (int ar = 0; ar < 2; ++ar) {
         const int a = 2 * warp + ar;
@@ -1599,7 +1699,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         for (int j = 0; j < 6; ++j) {
           double sm = 0.0;
 #pragma unroll
-          for (int t = 0; t < 6; ++t) sm = fma(di[t], LC[(t * 6 + j) * NS + k], sm);
+          for (int t = 0; t < 6; ++t) sm = fma(di[t], M[t * 6 + j], sm);
           dm[j] = sm;
         }
 #pragma unroll
@@ -1610,6 +1710,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       }
     }
     __syncthreads();
+    MQ_T(11);
   }
 
   // CTA-wide reduction of NM maxima and NS_ sums; every thread ends with the same values (fixed combination order).
@@ -1722,14 +1823,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           const int j = vj(e);
           X_(j, k) = x[e]; Z_(8 + j, k) = zb[e]; U_(8 + j, k) = ub[e]; B_(j, k) = b[e];
           WSDX_(j, k) = x[e] - OX_(j, k); WSDY_(8 + j, k) = rhb[e] * (ub[e] - OU_(8 + j, k));
+          if (e < 2 || hasu) RH_(8 + j, k) = rhb[e];
         }
 #pragma unroll
-        for (int t = 0; t < 2; ++t) { const int i = di(t); Z_(i, k) = zd[t]; U_(i, k) = ud[t]; WSDY_(i, k) = rhd[t] * (ud[t] - OU_(i, k)); }
+        for (int t = 0; t < 2; ++t) { const int i = di(t); Z_(i, k) = zd[t]; U_(i, k) = ud[t]; WSDY_(i, k) = rhd[t] * (ud[t] - OU_(i, k)); RH_(i, k) = rhd[t]; }
         if constexpr (AX) OG_(cc, k) = ogp;
 #pragma unroll
         for (int q = 0; q < NOW; ++q) {
           const int o = 4 * q + warp;
-          if (o < R) { Z_(NBR + o, k) = zo[q]; U_(NBR + o, k) = uo[q]; WSDY_(NBR + o, k) = orh[q] * (uo[q] - OU_(NBR + o, k)); }
+          if (o < R) { Z_(NBR + o, k) = zo[q]; U_(NBR + o, k) = uo[q]; WSDY_(NBR + o, k) = orh[q] * (uo[q] - OU_(NBR + o, k)); if (hasu) RH_(NBR + o, k) = orh[q]; }
         }
       }
     };
@@ -2057,18 +2159,23 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       const bool final_pass = iter >= st.max_iter;
       if (!final_pass) {
         if (refactor) {
+          __syncthreads();                                // parked iterates / new Rh of all warps are visible to warp 0
+          MQ_T0();
           if (warp == 0) {
             factor(); rows_phase<1>(); rhs_finish();      // leaf elimination + T blocks; whole right-hand side into B_
             MQ_FOR_STAGES(kk) { OG_(0, kk) = 0.0; OG_(1, kk) = 0.0; OG_(2, kk) = 0.0; }
           }
+          MQ_T(1);
           pcr_factor_cta(warp);                           // starts and ends with a CTA barrier
+          MQ_T(2);
           load();
+          MQ_T(3);
           refactor = false;
         }
         int nb = st.max_iter;
         if (st.check_termination) { int c2 = (iter / st.check_termination + 1) * st.check_termination; if (c2 < nb) nb = c2; }
         if (st.adaptive_rho && st.adaptive_rho_interval) { int c2 = (iter / st.adaptive_rho_interval + 1) * st.adaptive_rho_interval; if (c2 < nb) nb = c2; }
-        iterate(nb - iter);
+        { MQ_T0(); iterate(nb - iter); MQ_T(4); }
         iter = nb;
         do_check = st.check_termination && (iter % st.check_termination == 0);
         do_adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
@@ -2079,8 +2186,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       } else {
         do_info = false; do_check = true;
       }
+      MQ_T0();
       if (do_info) info(iter);
-      if (do_check && check(approx)) break;
+      const bool done_ = do_check && check(approx);
+      MQ_T(5);
+      if (done_) break;
       if (final_pass) {
         if (approx) { status = kMaxIter; break; }
         approx = true;
@@ -2093,10 +2203,22 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         double rn = rho * sqrt(pn / (dn + 1e-10));
         rn = fmin(fmax(rn, kRhoMin), kRhoMax);
         if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
-          park();
-          __syncthreads();
-          if (warp == 0) adapt_rho(); else rho = rn;       // warp 0 re-derives the same rho and rescales RH_, U_
+          MQ_T0();
+          // osqp_update_rho: new rho vector (auxil.h set_rho_vec classes on the SCALED bounds), y kept => u = y / Rh rescaled
+          rho = rn; rho_updates += 1;
+          auto rescale = [&](double& rh, double& u, double e, double lo_, double hi_) {
+            const int t = row_type(e, lo_, hi_);
+            if (t >= 0) { const double rnew = rho_of_type(t) * e * e; u = u * rh / rnew; rh = rnew; }
+          };
+#pragma unroll
+          for (int e = 0; e < NVR; ++e) if (e < 2 || hasu) rescale(rhb[e], ub[e], WSE_(8 + vj(e), k), blo(e), bhi(e));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) rescale(rhd[t], ud[t], WSE_(di(t), k), bnd[t], bnd[t]);
+#pragma unroll
+          for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R && hasu) rescale(orh[q], uo[q], WSE_(NBR + o, k), olo[q], INFINITY); }
+          park();                                          // also writes the new Rh for the factorisation
           refactor = true;
+          MQ_T(6);
         }
       }
     }
@@ -2108,17 +2230,28 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     // setup (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) builds the cold block in the still unused PCR
     // region of shared memory; the CTA then copies it to its global home in one pass
     {
+      MQ_T0();
       const Mem keep = m;
       map_cold(m, keep.PCR, NS, R);
-      load_and_scale(bt, b, warp, 4);           // all four warps; every thread ends with the same c, rho, |q| norms
+      load_and_scale<4>(bt, b, warp);           // all four warps; every thread ends with the same c, rho, |q| norms
       m = keep;
+      for (int i = threadIdx.x; i < cold_slots(R) * NS; i += blockDim.x) m.E[i] = m.PCR[i];
+      __syncthreads();
+      MQ_T(0);
     }
-    for (int i = threadIdx.x; i < cold_slots(R) * NS; i += blockDim.x) m.E[i] = m.PCR[i];
-    __syncthreads();
     if (warp < 3) solve_role<true>(warp, flag); else solve_role<false>(warp, flag);
     __syncthreads();
-    if (warp == 0) store(bt, b);
-    __syncthreads();
+    {
+      MQ_T0();
+      if (warp == 0) store(bt, b);
+      __syncthreads();
+      MQ_T(7);
+    }
+#ifdef MPCQP_PHASE_TIMING
+    tacc[12] = dbg_ruiz;
+    if (threadIdx.x == 0 && bt.dbg) { for (int i = 0; i < 16; ++i) bt.dbg[(size_t)b * 16 + i] = tacc[i]; }
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#endif
   }
 #endif
 

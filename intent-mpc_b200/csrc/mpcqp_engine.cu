@@ -189,7 +189,7 @@ struct mpcqp_engine {
   std::string err;
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
@@ -260,6 +260,13 @@ extern "C" int64_t mpcqp_engine_last_launches(const mpcqp_engine* e) { return e 
 extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->last_fast : -1; }
 extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
 extern "C" int mpcqp_engine_use_history(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->use_history = on ? 1 : 0; if (!on) e->hist_B = 0; return MPCQP_OK; }
+#ifdef MPCQP_PHASE_TIMING
+extern "C" int mpcqp_debug_phase_clocks(mpcqp_engine* e, long long* out, int B) {   // development builds only
+  if (!e || !out) return MPCQP_ERR_ARG;
+  CK(cudaMemcpy(out, e->dbg.p, (size_t)B * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return MPCQP_OK;
+}
+#endif
 extern "C" void* mpcqp_engine_stream(const mpcqp_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 static int check_settings(mpcqp_engine* e, const mpcqp_settings* s, Settings* o) {
@@ -433,6 +440,9 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
   bt.warm_x = warm_x; bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates;
   bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>(); bt.hard = e->hard.as<int>();
+#ifdef MPCQP_PHASE_TIMING
+  CK(e->dbg.need((size_t)B * 16 * sizeof(long long))); bt.dbg = e->dbg.as<long long>();
+#endif
   rc = launch_solve(e, sh, st, bt); if (rc) return rc;
   CK(cudaEventRecord(e->ev1, e->stream));
   if (e->use_history) {
