@@ -85,7 +85,9 @@ int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
 /* Which solve kernel the last batch ran: 2 = CTA kernel (one 4-warp CTA per QP, parallel-cyclic-reduction solve,
  * horizon 30, num_obs <= 8), 1 = one-warp-per-QP register-resident kernel (same shapes), 0 = generic one-warp
  * shared-memory kernel (any horizon/num_obs that fits).  force_generic(1) pins the generic kernel, (2) the
- * one-warp register kernel, (0) restores the default dispatch (used by the tests to cover all three). */
+ * one-warp register kernel, (3) the CTA kernel without its assistant warps (launches that give a CTA an SM to itself
+ * normally carry three more warps that hold the PCR matrices of levels 1..3 in registers), (0) restores the default
+ * dispatch (used by the tests to cover all of them). */
 int mpcqp_engine_last_path(const mpcqp_engine* e);
 int mpcqp_engine_force_generic(mpcqp_engine* e, int on);
 /* Scheduling hint (default on): the batched entry point remembers how many iterations each batch slot took and, when

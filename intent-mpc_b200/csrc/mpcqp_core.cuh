@@ -170,6 +170,9 @@ template <> struct DimsT<0, 0> {
 #if MQ_DEV
 #define MQ_FOR_STAGES(k) for (int k = lane; k < NS; k += 32)
 #define MQ_SYNC() __syncwarp()
+// Barrier of the four solver warps of a CTA-mode block (threads 0..127).  The block may carry three more warps (PCR
+// assistants, threads 128..223) that never take part in it.
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
 #else
 #define MQ_FOR_STAGES(k) for (int k = 0; k < NS; ++k)
 #define MQ_SYNC() ((void)0)
@@ -197,7 +200,7 @@ MQ_HD void inv6(double* a) {
   }
 }
 
-template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> struct Qp : DimsT<NST, RT> {
+template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), bool ASSIST = false> struct Qp : DimsT<NST, RT> {
   using Dm = DimsT<NST, RT>;
   using Dm::NS; using Dm::N; using Dm::R; using Dm::MK;
   static constexpr bool kFast = QMODE == kModeWarp;
@@ -329,7 +332,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   // of every stage are dealt round-robin to the warps, lane = stage in each of them.
   MQ_HD void setup_sync(int nw) const {
 #if MQ_DEV
-    if (nw > 1) __syncthreads(); else __syncwarp();
+    if (nw > 1) cta_sync(); else __syncwarp();
 #else
     (void)nw;
 #endif
@@ -341,10 +344,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     if (nw > 1) {
       double* red = m.YB;                       // exchange buffer outside the (aliased) PCR region
       if (lane == 0) { red[2 * wi] = sm; red[2 * wi + 1] = mx; }
-      __syncthreads();
+      cta_sync();
       double s2 = 0.0, m2 = 0.0;
       for (int w = 0; w < nw; ++w) { s2 += red[2 * w]; m2 = fmax(m2, red[2 * w + 1]); }
-      __syncthreads();
+      cta_sync();
       sm = s2; mx = m2;
     }
 #else
@@ -1480,10 +1483,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   // shared-memory buffers with named barriers (6 per iteration).
   // ================================================================================================
   static MQ_HD void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+  static MQ_HD void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
   static MQ_HD double up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
   static MQ_HD double dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
   static MQ_HD double clampd(double v, double lo, double hi) { double z = v > lo ? v : lo; return z < hi ? z : hi; }
-  static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3;
+  static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3, kBarT = 4, kBarCmd = 5, kBarH1 = 6, kBarH2 = 7, kBarA = 8;
 
 #ifdef MPCQP_PHASE_TIMING
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // setup, leaf, pcr factor, load, iterate, info+check, park/adapt, store
@@ -1501,7 +1505,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     const int k = lane < NS ? lane : NS - 1;
     const bool live = lane < NS;
     double* DI = m.WK; double* LC = m.WK + 36 * NS; double* LN = m.WK + 72 * NS;
-    __syncthreads();                                      // warp 0 has written T (SI_) and the couplings (GG_)
+    cta_sync();                                      // warp 0 has written T (SI_) and the couplings (GG_)
     MQ_T0();
     // initial D = T (leaf elimination, (p,v)-major) and L = coupling of stages k-1, k, permuted to axis-major.  T and
     // the couplings are staged in the workspace itself (SI_ in the LN slots, GG_ in the tail of LC): read, then write.
@@ -1520,7 +1524,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
 #pragma unroll
           for (int j = 0; j < 6; ++j) dr[ar * 6 + j] = SI_(pcr_old(2 * warp + ar) * 6 + pcr_old(j), k);
       }
-      __syncthreads();
+      cta_sync();
       if (live) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) { const int e = warp * 9 + q; DI[e * NS + k] = dv[q]; LC[e * NS + k] = lv[q]; }
@@ -1528,7 +1532,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     }
     for (int l = 0, s = 1; l < kPcrLevels; ++l, s <<= 1) {
       const bool last = l == kPcrLevels - 1;
-      __syncthreads();                                    // DI = D of every stage, LC = L
+      cta_sync();                                    // DI = D of every stage, LC = L
       MQ_T(l == 0 ? 8 : 10);
       if (warp == 3) {
         double S[36];
@@ -1540,7 +1544,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           for (int e = 0; e < 36; ++e) DI[e * NS + k] = S[e];
         }
       }
-      __syncthreads();                                    // DI = D^-1
+      cta_sync();                                    // DI = D^-1
       MQ_T(9);
       const bool hm = k - s >= 0, hp = k + s <= N, hmm = k - 2 * s >= 0;
       const int km = hm ? k - s : k, kp = hp ? k + s : k;
@@ -1663,7 +1667,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           for (int e = 0; e < 12; ++e) LN[(a0 * 6 + e) * NS + k] = out_l[e];
         }
       }
-      __syncthreads();                                    // everyone is done with D^-1 and L of this level
+      cta_sync();                                    // everyone is done with D^-1 and L of this level
       if (warp < 3 && live) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) DI[((2 * warp) * 6 + e) * NS + k] = dr[e];
@@ -1671,7 +1675,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       double* t_ = LC; LC = LN; LN = t_;
     }
     // D' of the last level is in DI, M in LC: invert, then rows of D'^-1 and D'^-1 M go to level 4 of the PCR store
-    __syncthreads();
+    cta_sync();
     MQ_T(10);
     if (warp == 3) {
       double S[36];
@@ -1683,7 +1687,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         for (int e = 0; e < 36; ++e) DI[e * NS + k] = S[e];
       }
     }
-    __syncthreads();
+    cta_sync();
     if (warp < 3 && live) {
       double2* const P2 = reinterpret_cast<double2*>(m.PCR) + (kPcrLevels - 1) * (kPcrLevelDoubles / 2) + (warp * 12) * NS + k;
       double M[36];
@@ -1709,7 +1713,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         }
       }
     }
-    __syncthreads();
+    cta_sync();
     MQ_T(11);
   }
 
@@ -1730,7 +1734,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
 #pragma unroll
       for (int e = 0; e < NS_; ++e) red[warp * (NM + NS_) + NM + e] = sm[e];
     }
-    __syncthreads();
+    cta_sync();
 #pragma unroll
     for (int e = 0; e < NM; ++e) {
       const double a0 = red[e], a1 = red[(NM + NS_) + e], a2 = red[2 * (NM + NS_) + e], a3 = red[3 * (NM + NS_) + e];
@@ -1739,7 +1743,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     }
 #pragma unroll
     for (int e = 0; e < NS_; ++e) sm[e] = (red[NM + e] + red[(NM + NS_) + NM + e]) + (red[2 * (NM + NS_) + NM + e] + red[3 * (NM + NS_) + NM + e]);
-    __syncthreads();
+    cta_sync();
   }
 
   // The whole osqp_solve of one QP for one role (AX: axis warp `warp` in 0..2; !AX: slack/obstacle warp).  The
@@ -1747,7 +1751,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
   // evaluated from registers by all four warps (update_info / check_termination / compute_rho_estimate of auxil.h);
   // only a rho change (re-factorisation) or a suspected infeasibility certificate parks the state and runs the
   // single-warp array code on warp 0.
-  template <bool AX> MQ_HD void solve_role(const int warp, volatile int* flag) {
+  template <bool AX> MQ_HD void solve_role(const int warp, volatile int* flag, volatile int* cmd) {
     constexpr int NVR = AX ? 3 : 4;
     constexpr int NOW = (R + 3) / 4;                    // obstacle rows owned per warp: row o belongs to warp o % 4
     constexpr int RW = NOW > 0 ? NOW : 1;
@@ -1778,6 +1782,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     double zo[RW], uo[RW], orh[RW], og3[3 * RW], olo[RW], odg[RW], ofs[3 * RW];
     int osl[RW]; bool oex[RW];
 
+    // b (slack inputs) stays WITHOUT the obstacle sums in registers; ps holds the sums of the last completed iteration
+    // (the position rows carry the matching part in ogp), so a burst can resume where the previous one stopped.
+    double r11[2] = {0.0, 0.0}, ps[2] = {0.0, 0.0};
+
     auto load = [&]() {
 #pragma unroll
       for (int e = 0; e < NVR; ++e) {
@@ -1800,7 +1808,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
         for (int t = 0; t < 2; ++t) { dsi[t] = DSI_(t, k); esd[t] = notfirst ? ESD_(t, k) : 0.0; esdn[t] = ESD_(t, kp); dgi[t] = DGI_(t, k); }
 #pragma unroll
         for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
-        slmask = 0;
+        slmask = 0; ps[0] = ps[1] = 0.0;              // b comes back complete from the array code
 #pragma unroll
         for (int o = 0; o < R; ++o) slmask |= (hasu && SLK_(o, k)) ? (1u << o) : 0u;
       }
@@ -1837,7 +1845,34 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     };
 
     // ---- one burst of ADMM iterations (auxil.h:67-112) in registers; the last one records delta_x, delta_u
+    // Slack role: r11 (rhs of the slack-input elimination) and the position-row terms rs that it produces are formed at
+    // the END of an iteration from the part of the rhs that does not depend on this iteration's obstacle rows, so that
+    // the axis warps never wait for them; the obstacle rows' part reaches the position rows through T4 (the row owner
+    // folds the slack elimination into what it writes) and r11 itself once all rows are in (after the next barrier).
+    auto slack_forward = [&]() {                      // !AX: r11, rs from b -> RS2
+      if constexpr (!AX) {
+        double f[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const double bn = dn1(b[t]);
+          const double v = b[2 + t] - esdn[t] * bn;
+          r11[t] = hasu ? v : 0.0;
+          f[t] = dgi[t] * r11[t];
+        }
+        const double rs0 = -fs[0] * f[0] - fs[3] * f[1], rs1 = -fs[1] * f[0] - fs[4] * f[1], rs2 = -fs[2] * f[0] - fs[5] * f[1];
+        if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); }
+      }
+    };
+    auto slack_obstacle_sums = [&]() {                // !AX: the obstacle rows' part of b (slack inputs) and of r11
+      if constexpr (!AX && R > 0) {
+        double s0 = 0.0, s1 = 0.0;                    // sum of t over the rows softened by sigma_d / sigma_s
+#pragma unroll
+        for (int o = 0; o < R; ++o) { const double t = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) s1 += t; else s0 += t; }
+        ps[0] = hasu ? s0 : 0.0; ps[1] = hasu ? s1 : 0.0;
+      }
+    };
     auto iterate = [&](const int niter) {
+      if constexpr (!AX) { slack_forward(); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
       for (int it = 0; it < niter; ++it) {
         const bool lastit = it == niter - 1;
         if (lastit && live) {                       // iterate k-1 for the infeasibility certificates (delta_x, delta_y)
@@ -1864,9 +1899,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
           bar_sync(kBarAll, 128);
           r0 += m.RS[k * 4 + cc];
-          // ---- PCR levels 0..3
+          // ---- PCR levels 0..3 (with assistants: level 0 only; they run levels 1..3 from registers)
+          constexpr int kRowLevels = ASSIST ? 1 : kPcrLevels - 1;
 #pragma unroll
-          for (int l = 0; l < kPcrLevels - 1; ++l) {
+          for (int l = 0; l < kRowLevels; ++l) {
             const int s = 1 << l, cur = l & 1;
             const int kmm = k - s >= 0 ? k - s : k, kpp = k + s <= N ? k + s : k;
             const double2* ra = RA2 + cur * 3 * NS;
@@ -1883,13 +1919,22 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             sa0 = fma(mt[1].y, a1.y, sa0); sa1 = fma(mt[4].y, a1.y, sa1); sg0 = fma(mt[7].y, c1.y, sg0); sg1 = fma(mt[10].y, c1.y, sg1);
             sa0 = fma(mt[2].x, a2.x, sa0); sa1 = fma(mt[5].x, a2.x, sa1); sg0 = fma(mt[8].x, c2.x, sg0); sg1 = fma(mt[11].x, c2.x, sg1);
             sa0 = fma(mt[2].y, a2.y, sa0); sa1 = fma(mt[5].y, a2.y, sa1); sg0 = fma(mt[8].y, c2.y, sg0); sg1 = fma(mt[11].y, c2.y, sg1);
-            // next level's matrices: issued before the barrier, consumed after it
-            const double2* mn = M + (l + 1) * (kPcrLevelDoubles / 2);
-#pragma unroll
-            for (int h = 0; h < 12; ++h) mt[h] = mn[h * NS];
             r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
-            if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
-            bar_sync(kBarAxis, 96);
+            if constexpr (ASSIST) {
+              if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
+              bar_arrive(kBarH1, 192);                     // hand over to the assistants; fetch the last level meanwhile
+              const double2* mn = M + (kPcrLevels - 1) * (kPcrLevelDoubles / 2);
+#pragma unroll
+              for (int h = 0; h < 12; ++h) mt[h] = mn[h * NS];
+              bar_sync(kBarH2, 192);                       // level 3 is in buffer 0
+            } else {
+              // next level's matrices: issued before the barrier, consumed after it
+              const double2* mn = M + (l + 1) * (kPcrLevelDoubles / 2);
+#pragma unroll
+              for (int h = 0; h < 12; ++h) mt[h] = mn[h * NS];
+              if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
+              bar_sync(kBarAxis, 96);
+            }
           }
           // ---- last level fused with D'^-1:  y = D'^-1 r_k - (D'^-1 M) r_partner   (buffer 0 holds the level-4 input)
           double y0, y1;
@@ -1925,21 +1970,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             racc[0] = -td[0]; racc[1] = -td[1]; racc[2] = 0.0;
           }
         } else {
-          // ---- leaf forward, slack part: eliminate s_{k+1,t} then sigma_{k,t}; what that does to the position rows
-          double r11[2];
-          {
-            double f[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const double bn = dn1(b[t]);
-              const double v = b[2 + t] - esdn[t] * bn;
-              r11[t] = hasu ? v : 0.0;
-              f[t] = dgi[t] * r11[t];
-            }
-            const double rs0 = -fs[0] * f[0] - fs[3] * f[1], rs1 = -fs[1] * f[0] - fs[4] * f[1], rs2 = -fs[2] * f[0] - fs[5] * f[1];
-            if (live) { RS2[k * 2] = make_double2(rs0, rs1); RS2[k * 2 + 1] = make_double2(rs2, 0.0); XR[k] = r11[0]; XR[NS + k] = r11[1]; }
-          }
+          // ---- leaf forward, slack part (eliminate s_{k+1,t} then sigma_{k,t}): RS2 was written at the end of the last
+          // iteration (or by the prologue); once every warp is past its obstacle rows, their part is added to r11
           bar_sync(kBarAll, 128);
+          if (it > 0) { slack_obstacle_sums(); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
           bar_sync(kBarY, 128);
           yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4];
           // ---- leaf backward: slack inputs, then slack states
@@ -1975,7 +2009,12 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             const double zn = v > olo[q] ? v : olo[q];
             zo[q] = zn; uo[q] = v - zn;
             const double t = orh[q] * (zn - uo[q]);
-            if (live) { T4[(4 * o) * NS + k] = og3[3 * q] * t; T4[(4 * o + 1) * NS + k] = og3[3 * q + 1] * t; T4[(4 * o + 2) * NS + k] = og3[3 * q + 2] * t; T4[(4 * o + 3) * NS + k] = t; }
+            // position rows get grad' t directly and, through the eliminated slack input of the row, fs dg t
+            const double ts_ = oex[q] ? odg[q] * t : 0.0;
+            if (live) {
+              T4[(4 * o) * NS + k] = fma(ofs[3 * q], ts_, og3[3 * q] * t); T4[(4 * o + 1) * NS + k] = fma(ofs[3 * q + 1], ts_, og3[3 * q + 1] * t);
+              T4[(4 * o + 2) * NS + k] = fma(ofs[3 * q + 2], ts_, og3[3 * q + 2] * t); T4[(4 * o + 3) * NS + k] = t;
+            }
           }
         }
         // ---- box rows
@@ -1999,22 +2038,23 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
             else { b[2] += t0; b[3] += t1; }
           }
         }
-        // ---- obstacle rows' contributions to the next right-hand side: positions (axis warps), slack inputs (warp 3)
-        if constexpr (R > 0) {
-          __syncthreads();
-          if constexpr (AX) {
+        // ---- obstacle rows' contributions to the next right-hand side: positions (axis warps) now; the slack warp only
+        // announces its own row and goes on to the next iteration's r11 / rs (its sums follow after the next barrier)
+        if constexpr (AX) {
+          if constexpr (R > 0) {
+            bar_sync(kBarT, 128);
             double sgo = 0.0;
 #pragma unroll
             for (int o = 0; o < R; ++o) sgo += T4[(4 * o + cc) * NS + k];
             ogp = hasu ? sgo : 0.0;
-          } else {
-            double s0 = 0.0, s1 = 0.0;             // sum of t over the rows softened by sigma_d / sigma_s
-#pragma unroll
-            for (int o = 0; o < R; ++o) { const double t = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) s1 += t; else s0 += t; }
-            if (hasu) { b[2] -= s0; b[3] -= s1; }
           }
+        } else {
+          if constexpr (R > 0) bar_arrive(kBarT, 128);
+          slack_forward();
         }
       }
+      // burst end: all obstacle rows of the last iteration are in; the slack warp completes its rhs
+      if constexpr (R > 0) { cta_sync(); slack_obstacle_sums(); }
     };
 
     // screening values for the infeasibility certificates (filled by info())
@@ -2034,7 +2074,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp, oo = o < R ? o : 0; eo_[q] = WSE_(NBR + oo, k); ouo_[q] = OU_(NBR + oo, k); }
       // exchange: positions for the obstacle rows' A x; obstacle multipliers for the position / slack-input columns' A' y.
       // The buffers are the iteration's: wait until every warp has consumed the last iteration's obstacle terms.
-      __syncthreads();
+      cta_sync();
       if constexpr (AX) { if (live) RA2[k * 3 + cc] = make_double2(x[0], x[1]); }
       else { if (live) { XR[k] = x[2]; XR[NS + k] = x[3]; } }
 #pragma unroll
@@ -2046,7 +2086,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           T4[(4 * o + 3) * NS + k] = yo;
         }
       }
-      __syncthreads();
+      cta_sync();
       double mx[15], sm[3];
 #pragma unroll
       for (int e = 0; e < 15; ++e) mx[e] = 0.0;
@@ -2142,24 +2182,24 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       if (!dr) maybe = maybe || ((s_ndx > edi) && (s_qd < -c * edi * s_ndx) && (s_pm < c * edi * s_ndx));
       if (!maybe) return false;
       park();
-      __syncthreads();
+      cta_sync();
       if (warp == 0) { const bool d = check_termination(approx); if (lane == 0) *flag = d ? 1 : 0; }
-      __syncthreads();
+      cta_sync();
       const int f = *flag;
-      __syncthreads();
+      cta_sync();
       return f != 0;
     };
 
     // ---- osqp_solve (osqp.h:78): same control flow as solve() below
     status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
     int iter = 0;
-    bool refactor = true, last_checked = false, approx = false;
+    bool refactor = true, last_checked = false, approx = false, reload = false;
     for (;;) {
       bool do_info, do_check, do_adapt = false;
       const bool final_pass = iter >= st.max_iter;
       if (!final_pass) {
         if (refactor) {
-          __syncthreads();                                // parked iterates / new Rh of all warps are visible to warp 0
+          cta_sync();                                // parked iterates / new Rh of all warps are visible to warp 0
           MQ_T0();
           if (warp == 0) {
             factor(); rows_phase<1>(); rhs_finish();      // leaf elimination + T blocks; whole right-hand side into B_
@@ -2170,11 +2210,16 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
           MQ_T(2);
           load();
           MQ_T(3);
-          refactor = false;
+          refactor = false; reload = true;
         }
         int nb = st.max_iter;
         if (st.check_termination) { int c2 = (iter / st.check_termination + 1) * st.check_termination; if (c2 < nb) nb = c2; }
         if (st.adaptive_rho && st.adaptive_rho_interval) { int c2 = (iter / st.adaptive_rho_interval + 1) * st.adaptive_rho_interval; if (c2 < nb) nb = c2; }
+        if constexpr (ASSIST) {                          // tell the assistants how long the burst is / to re-read the matrices
+          if (warp == 0 && lane == 0) { cmd[0] = nb - iter; cmd[1] = reload ? 1 : 0; }
+          bar_sync(kBarCmd, 224);
+          reload = false;
+        }
         { MQ_T0(); iterate(nb - iter); MQ_T(4); }
         iter = nb;
         do_check = st.check_termination && (iter % st.check_termination == 0);
@@ -2225,7 +2270,57 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
     park();
   }
 
-  MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag) {
+  // PCR assistant (threads 128..223 of an ASSIST block): axis warp `a` keeps its rows of the level 1..3 matrices in
+  // registers (144 of them) and runs those levels of every solve; the row warps hand the level-0 result over in
+  // buffer 1 (kBarH1) and take the level-3 result back from buffer 0 (kBarH2).  Commands arrive through cmd[]:
+  // cmd[0] = iterations of the next burst (< 0: the block is done), cmd[1] = the factorisation changed.
+  MQ_HD void assist_role(const int a, volatile int* cmd) {
+    const int k = lane < NS ? lane : NS - 1;
+    const bool live = lane < NS;
+    double2* const RA2 = reinterpret_cast<double2*>(m.RA);
+    const double2* const M = reinterpret_cast<const double2*>(m.PCR) + (a * 12) * NS + k;
+    double2 mt[3][12];
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+      for (int h = 0; h < 12; ++h) mt[l][h] = make_double2(0.0, 0.0);
+    for (;;) {
+      bar_sync(kBarCmd, 224);
+      const int n = cmd[0], rl = cmd[1];
+      if (n < 0) break;
+      if (rl) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+#pragma unroll
+          for (int h = 0; h < 12; ++h) mt[l][h] = M[(l + 1) * (kPcrLevelDoubles / 2) + h * NS];
+      }
+      for (int it = 0; it < n; ++it) {
+        bar_sync(kBarH1, 192);
+        double r0, r1;
+        { const double2 own = RA2[3 * NS + k * 3 + a]; r0 = own.x; r1 = own.y; }
+#pragma unroll
+        for (int l = 1; l < kPcrLevels - 1; ++l) {
+          const int s = 1 << l, cur = l & 1;
+          const int kmm = k - s >= 0 ? k - s : k, kpp = k + s <= N ? k + s : k;
+          const double2* ra = RA2 + cur * 3 * NS;
+          const double2 a0 = ra[kmm * 3], a1 = ra[kmm * 3 + 1], a2 = ra[kmm * 3 + 2];
+          const double2 c0 = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
+          const double2* w = mt[l - 1];
+          double sa0 = w[0].x * a0.x, sa1 = w[3].x * a0.x, sg0 = w[6].x * c0.x, sg1 = w[9].x * c0.x;
+          sa0 = fma(w[0].y, a0.y, sa0); sa1 = fma(w[3].y, a0.y, sa1); sg0 = fma(w[6].y, c0.y, sg0); sg1 = fma(w[9].y, c0.y, sg1);
+          sa0 = fma(w[1].x, a1.x, sa0); sa1 = fma(w[4].x, a1.x, sa1); sg0 = fma(w[7].x, c1.x, sg0); sg1 = fma(w[10].x, c1.x, sg1);
+          sa0 = fma(w[1].y, a1.y, sa0); sa1 = fma(w[4].y, a1.y, sa1); sg0 = fma(w[7].y, c1.y, sg0); sg1 = fma(w[10].y, c1.y, sg1);
+          sa0 = fma(w[2].x, a2.x, sa0); sa1 = fma(w[5].x, a2.x, sa1); sg0 = fma(w[8].x, c2.x, sg0); sg1 = fma(w[11].x, c2.x, sg1);
+          sa0 = fma(w[2].y, a2.y, sa0); sa1 = fma(w[5].y, a2.y, sa1); sg0 = fma(w[8].y, c2.y, sg0); sg1 = fma(w[11].y, c2.y, sg1);
+          r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
+          if (live) RA2[(1 - cur) * 3 * NS + k * 3 + a] = make_double2(r0, r1);
+          if (l < kPcrLevels - 2) bar_sync(kBarA, 96); else bar_arrive(kBarH2, 192);
+        }
+      }
+    }
+  }
+
+  MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag, volatile int* cmd = nullptr) {
     x0p = bt.x0 + (size_t)b * 8;
     // setup (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) builds the cold block in the still unused PCR
     // region of shared memory; the CTA then copies it to its global home in one pass
@@ -2235,16 +2330,16 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric)> str
       map_cold(m, keep.PCR, NS, R);
       load_and_scale<4>(bt, b, warp);           // all four warps; every thread ends with the same c, rho, |q| norms
       m = keep;
-      for (int i = threadIdx.x; i < cold_slots(R) * NS; i += blockDim.x) m.E[i] = m.PCR[i];
-      __syncthreads();
+      for (int i = threadIdx.x; i < cold_slots(R) * NS; i += 128) m.E[i] = m.PCR[i];
+      cta_sync();
       MQ_T(0);
     }
-    if (warp < 3) solve_role<true>(warp, flag); else solve_role<false>(warp, flag);
-    __syncthreads();
+    if (warp < 3) solve_role<true>(warp, flag, cmd); else solve_role<false>(warp, flag, cmd);
+    cta_sync();
     {
       MQ_T0();
       if (warp == 0) store(bt, b);
-      __syncthreads();
+      cta_sync();
       MQ_T(7);
     }
 #ifdef MPCQP_PHASE_TIMING

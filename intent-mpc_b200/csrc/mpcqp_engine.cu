@@ -102,22 +102,26 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
   }
 }
 
-// CTA kernel: persistent, one 4-warp CTA per QP at a time (mode 2 of mpcqp_core.cuh), two CTAs per SM.
-template <int RT>
-__global__ void __launch_bounds__(128, 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
-                                                                 const __grid_constant__ Batch bt, int ws_stride, int* counter) {
+// CTA kernel: persistent, one 4-warp CTA per QP at a time (mode 2 of mpcqp_core.cuh), two CTAs per SM.  ASSIST: the
+// block has the SM to itself and carries three more warps that keep the PCR matrices of levels 1..3 in registers.
+template <int RT, bool ASSIST>
+__global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+                                                                                        const __grid_constant__ Batch bt, int ws_stride, int* counter) {
   extern __shared__ double smem[];
-  __shared__ int s_next, s_flag;
+  __shared__ int s_next, s_flag, s_cmd[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Qp<30, RT, kModeCta> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  Qp<30, RT, kModeCta, ASSIST> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  if constexpr (ASSIST) {
+    if (warp >= 4) { qp.assist_role(warp - 4, s_cmd); return; }
+  }
   // queue 0: all instances in natural order.  queue 1: the hard list only.  queue 2: everything not flagged hard, then
   // whatever is left of the hard list (so an over-long hard list does not serialise on the one-per-SM launch).
   bool natural = bt.queue != 1;
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(counter + ((natural && bt.queue == 2) ? 3 : 0), 1);
-    __syncthreads();
+    cta_sync();
     const int idx = s_next;
-    __syncthreads();
+    cta_sync();
     int b = idx;
     if (natural) {
       if (idx >= bt.B) { if (bt.queue == 2) { natural = false; continue; } break; }
@@ -126,7 +130,11 @@ __global__ void __launch_bounds__(128, 2) mpcqp_solve_cta_kernel(const __grid_co
       if (idx >= *bt.nhard) break;
       b = bt.order[idx];
     }
-    qp.run_cta(bt, b, warp, &s_flag);
+    qp.run_cta(bt, b, warp, &s_flag, s_cmd);
+  }
+  if constexpr (ASSIST) {                                  // release the assistants
+    if (threadIdx.x == 0) s_cmd[0] = -1;
+    asm volatile("bar.sync 5, 224;" ::: "memory");
   }
 }
 
@@ -136,11 +144,11 @@ typedef void (*SolveKernel)(const Shape, const Settings, const Batch, int, int*)
 #define MPCQP_FAST_R_LIST X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #endif
 // want: 2 = CTA kernel if available, 1 = warp-fast kernel if available, 0 = generic.  *mode returns what was picked.
-static SolveKernel pick_kernel(int NS, int R, int want, int* mode) {
+static SolveKernel pick_kernel(int NS, int R, int want, int* mode, bool assist = false) {
   if (NS == 30 && want == kModeCta) {
     *mode = kModeCta;
     switch (R) {
-#define X(r) case r: return mpcqp_solve_cta_kernel<r>;
+#define X(r) case r: return assist ? mpcqp_solve_cta_kernel<r, true> : mpcqp_solve_cta_kernel<r, false>;
       MPCQP_FAST_R_LIST
 #undef X
       default: break;
@@ -187,7 +195,7 @@ struct mpcqp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
@@ -324,6 +332,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   int mode = kModeGeneric;
   // force_generic: 0 = best available (CTA kernel), 1 = generic kernel, 2 = warp-fast kernel
   const int want = e->force_generic == 1 ? kModeGeneric : (e->force_generic == 2 ? kModeWarp : kModeCta);
+  e->no_assist = e->force_generic == 3;           // 3 = CTA kernel without the assistant warps (A/B tests)
   SolveKernel kern = pick_kernel(sh.NS, sh.R, want, &mode);
   const int threads = mode == kModeCta ? 128 : 32;
   const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, mode) * sizeof(double);
@@ -349,13 +358,18 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     // the instances flagged hard (they run to max_iter and would otherwise form the tail of the batch) one per SM on
     // the main stream, everything else two per SM on the side stream, on whatever SMs the first launch leaves free.
     const size_t smem_solo = (size_t)e->max_smem_optin - 2048;   // more than half an SM: nothing else fits beside it
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
+    // one-per-SM launches use the variant with PCR assistant warps (224 threads, matrices of levels 1..3 in registers)
+    int mode_a = 0;
+    SolveKernel kern_solo = e->no_assist ? kern : pick_kernel(sh.NS, sh.R, want, &mode_a, true);
+    const int threads_solo = e->no_assist ? threads : 224;
+    CK(cudaFuncSetAttribute(kern_solo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
     if (bt.B <= e->num_sms || !bt.order) {
       const bool solo = bt.B <= e->num_sms;
       CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
       bt.ws = e->ws.as<double>();
       CK(cudaEventRecord(e->evs, e->stream));
-      kern<<<(unsigned)grid, threads, solo ? smem_solo : smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+      if (solo) kern_solo<<<(unsigned)grid, threads_solo, smem_solo, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+      else kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
       CK(cudaGetLastError());
       e->last_launches += 1;
       return MPCQP_OK;
@@ -367,7 +381,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     CK(cudaEventRecord(e->evf, e->stream));
     CK(cudaStreamWaitEvent(e->stream2, e->evf, 0));
     Batch bh = bt; bh.queue = 1; bh.ws = e->ws.as<double>();
-    kern<<<(unsigned)gh, threads, smem_solo, e->stream>>>(sh, st, bh, wsd, e->counter.as<int>());
+    kern_solo<<<(unsigned)gh, threads_solo, smem_solo, e->stream>>>(sh, st, bh, wsd, e->counter.as<int>());
     CK(cudaGetLastError());
     Batch bn = bt; bn.queue = 2; bn.ws = e->ws.as<double>() + (size_t)gh * wsd;
     kern<<<(unsigned)grid, threads, smem, e->stream2>>>(sh, st, bn, wsd, e->counter.as<int>());

@@ -141,8 +141,9 @@ class Engine:
         return {2: "cta", 1: "fast"}.get(int(self.lib.mpcqp_engine_last_path(self.h)), "generic")
 
     def force_generic(self, on=True):
-        """True / 1 / 'generic': generic kernel; 2 / 'fast': one-warp register kernel; False / 0: default dispatch."""
-        names = {"generic": 1, "fast": 2, "cta": 0}
+        """True / 1 / 'generic': generic kernel; 2 / 'fast': one-warp register kernel; 3 / 'cta_plain': CTA kernel without
+        the assistant warps on one-per-SM launches; False / 0 / 'cta': default dispatch."""
+        names = {"generic": 1, "fast": 2, "cta": 0, "cta_plain": 3}
         code = names[on] if isinstance(on, str) else (1 if on is True else int(on))
         self._check(self.lib.mpcqp_engine_force_generic(self.h, C.c_int(code)))
 

@@ -34,17 +34,17 @@ def test_gpu_matches_reference_golden(eng, name):
     assert np.abs((out["obj"] - g[name + "_obj"]) / g[name + "_obj"]).max() < TOL
 
 
-@pytest.mark.parametrize("path", ["generic", "fast"])
+@pytest.mark.parametrize("path", ["generic", "fast", "cta_plain"])
 @pytest.mark.parametrize("name", ["snapshot", "static4", "static0", "static8"])
 def test_other_kernels_match_reference_golden(eng, name, path):
     """The one-warp kernels — generic shared-memory (used for horizons / obstacle counts without a compiled
-    specialisation) and register-resident — on the same golden cases; the default dispatch above runs them on the
-    CTA kernel."""
+    specialisation) and register-resident — and the CTA kernel without its assistant warps on the same golden cases;
+    the default dispatch above runs them on the CTA kernel (with assistants where a CTA has an SM to itself)."""
     g = np.load(GOLD)
     eng.force_generic(path)
     try:
         out = eng.solve_mpc_batch(cases()[name])
-        assert eng.last_path == path
+        assert eng.last_path == ("cta" if path == "cta_plain" else path)
     finally:
         eng.force_generic(False)
     assert (out["status"] == g[name + "_status"]).all()
