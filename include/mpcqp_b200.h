@@ -94,6 +94,10 @@ int mpcqp_engine_force_generic(mpcqp_engine* e, int on);
  * the next call has the same batch size and num_obs (a receding-horizon loop: slot b is the same scenario one control
  * step later), starts the slots that ran long first, one per SM.  Results never depend on it.  0 switches it off. */
 int mpcqp_engine_use_history(mpcqp_engine* e, int on);
+/* Layout of the obs_dyn argument of the batched entry point: 0 (default) = one [N][R] pattern shared by the batch (the
+ * candidates of one control step), 1 = [B][N][R], one pattern per instance (Monte-Carlo sweeps where every instance has
+ * its own mix of dynamic and static obstacles; updateObstacleParam's flags, mpcPlanner.cpp:1148-1197). */
+int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on);
 /* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */
 int mpcqp_engine_sync(mpcqp_engine* e);
 /* FP64 FMA-pipe microbenchmark (all SMs, 8 independent DFMA chains per thread): the measured roofline
@@ -111,7 +115,8 @@ void* mpcqp_engine_stream(const mpcqp_engine* e);
  *   obs_c    [B][N][R][3]  obstacle centre per stage             (updateObstacleParam, mpcPlanner.cpp:1148-1197)
  *   obs_semi [B][N][R][3]  semi-axes = size/2 + safety distance
  *   obs_yaw  [B][N][R]
- *   obs_dyn  [N][R] int32  1: row is softened by slack input 3 (dynamic), 0: by slack input 4 (static)
+ *   obs_dyn  [N][R] int32  1: row is softened by slack input 3 (dynamic), 0: by slack input 4 (static); HOST pointer in
+ *                          both forms; [B][N][R] after mpcqp_engine_obs_dyn_per_instance(e, 1)
  *   lin_pt   [B][N][3]     linearisation point (previous plan, unshifted, or current position; :1042-1051)
  *   warm_x   [B][n] or NULL  primal warm start (previous plan; dual warm start is always 0, :487)
  * Outputs: x [B][n]; y [B][m] or NULL; status/iter/rho_updates [B] int32; obj/pri_res/dua_res [B].

@@ -68,7 +68,7 @@ struct Settings {           // third_party/osqp/types.h:139-176 (subset that aff
 
 struct Batch {              // device pointers
   const double* pd;             // [NS*13] diagonal of P per stage variable (batch-uniform)
-  const unsigned char* slack;   // [(NS-1)*R] 0: row uses slack input 3 (dynamic), 1: slack input 4 (static)
+  const unsigned char* slack;   // [(NS-1)*R] 0: row uses slack input 3 (dynamic), 1: slack input 4 (static); per instance if slack_stride
   const double* q;              // [B][n]   linear cost, reference variable order
   const double* x0;             // [B][8]   stage-0 equality right-hand side is -x0
   const double* g;              // [B][NS-1][R][3] obstacle-row gradients
@@ -84,6 +84,7 @@ struct Batch {              // device pointers
   const int* hard;              // [B] hard flags, or nullptr
   const int* nhard;             // number of hard instances (device scalar), or nullptr
   int queue;                    // 0: one queue over all B; 1: hard instances only; 2: the others only
+  int slack_stride;             // 0: one slack pattern for the batch; (NS-1)*R: one per instance
   long long* dbg;               // [B][8] per-phase clock64 totals (only with MPCQP_PHASE_TIMING), or nullptr
   int B;
 };
@@ -2322,6 +2323,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 
   MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag, volatile int* cmd = nullptr) {
     x0p = bt.x0 + (size_t)b * 8;
+    slack = bt.slack + (size_t)b * bt.slack_stride;
     // setup (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) builds the cold block in the still unused PCR
     // region of shared memory; the CTA then copies it to its global home in one pass
     {
@@ -2417,6 +2419,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   }
   MQ_HD void run(const Batch& bt, int b) {
     x0p = bt.x0 + (size_t)b * 8;
+    slack = bt.slack + (size_t)b * bt.slack_stride;
     load_and_scale(bt, b);
     solve();
     store(bt, b);

@@ -195,7 +195,7 @@ struct mpcqp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
@@ -267,6 +267,7 @@ extern "C" double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e) { ret
 extern "C" int64_t mpcqp_engine_last_launches(const mpcqp_engine* e) { return e ? e->last_launches : 0; }
 extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->last_fast : -1; }
 extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
+extern "C" int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->dyn_per_instance = on ? 1 : 0; return MPCQP_OK; }
 extern "C" int mpcqp_engine_use_history(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->use_history = on ? 1 : 0; if (!on) e->hist_B = 0; return MPCQP_OK; }
 #ifdef MPCQP_PHASE_TIMING
 extern "C" int mpcqp_debug_phase_clocks(mpcqp_engine* e, long long* out, int B) {   // development builds only
@@ -416,8 +417,9 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   CK(cudaSetDevice(e->device));
   CK(e->pd.need(pd.size() * sizeof(double)));
   CK(cudaMemcpyAsync(e->pd.p, pd.data(), pd.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  std::vector<unsigned char> slk((size_t)N * (R > 0 ? R : 1), 0);
-  for (int i = 0; i < N * R; ++i) slk[i] = obs_dyn_host[i] ? 0 : 1;   // MP.cpp:1064-1069
+  const size_t nflag = (size_t)N * R * (e->dyn_per_instance ? B : 1);
+  std::vector<unsigned char> slk(nflag ? nflag : 1, 0);
+  for (size_t i = 0; i < nflag; ++i) slk[i] = obs_dyn_host[i] ? 0 : 1;   // MP.cpp:1064-1069
   CK(e->slack.need(slk.size()));
   CK(cudaMemcpyAsync(e->slack.p, slk.data(), slk.size(), cudaMemcpyHostToDevice, e->stream));
   CK(e->q.need((size_t)B * sh.n * sizeof(double)));
@@ -451,7 +453,7 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
     e->last_launches += 2;
   }
   Batch bt; memset(&bt, 0, sizeof bt);
-  bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
+  bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.slack_stride = e->dyn_per_instance ? N * R : 0; bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
   bt.warm_x = warm_x; bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates;
   bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>(); bt.hard = e->hard.as<int>();
 #ifdef MPCQP_PHASE_TIMING

@@ -174,6 +174,7 @@ class Engine:
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         x0, xref, oc, os_, oy, lp, wx = map(f, (mb.x0, mb.xref, mb.obs_c, mb.obs_semi, mb.obs_yaw, mb.lin_pt, mb.warm_x))
         od = np.ascontiguousarray(mb.obs_dyn, dtype=np.int32)
+        self._check(self.lib.mpcqp_engine_obs_dyn_per_instance(self.h, C.c_int(1 if od.ndim == 3 else 0)))
         if out is None:
             out = dict(x=np.empty((B, n)), y=np.empty((B, m)) if want_y else None, status=np.empty(B, np.int32),
                        iter=np.empty(B, np.int32), rho_updates=np.empty(B, np.int32), obj=np.empty(B),
@@ -194,6 +195,7 @@ class Engine:
         engine stream (call sync()); device=False: host pointers, synchronous."""
         p = params_to_c(params)
         od = np.ascontiguousarray(obs_dyn, dtype=np.int32)
+        self._check(self.lib.mpcqp_engine_obs_dyn_per_instance(self.h, C.c_int(1 if od.ndim == 3 else 0)))
         g = lambda k: C.c_void_p(ptrs.get(k) or None)
         fn = self.lib.mpcqp_solve_mpc_batch_device if device else self.lib.mpcqp_solve_mpc_batch_host
         rc = fn(self.h, C.byref(p), C.byref(settings), C.c_int32(B), C.c_int32(R), g("x0"), g("xref"), g("obs_c"),

@@ -175,3 +175,104 @@ def stress_batch(B: int, seed0: int = 0, num_obs: int = 2) -> MpcBatch:
         mb.xref[b] = mb.x0[b, None, 0:3] + d[None, :] * 1.2 * (np.arange(N + 1) * p.ts)[:, None]
     mb.warm_x, mb.lin_pt = _const_vel_plan(p, mb.x0)
     return mb
+
+
+# ---- BASELINE.json configs[4]: Monte-Carlo sweep -------------------------------------------------------------------
+SWEEP_OBSTACLES = (50, 100, 200)                       # docker/README.md:1004-1014 (run_mpc_benchmark grid)
+SWEEP_LIMITS = ((1.5, 1.5), (3.0, 3.0), (5.0, 20.0))   # (max_vel, max_acc)
+SWEEP_DYNAMIC_RATIO = 0.65
+SWEEP_FIELD = ((5.0, 105.0), (-15.0, 15.0), (0.0, 7.0))  # dynus_obstacles_node.cpp:61-66
+SWEEP_RADIUS = 30.0                                    # fake_detector_param.yaml:2
+SWEEP_CAP = 32                                         # rows per stage kept (nearest first); reported by sweep_groups
+SWEEP_CLEARANCE = 3.0                                  # obstacles closer than this to the start are dropped (the UAV is flying)
+SWEEP_CHUNK = 4096
+ROBOT_SIZE = np.array([0.5, 0.5, 0.3])                 # mapping_param.yaml:11
+
+
+def _sweep_chunk(chunk: int, seed0: int):
+    """Instances [chunk*SWEEP_CHUNK, (chunk+1)*SWEEP_CHUNK) of the sweep, vectorised; one Generator per chunk so that a
+    multi-GPU shard can regenerate exactly its own index range."""
+    C_ = SWEEP_CHUNK
+    r = np.random.default_rng([seed0, chunk])
+    idx = chunk * C_ + np.arange(C_)
+    scen = idx % 9
+    nobs = np.array(SWEEP_OBSTACLES)[scen % 3]
+    lim = scen // 3
+    vmax = np.array([l[0] for l in SWEEP_LIMITS])[lim]
+    pos = np.stack([r.uniform(5, 95, C_), r.uniform(-3, 3, C_), r.uniform(1, 4, C_)], axis=1)
+    vel = r.uniform(-0.6, 0.6, (C_, 3)) * vmax[:, None]
+    speed = r.uniform(0.3, 1.0, C_) * vmax
+    M = max(SWEEP_OBSTACLES)
+    f = SWEEP_FIELD
+    oc = np.stack([r.uniform(f[0][0], f[0][1], (C_, M)), r.uniform(f[1][0], f[1][1], (C_, M)), r.uniform(f[2][0], f[2][1], (C_, M))], axis=2)
+    dyn = r.uniform(size=(C_, M)) < SWEEP_DYNAMIC_RATIO
+    ang = r.uniform(-np.pi, np.pi, (C_, M)); spd = r.uniform(0.5, 2.0, (C_, M))
+    ov = np.stack([np.cos(ang) * spd, np.sin(ang) * spd, np.zeros((C_, M))], axis=2) * dyn[:, :, None]
+    pillar = r.uniform(size=(C_, M)) < 0.35
+    yaw = r.uniform(-np.pi / 2, np.pi / 2, (C_, M)) * (~dyn)        # updateObstacleParam: yaw 0 for dynamic obstacles
+    dist = np.linalg.norm(oc - pos[:, None, :], axis=2)
+    ok = (np.arange(M)[None, :] < nobs[:, None]) & (dist <= SWEEP_RADIUS) & (dist >= SWEEP_CLEARANCE)
+    return dict(idx=idx, lim=lim, pos=pos, vel=vel, speed=speed, oc=oc, ov=ov, dyn=dyn, pillar=pillar, yaw=yaw,
+                dist=np.where(ok, dist, np.inf), in_range=ok.sum(axis=1))
+
+
+def sweep_groups(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = None):
+    """BASELINE.json configs[4] (SURVEY.md §8d "Config 5"): instances [lo, hi) of the Monte-Carlo sweep over the
+    run_mpc_benchmark scenario grid — {50,100,200} obstacles in the 100 x 30 x 7 m field, 65 % of them moving, velocity /
+    acceleration limits (1.5,1.5), (3,3), (5,20) — one control step each.  Obstacles within 30 m of the UAV become
+    constraint rows, nearest first, capped at SWEEP_CAP per stage.  Every instance therefore has its own obstacle
+    count and its own mix of dynamic / static rows (updateObstacleParam order: dynamic first; the isDyamic quirk,
+    mpcPlanner.cpp:1194, flags the first min(S, D) dynamic ones static).  Moving obstacles are predicted at constant
+    velocity over the horizon (the FORWARD intent of dynamicPredictor.cpp:351-501, closed form).
+
+    Returns (groups, meta): groups = list of (index array, MpcBatch) with one batch per (limits, obstacle count) pair —
+    the QP dimensions are batch-uniform — whose obs_dyn is [B,N,R] (per instance); meta counts capped instances."""
+    base = params or MpcParams()
+    N = base.N
+    t = np.arange(N) * base.ts
+    parts = []
+    for chunk in range(lo // SWEEP_CHUNK, (hi - 1) // SWEEP_CHUNK + 1):
+        c = _sweep_chunk(chunk, seed0)
+        sel = (c["idx"] >= lo) & (c["idx"] < hi)
+        parts.append({k: v[sel] for k, v in c.items()})
+    c = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    Bt = len(c["idx"])
+    order = np.argsort(c["dist"], axis=1, kind="stable")[:, :SWEEP_CAP]
+    take = lambda a: np.take_along_axis(a, order if a.ndim == 2 else order[:, :, None], axis=1)
+    dist = take(c["dist"]); valid = np.isfinite(dist)
+    R_i = valid.sum(axis=1)
+    dyn = take(c["dyn"]) & valid
+    # dynamic rows first, then static, each nearest first (stable sort on the key "not dynamic", invalid last)
+    key = np.where(valid, np.where(dyn, 0, 1), 2)
+    perm = np.argsort(key, axis=1, kind="stable")
+    take2 = lambda a: np.take_along_axis(a, perm if a.ndim == 2 else perm[:, :, None], axis=1)
+    oc = take2(take(c["oc"])); ov = take2(take(c["ov"])); dyn = take2(dyn); pillar = take2(take(c["pillar"])); yaw = take2(take(c["yaw"]))
+    D_i = dyn.sum(axis=1); S_i = R_i - D_i
+    groups = []
+    for li, (vm, am) in enumerate(SWEEP_LIMITS):
+        for R in range(SWEEP_CAP + 1):
+            g = np.nonzero((c["lim"] == li) & (R_i == R))[0]
+            if len(g) == 0:
+                continue
+            p = dataclasses.replace(base, max_vel=vm, max_acc=am)
+            B = len(g)
+            x0 = np.concatenate([c["pos"][g], c["vel"][g]], axis=1)
+            d = GOAL[None, :] - c["pos"][g]
+            d = d / np.linalg.norm(d, axis=1, keepdims=True)
+            xref = c["pos"][g][:, None, :] + d[:, None, :] * (c["speed"][g][:, None, None] * (np.arange(N + 1) * p.ts)[None, :, None])
+            o_c = oc[g][:, None, :R, :] + ov[g][:, None, :R, :] * t[None, :, None, None]
+            dy = dyn[g][:, :R]
+            static_size = np.where(pillar[g][:, :R, None], np.array([0.4, 0.4, 4.0])[None, None, :], np.array([0.4, 4.0, 0.4])[None, None, :])
+            semi = np.where(dy[:, :, None], (np.array([0.8, 0.8, 0.8]) + ROBOT_SIZE)[None, None, :] / 2 + p.dynamic_safety_dist,
+                            static_size / 2 + p.static_safety_dist)
+            flags = dy.astype(np.int32)
+            quirk = np.arange(R)[None, :] < np.minimum(S_i[g], D_i[g])[:, None]     # isDyamic[j][i] = 0 for i < numStatic
+            flags[quirk] = 0
+            warm_x, lin_pt = _const_vel_plan(p, x0)
+            mb = MpcBatch(p, x0, xref, np.ascontiguousarray(o_c), np.ascontiguousarray(np.broadcast_to(semi[:, None], (B, N, R, 3))),
+                          np.ascontiguousarray(np.broadcast_to(yaw[g][:, None, :R], (B, N, R))),
+                          np.ascontiguousarray(np.broadcast_to(flags[:, None, :], (B, N, R))), lin_pt, warm_x)
+            groups.append((c["idx"][g], mb))
+    meta = dict(instances=Bt, capped=int((c["in_range"] > SWEEP_CAP).sum()), cap=SWEEP_CAP,
+                obstacle_rows_hist=np.bincount(R_i, minlength=SWEEP_CAP + 1))
+    return groups, meta
