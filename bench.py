@@ -287,6 +287,33 @@ def run_b200(args, rank, world, local_rank):
             eng.solve_mpc_batch(m1); lat.append(eng.last_kernel_ms)
         lat = np.sort(np.array(lat))
         extras["single_qp_latency_ms"] = {"p50": float(lat[len(lat) // 2]), "p90": float(lat[int(0.9 * len(lat))]), "max": float(lat[-1]), "samples": len(lat)}
+        # BASELINE.json configs[4]: a slice of the Monte-Carlo sweep (per-instance obstacle counts up to 32 rows per stage,
+        # three launches: one per velocity/acceleration limit pair), device kernels only; the CPU reference on a sample of it
+        Bs = 16384
+        sb, smeta = W.sweep_batches(rank * Bs, (rank + 1) * Bs)
+        for _ in range(2):
+            sms = 0.0; sit = 0; shist = {}
+            for _, smb in sb:
+                so = eng.solve_mpc_batch(smb); sms += eng.last_kernel_ms; sit += int(so["iter"].sum())
+                for k_, v_ in _hist(so["status"]).items():
+                    shist[k_] = shist.get(k_, 0) + v_
+        sw = {"instances_per_gpu": Bs, "value": Bs / (sms * 1e-3), "unit": UNIT, "ms": sms, "iterations_total": sit, "launches": len(sb),
+              "rows_per_stage_cap": smeta["cap"], "capped_instances": smeta["capped"], "status_hist": shist,
+              "note": "configs[4] slice; every instance has its own obstacle count (7..32) and dynamic/static mix; device kernels only"}
+        if not args.no_cpu_baseline:
+            from oracle import bindings as OB2
+            from tests.helpers import oracle_solve
+            if OB2.RefOsqp.available():
+                o2 = OB2.RefOsqp()
+                sg, _ = W.sweep_groups(rank * Bs, rank * Bs + 2048)
+                sg = [g_ for g_ in sg if g_[1].num_obs == smeta["cap"]]          # the three large groups: enough QPs per call to fill the cores
+                nq = sum(g_[1].B for g_ in sg)
+                t0 = time.perf_counter()
+                for _, g_ in sg:
+                    oracle_solve(o2, g_, nthreads=os.cpu_count() or 1)
+                sw["cpu_reference"] = {"value": nq / (time.perf_counter() - t0), "unit": UNIT, "cores": os.cpu_count() or 1,
+                                       "sample": f"{nq} instances with {smeta['cap']} rows per stage out of the first 2048, assembly by pattern group + libosqp one QP per thread (includes the numpy assembly)"}
+        extras["sweep"] = sw
     except Exception as ex:
         extras["error"] = repr(ex)
 

@@ -98,6 +98,12 @@ int mpcqp_engine_use_history(mpcqp_engine* e, int on);
  * candidates of one control step), 1 = [B][N][R], one pattern per instance (Monte-Carlo sweeps where every instance has
  * its own mix of dynamic and static obstacles; updateObstacleParam's flags, mpcPlanner.cpp:1148-1197). */
 int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on);
+/* Per-instance obstacle counts for the batched entry point (Monte-Carlo sweeps: every instance sees its own number of
+ * obstacles).  nobs = host array [B] with 0 <= nobs[b] <= num_obs, or NULL to switch back.  While set, num_obs is the
+ * STRIDE of the obstacle arrays (instance b uses rows 0 .. nobs[b]-1 of every stage, the rest is padding that is never
+ * read), its QP has m_b = 16*horizon + 5*N + nobs[b]*N constraints laid out compactly at y + b*m (m from num_obs).
+ * Needs horizon 30 and 1 <= num_obs <= 32.  The pointer is read at every call until it is replaced. */
+int mpcqp_engine_num_obs_per_instance(mpcqp_engine* e, const int32_t* nobs);
 /* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */
 int mpcqp_engine_sync(mpcqp_engine* e);
 /* FP64 FMA-pipe microbenchmark (all SMs, 8 independent DFMA chains per thread): the measured roofline

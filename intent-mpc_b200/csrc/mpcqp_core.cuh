@@ -85,6 +85,8 @@ struct Batch {              // device pointers
   const int* nhard;             // number of hard instances (device scalar), or nullptr
   int queue;                    // 0: one queue over all B; 1: hard instances only; 2: the others only
   int slack_stride;             // 0: one slack pattern for the batch; (NS-1)*R: one per instance
+  const int* nobs;              // [B] obstacle rows per stage of each instance (wide CTA kernel only; R is then the stride of
+                                // g / low / slack and m the stride of y), or nullptr
   long long* dbg;               // [B][8] per-phase clock64 totals (only with MPCQP_PHASE_TIMING), or nullptr
   int B;
 };
@@ -108,6 +110,7 @@ struct Mem {
   double *E, *D, *DY, *DX;                               // always in global scratch
   double *PCR, *WK, *RA, *RS, *YB;                          // mode 2, shared: PCR matrices, r ping-pong, slack part of r, y
   double *PD, *PL, *PI, *OG, *OX, *OU;                           // mode 2, global: PCR factor workspace (D, L x2, D^-1); parked obstacle part of the rhs
+  double *ROW;                                                   // mode 2 wide, shared: obstacle rows' z, u, Rh, low, gradient ([7 R] slots)
 };
 MQ_HHD int hot_slots(int R, int mode) {
   return (NBR + R) + NV + NV + 3 * R + R + (mode == kModeWarp ? 6 : NV) + 36 + 36 + 2 + 2 + 2 + 6 + 3 + 12;
@@ -117,8 +120,8 @@ MQ_HHD int iter_slots(int R) { return NV + 2 * (NBR + R) + NV + 8 + 3; }
 // slots so that the setup phase can build it in shared memory (in the not-yet-used PCR region) and copy it out once.
 MQ_HHD int cold_slots(int R) { return 2 * (NBR + R) + 2 * NV + (NBR + R) + NV + NV + 3 * R + R + iter_slots(R); }
 constexpr int kWorkSlots = 108;             // PCR factor workspace: D / D^-1, L, next L (36 slots each); r / y exchange buffers alias it
-MQ_HHD int smem_doubles(int NS, int R, int mode) {
-  if (mode == kModeCta) return kPcrDoubles + kWorkSlots * NS;
+MQ_HHD int smem_doubles(int NS, int R, int mode, bool wide = false) {
+  if (mode == kModeCta) return kPcrDoubles + (kWorkSlots + (wide ? 7 * R : 0)) * NS;
   return (hot_slots(R, mode) + (mode == kModeWarp ? 0 : iter_slots(R))) * NS + 72;
 }
 MQ_HHD int ws_doubles(int NS, int R, int mode) {
@@ -140,7 +143,7 @@ MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) 
   double* g = ws;
   if (mode == kModeCta) {
     m.PCR = p; p += kPcrDoubles;
-    m.WK = p; m.RA = p; m.RS = p + 2 * 6 * NS; m.YB = p + 2 * 6 * NS + 4 * NS;
+    m.WK = p; m.RA = p; m.RS = p + 2 * 6 * NS; m.YB = p + 2 * 6 * NS + 4 * NS; m.ROW = p + kWorkSlots * NS;
     g = map_cold(m, g, NS, R);
     // T blocks (SI) and couplings (GG, 12 slots used) are staged in the factor workspace: LN slots / tail of the LC slots
     m.W = g; g += NV * NS; m.SI = m.WK + 72 * NS; m.GG = m.WK + 60 * NS; m.DSI = g; g += 2 * NS; m.ESD = g; g += 2 * NS;
@@ -150,7 +153,7 @@ MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) 
   }
   m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
   const bool fast = mode == kModeWarp;
-  m.PCR = m.WK = m.RA = m.RS = m.YB = m.PD = m.PL = m.PI = m.OG = m.OX = m.OU = nullptr;
+  m.PCR = m.WK = m.RA = m.RS = m.YB = m.PD = m.PL = m.PI = m.OG = m.OX = m.OU = m.ROW = nullptr;
   m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
   m.W = p; p += (fast ? 6 : NV) * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
   m.DGI = p; p += 2 * NS; m.FS = p; p += 6 * NS; m.DAI = p; p += 3 * NS; m.CV = p; p += 12 * NS; m.PK = p; p += 72;
@@ -162,6 +165,13 @@ MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) 
 template <int NST, int RT> struct DimsT {
   static constexpr int NS = NST, N = NST - 1, R = RT, MK = NBR + RT;
   MQ_HHD DimsT(int, int) {}
+};
+// CTA mode with a run-time obstacle count (9 .. kWideMax rows per stage): the rows' state lives in shared memory
+constexpr int kWideR = -1, kWideMax = 32;
+template <int NST> struct DimsT<NST, kWideR> {
+  static constexpr int NS = NST, N = NST - 1;
+  int R, MK;
+  MQ_HHD DimsT(int, int r) : R(r), MK(NBR + r) {}
 };
 template <> struct DimsT<0, 0> {
   int NS, N, R, MK;
@@ -206,6 +216,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   using Dm::NS; using Dm::N; using Dm::R; using Dm::MK;
   static constexpr bool kFast = QMODE == kModeWarp;
   static constexpr bool kCta = QMODE == kModeCta;
+  static constexpr bool kWide = RT == kWideR;            // run-time R, obstacle rows in shared memory (CTA mode only)
+  static constexpr int RC = kWide ? 0 : RT;              // compile-time R of the register-row code (none in wide mode)
+  static_assert(!kWide || (QMODE == kModeCta && ASSIST), "wide mode is a one-per-SM CTA kernel");
   static_assert(QMODE == kModeGeneric || NST > 0, "modes 1 and 2 need compile-time dims");
   static_assert(QMODE != kModeCta || NST == 30, "the CTA path is built for horizon 30 (5 PCR levels)");
   static constexpr int kWS = 6;    // fast mode: W holds one 6-vector per stage, stage-major (16-byte aligned rows)
@@ -214,6 +227,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   // slots mid+1..N.
   MQ_HD int cslot(int k) const { return k <= NS / 2 ? k : (NS / 2 + 1) + (N - k); }
   Mem m; const Shape& sh; const Settings& st; int lane;
+  int Rs;                                        // stride of the obstacle-row inputs (= R unless instances carry their own count)
+  double *smem0, *ws0;
   const double* pd; const unsigned char* slack; const double* x0p;
   double c, cinv, rho, nq, nq_s;                 // cost scaling, current rho, |q|_inf norms (unscaled / scaled)
   double pri_res, dua_res, obj, nAx, nZ, nPx, nAty, pri_s, dua_s, nAx_s, nZ_s, nPx_s, nAty_s;
@@ -247,7 +262,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 #define WSD_(j, k) m.D[(j) * NS + (k)]
 #define WSDY_(i, k) m.DY[(i) * NS + (k)]
 #define WSDX_(j, k) m.DX[(j) * NS + (k)]
-#define SLK_(o, k) ((int)slack[(k) * R + (o)])
+#define SLK_(o, k) ((int)slack[(k) * Rs + (o)])
 #define PD_(e, k) m.PD[(e) * NS + (k)]
 #define PL_(buf, e, k) m.PL[((buf) * 36 + (e)) * NS + (k)]
 #define PI_(e, k) m.PI[(e) * NS + (k)]
@@ -343,7 +358,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     sm = wsum(sm); mx = wmax(mx);
 #if MQ_DEV
     if (nw > 1) {
-      double* red = m.YB;                       // exchange buffer outside the (aliased) PCR region
+      // exchange buffer outside the (aliased) PCR region; the wide cold block spills into the workspace: use its tail
+      double* red = kWide ? m.ROW + 7 * R * NS - 8 : m.YB;
       if (lane == 0) { red[2 * wi] = sm; red[2 * wi + 1] = mx; }
       cta_sync();
       double s2 = 0.0, m2 = 0.0;
@@ -360,8 +376,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   template <int NW = 1> MQ_NOINL void load_and_scale(const Batch& bt, int b, const int wi = 0) {
     constexpr int nw = NW;
     const double* q = bt.q + (size_t)b * sh.n;
-    const double* gp = bt.g + (size_t)b * N * R * 3;
-    const double* lp = bt.low + (size_t)b * N * R;
+    const double* gp = bt.g + (size_t)b * N * Rs * 3;
+    const double* lp = bt.low + (size_t)b * N * Rs;
     MQ_FOR_STAGES(k) {
       for (int j = wi; j < NV; j += nw) {
         bool ex = j < nvars(k);
@@ -372,10 +388,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
       for (int i = wi; i < MK; i += nw) { RH_(i, k) = 1.0; Z_(i, k) = 0.0; U_(i, k) = 0.0; }  // RH holds E during Ruiz
       for (int o = wi; o < R; o += nw) {
         bool ex = k < N;
-        G3_(3 * o, k) = ex ? gp[(k * R + o) * 3] : 0.0;
-        G3_(3 * o + 1, k) = ex ? gp[(k * R + o) * 3 + 1] : 0.0;
-        G3_(3 * o + 2, k) = ex ? gp[(k * R + o) * 3 + 2] : 0.0;
-        LO_(o, k) = ex ? lp[k * R + o] : 0.0;
+        G3_(3 * o, k) = ex ? gp[(k * Rs + o) * 3] : 0.0;
+        G3_(3 * o + 1, k) = ex ? gp[(k * Rs + o) * 3 + 1] : 0.0;
+        G3_(3 * o + 2, k) = ex ? gp[(k * Rs + o) * 3 + 2] : 0.0;
+        LO_(o, k) = ex ? lp[k * Rs + o] : 0.0;
       }
       if (wi == 0) {
         for (int r = 0; r < 8; ++r) TD_(r, k) = 0.0;
@@ -1754,7 +1770,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   // single-warp array code on warp 0.
   template <bool AX> MQ_HD void solve_role(const int warp, volatile int* flag, volatile int* cmd) {
     constexpr int NVR = AX ? 3 : 4;
-    constexpr int NOW = (R + 3) / 4;                    // obstacle rows owned per warp: row o belongs to warp o % 4
+    constexpr int NOW = (RC + 3) / 4;                   // obstacle rows owned per warp: row o belongs to warp o % 4
+    constexpr bool kRows = kWide || RC > 0;             // the QP has obstacle rows
     constexpr int RW = NOW > 0 ? NOW : 1;
     const int cc = warp;
     const int k = lane < NS ? lane : NS - 1;            // ghost lanes shadow the last stage, never write
@@ -1766,6 +1783,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     double2* const YB2 = reinterpret_cast<double2*>(m.YB);      // [NS][3] pairs
     double* const XR = m.YB + 6 * NS;                           // [2][NS]   r11 of the slack-input elimination
     double* const T4 = XR + 2 * NS;                             // [R][4][NS] obstacle rows: (g0 t, g1 t, g2 t, t)
+    // wide mode: the rows of a warp (o = warp, warp + 4, ...) are kept in shared memory and each warp hands over only
+    // its partial sums TP[warp][5] = (sum w0 t, sum w1 t, sum w2 t, sum t | sigma_d, sum t | sigma_s)
+    double* const TP = T4;
+    double* const ZO = m.ROW; double* const UO = ZO + (kWide ? R * NS : 0); double* const ORH = UO + (kWide ? R * NS : 0);
+    double* const OLO = ORH + (kWide ? R * NS : 0); double* const OG3 = OLO + (kWide ? R * NS : 0);
     const double2* const M = reinterpret_cast<const double2*>(m.PCR) + ((AX ? cc : 0) * 12) * NS + k;
     const int kq = k >= 16 ? k - 16 : (k + 16 <= N ? k + 16 : k);
     auto vj = [&](int e) { return AX ? (e == 0 ? cc : (e == 1 ? 3 + cc : 8 + cc)) : (e < 2 ? 6 + e : 9 + e); };
@@ -1804,14 +1826,31 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         dai = DAI_(cc, k); cv0 = CV_(4 * cc, k); cv1 = CV_(4 * cc + 1, k); cv2 = CV_(4 * cc + 2, k); cv3 = CV_(4 * cc + 3, k);
         cv2m = notfirst ? CV_(4 * cc + 2, km) : 0.0; cv3m = notfirst ? CV_(4 * cc + 3, km) : 0.0;
         ogp = OG_(cc, k);
+        if constexpr (kWide) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) dgi[t] = DGI_(t, k);
+#pragma unroll
+          for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
+        }
       } else {
 #pragma unroll
         for (int t = 0; t < 2; ++t) { dsi[t] = DSI_(t, k); esd[t] = notfirst ? ESD_(t, k) : 0.0; esdn[t] = ESD_(t, kp); dgi[t] = DGI_(t, k); }
 #pragma unroll
         for (int e = 0; e < 6; ++e) fs[e] = FS_(e, k);
-        slmask = 0; ps[0] = ps[1] = 0.0;              // b comes back complete from the array code
+        ps[0] = ps[1] = 0.0;                          // b comes back complete from the array code
+        if constexpr (!kWide) {
+          slmask = 0;
 #pragma unroll
+          for (int o = 0; o < R; ++o) slmask |= (hasu && SLK_(o, k)) ? (1u << o) : 0u;
+        }
+      }
+      if constexpr (kWide) {
+        slmask = 0;
         for (int o = 0; o < R; ++o) slmask |= (hasu && SLK_(o, k)) ? (1u << o) : 0u;
+        if (live) for (int o = warp; o < R; o += 4) {
+          ZO[o * NS + k] = Z_(NBR + o, k); UO[o * NS + k] = U_(NBR + o, k); ORH[o * NS + k] = RH_(NBR + o, k); OLO[o * NS + k] = LO_(o, k);
+          OG3[(3 * o) * NS + k] = G3_(3 * o, k); OG3[(3 * o + 1) * NS + k] = G3_(3 * o + 1, k); OG3[(3 * o + 2) * NS + k] = G3_(3 * o + 2, k);
+        }
       }
 #pragma unroll
       for (int q = 0; q < NOW; ++q) {
@@ -1842,6 +1881,12 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           const int o = 4 * q + warp;
           if (o < R) { Z_(NBR + o, k) = zo[q]; U_(NBR + o, k) = uo[q]; WSDY_(NBR + o, k) = orh[q] * (uo[q] - OU_(NBR + o, k)); if (hasu) RH_(NBR + o, k) = orh[q]; }
         }
+        if constexpr (kWide) {
+          for (int o = warp; o < R; o += 4) {
+            const double zv = ZO[o * NS + k], uv = UO[o * NS + k], rv = ORH[o * NS + k];
+            Z_(NBR + o, k) = zv; U_(NBR + o, k) = uv; WSDY_(NBR + o, k) = rv * (uv - OU_(NBR + o, k)); if (hasu) RH_(NBR + o, k) = rv;
+          }
+        }
       }
     };
 
@@ -1865,10 +1910,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
       }
     };
     auto slack_obstacle_sums = [&]() {                // !AX: the obstacle rows' part of b (slack inputs) and of r11
-      if constexpr (!AX && R > 0) {
+      if constexpr (!AX && kRows) {
         double s0 = 0.0, s1 = 0.0;                    // sum of t over the rows softened by sigma_d / sigma_s
+        if constexpr (kWide) {
 #pragma unroll
-        for (int o = 0; o < R; ++o) { const double t = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) s1 += t; else s0 += t; }
+          for (int w = 0; w < 4; ++w) { s0 += TP[(5 * w + 3) * NS + k]; s1 += TP[(5 * w + 4) * NS + k]; }
+        } else {
+#pragma unroll
+          for (int o = 0; o < R; ++o) { const double t = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) s1 += t; else s0 += t; }
+        }
         ps[0] = hasu ? s0 : 0.0; ps[1] = hasu ? s1 : 0.0;
       }
     };
@@ -1882,6 +1932,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           OU_(di(0), k) = ud[0]; OU_(di(1), k) = ud[1];
 #pragma unroll
           for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R) OU_(NBR + o, k) = uo[q]; }
+          if constexpr (kWide) { for (int o = warp; o < R; o += 4) OU_(NBR + o, k) = UO[o * NS + k]; }
         }
         double xt[NVR], td[2], racc[NVR], yp0, yp1, yp2;
         if constexpr (AX) {
@@ -1952,7 +2003,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           }
           if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
           bar_sync(kBarY, 128);
-          if constexpr (NOW > 0) { yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4]; }
+          if constexpr (kRows) { yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4]; }
           // ---- leaf backward: acceleration of this axis
           xt[0] = y0; xt[1] = y1;
           {
@@ -2018,6 +2069,30 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             }
           }
         }
+        if constexpr (kWide) {
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, as0 = 0.0, as1 = 0.0;
+          const double r11d = XR[k], r11st = XR[NS + k];
+          const double sgd = hasu ? dgi[0] * (r11d - fs[0] * yp0 - fs[1] * yp1 - fs[2] * yp2) : 0.0;     // slack inputs of this stage
+          const double sgs = hasu ? dgi[1] * (r11st - fs[3] * yp0 - fs[4] * yp1 - fs[5] * yp2) : 0.0;
+          for (int o = warp; o < R; o += 4) {
+            const bool st_ = (slmask >> o) & 1u;
+            const double g0 = OG3[(3 * o) * NS + k], g1 = OG3[(3 * o + 1) * NS + k], g2 = OG3[(3 * o + 2) * NS + k];
+            const double zv = ZO[o * NS + k], uv = UO[o * NS + k], rv = ORH[o * NS + k], lv = OLO[o * NS + k];
+            const double zt = g0 * yp0 + g1 * yp1 + g2 * yp2 - (st_ ? sgs : sgd);
+            const double v = al * zt + om * zv + uv;
+            const double zn = v > lv ? v : lv;
+            const double un = v - zn;
+            if (live) { ZO[o * NS + k] = zn; UO[o * NS + k] = un; }
+            const double t = rv * (zn - un);
+            const double ts_ = hasu ? (st_ ? dgi[1] : dgi[0]) * t : 0.0;
+            a0 += fma(st_ ? fs[3] : fs[0], ts_, g0 * t); a1 += fma(st_ ? fs[4] : fs[1], ts_, g1 * t); a2 += fma(st_ ? fs[5] : fs[2], ts_, g2 * t);
+            if (st_) as1 += t; else as0 += t;
+          }
+          if (live) {
+            TP[(5 * warp) * NS + k] = a0; TP[(5 * warp + 1) * NS + k] = a1; TP[(5 * warp + 2) * NS + k] = a2;
+            TP[(5 * warp + 3) * NS + k] = as0; TP[(5 * warp + 4) * NS + k] = as1;
+          }
+        }
         // ---- box rows
 #pragma unroll
         for (int e = 0; e < NVR; ++e) {
@@ -2042,20 +2117,25 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         // ---- obstacle rows' contributions to the next right-hand side: positions (axis warps) now; the slack warp only
         // announces its own row and goes on to the next iteration's r11 / rs (its sums follow after the next barrier)
         if constexpr (AX) {
-          if constexpr (R > 0) {
+          if constexpr (kRows) {
             bar_sync(kBarT, 128);
             double sgo = 0.0;
+            if constexpr (kWide) {
 #pragma unroll
-            for (int o = 0; o < R; ++o) sgo += T4[(4 * o + cc) * NS + k];
+              for (int w = 0; w < 4; ++w) sgo += TP[(5 * w + cc) * NS + k];
+            } else {
+#pragma unroll
+              for (int o = 0; o < R; ++o) sgo += T4[(4 * o + cc) * NS + k];
+            }
             ogp = hasu ? sgo : 0.0;
           }
         } else {
-          if constexpr (R > 0) bar_arrive(kBarT, 128);
+          if constexpr (kRows) bar_arrive(kBarT, 128);
           slack_forward();
         }
       }
       // burst end: all obstacle rows of the last iteration are in; the slack warp completes its rhs
-      if constexpr (R > 0) { cta_sync(); slack_obstacle_sums(); }
+      if constexpr (kRows) { cta_sync(); slack_obstacle_sums(); }
     };
 
     // screening values for the infeasibility certificates (filled by info())
@@ -2085,6 +2165,18 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           const double yo = orh[q] * uo[q];
           T4[(4 * o) * NS + k] = og3[3 * q] * yo; T4[(4 * o + 1) * NS + k] = og3[3 * q + 1] * yo; T4[(4 * o + 2) * NS + k] = og3[3 * q + 2] * yo;
           T4[(4 * o + 3) * NS + k] = yo;
+        }
+      }
+      if constexpr (kWide) {                     // partial sums of A' y over this warp's rows
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, as0 = 0.0, as1 = 0.0;
+        for (int o = warp; o < R; o += 4) {
+          const double yo = ORH[o * NS + k] * UO[o * NS + k];
+          a0 += OG3[(3 * o) * NS + k] * yo; a1 += OG3[(3 * o + 1) * NS + k] * yo; a2 += OG3[(3 * o + 2) * NS + k] * yo;
+          if ((slmask >> o) & 1u) as1 += yo; else as0 += yo;
+        }
+        if (live) {
+          TP[(5 * warp) * NS + k] = a0; TP[(5 * warp + 1) * NS + k] = a1; TP[(5 * warp + 2) * NS + k] = a2;
+          TP[(5 * warp + 3) * NS + k] = as0; TP[(5 * warp + 4) * NS + k] = as1;
         }
       }
       cta_sync();
@@ -2125,8 +2217,13 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         aty[0] = rhb[0] * ub[0] - yd0; aty[1] = rhb[1] * ub[1] - yd1; aty[2] = rhb[2] * ub[2];
         if (hasu) {
           double gy = 0.0;
+          if constexpr (kWide) {
 #pragma unroll
-          for (int o = 0; o < R; ++o) gy += T4[(4 * o + cc) * NS + k];
+            for (int w = 0; w < 4; ++w) gy += TP[(5 * w + cc) * NS + k];
+          } else {
+#pragma unroll
+            for (int o = 0; o < R; ++o) gy += T4[(4 * o + cc) * NS + k];
+          }
           aty[0] += yn0 + gy; aty[1] += apv * yn0 + yn1; aty[2] += bpa * yn0 + bva * yn1;
         }
       } else {
@@ -2135,8 +2232,13 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         aty[0] = rhb[0] * ub[0] - yd0; aty[1] = rhb[1] * ub[1] - yd1; aty[2] = rhb[2] * ub[2]; aty[3] = rhb[3] * ub[3];
         if (hasu) {
           aty[2] += yn0; aty[3] += yn1;
+          if constexpr (kWide) {
 #pragma unroll
-          for (int o = 0; o < R; ++o) { const double yo = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) aty[3] -= yo; else aty[2] -= yo; }
+            for (int w = 0; w < 4; ++w) { aty[2] -= TP[(5 * w + 3) * NS + k]; aty[3] -= TP[(5 * w + 4) * NS + k]; }
+          } else {
+#pragma unroll
+            for (int o = 0; o < R; ++o) { const double yo = T4[(4 * o + 3) * NS + k]; if ((slmask >> o) & 1u) aty[3] -= yo; else aty[2] -= yo; }
+          }
         }
       }
 #pragma unroll
@@ -2146,6 +2248,17 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4], xs = XR[osl[q] * NS + k];
           row(og3[3 * q] * x0v + og3[3 * q + 1] * x1v + og3[3 * q + 2] * x2v - xs, zo[q], eo_[q]);
           cert(orh[q] * (uo[q] - ouo_[q]), eo_[q], olo[q], INFINITY);
+        }
+      }
+      if constexpr (kWide) {
+        if (hasu) {
+          const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4], xd = XR[k], xs_ = XR[NS + k];
+          for (int o = warp; o < R; o += 4) {
+            const double e_ = WSE_(NBR + o, k), uv = UO[o * NS + k], rv = ORH[o * NS + k];
+            row(OG3[(3 * o) * NS + k] * x0v + OG3[(3 * o + 1) * NS + k] * x1v + OG3[(3 * o + 2) * NS + k] * x2v - (((slmask >> o) & 1u) ? xs_ : xd),
+                ZO[o * NS + k], e_);
+            cert(rv * (uv - OU_(NBR + o, k)), e_, OLO[o * NS + k], INFINITY);
+          }
         }
       }
       cert(rhd[0] * (ud[0] - oud_[0]), ed_[0], bnd[0], bnd[0]); cert(rhd[1] * (ud[1] - oud_[1]), ed_[1], bnd[1], bnd[1]);
@@ -2262,6 +2375,13 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           for (int t = 0; t < 2; ++t) rescale(rhd[t], ud[t], WSE_(di(t), k), bnd[t], bnd[t]);
 #pragma unroll
           for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R && hasu) rescale(orh[q], uo[q], WSE_(NBR + o, k), olo[q], INFINITY); }
+          if constexpr (kWide) {
+            if (hasu) for (int o = warp; o < R; o += 4) {
+              double rv = ORH[o * NS + k], uv = UO[o * NS + k];
+              rescale(rv, uv, WSE_(NBR + o, k), OLO[o * NS + k], INFINITY);
+              ORH[o * NS + k] = rv; UO[o * NS + k] = uv;
+            }
+          }
           park();                                          // also writes the new Rh for the factorisation
           refactor = true;
           MQ_T(6);
@@ -2324,6 +2444,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag, volatile int* cmd = nullptr) {
     x0p = bt.x0 + (size_t)b * 8;
     slack = bt.slack + (size_t)b * bt.slack_stride;
+    if constexpr (kWide) {
+      if (bt.nobs) { Dm::R = bt.nobs[b]; Dm::MK = NBR + Dm::R; map_memory(m, smem0, ws0, NS, Dm::R, QMODE); }
+    }
     // setup (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) builds the cold block in the still unused PCR
     // region of shared memory; the CTA then copies it to its global home in one pass
     {
@@ -2413,7 +2536,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 
   MQ_HD Qp(double* smem, const Shape& shape, const Settings& set, const Batch& bt, double* ws, int lane_)
       : Dm(shape.NS, shape.R), sh(shape), st(set) {
-    lane = lane_;
+    lane = lane_; Rs = shape.R; smem0 = smem; ws0 = ws;
     map_memory(m, smem, ws, NS, R, QMODE);
     pd = bt.pd; slack = bt.slack;
   }

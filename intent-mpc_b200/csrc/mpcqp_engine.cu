@@ -31,6 +31,7 @@ struct AsmArgs {
   double* q; double* x0s; double* g; double* low;
   int* hard;                    // [B] set when a stage-0 obstacle row is violated by the (fixed) current position
   const int* hist; int hist_thresh;   // iterations each slot took in the previous call (or null): >= thresh -> hard
+  const int* nobs;              // [B] obstacle rows per stage of each instance (<= R, the array stride), or null: R everywhere
 };
 
 __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
@@ -52,6 +53,10 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
     } else {                                        // obstacle rows                   (MP.cpp:1040-1071, 1114-1139)
       const long long u = t - nq - n0;
       const long long bk = u / a.R;                 // b*N + k
+      if (a.nobs && (int)(u - bk * a.R) >= a.nobs[bk / N]) {      // padding beyond this instance's rows: never read
+        a.g[u * 3] = 0.0; a.g[u * 3 + 1] = 0.0; a.g[u * 3 + 2] = 0.0; a.low[u] = 0.0;
+        continue;
+      }
       const double cx = a.lin_pt[bk * 3], cy = a.lin_pt[bk * 3 + 1], cz = a.lin_pt[bk * 3 + 2];
       const double ox = a.obs_c[u * 3], oy = a.obs_c[u * 3 + 1], oz = a.obs_c[u * 3 + 2];
       const double sx = a.obs_semi[u * 3], sy = a.obs_semi[u * 3 + 1], sz = a.obs_semi[u * 3 + 2];
@@ -116,18 +121,19 @@ __global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solv
   }
   // queue 0: all instances in natural order.  queue 1: the hard list only.  queue 2: everything not flagged hard, then
   // whatever is left of the hard list (so an over-long hard list does not serialise on the one-per-SM launch).
-  bool natural = bt.queue != 1;
+  // queue 3: the hard list first, then everything else (one launch; used when every CTA has an SM to itself anyway).
+  bool natural = bt.queue != 1 && bt.queue != 3;
   for (;;) {
-    if (threadIdx.x == 0) s_next = atomicAdd(counter + ((natural && bt.queue == 2) ? 3 : 0), 1);
+    if (threadIdx.x == 0) s_next = atomicAdd(counter + ((natural && bt.queue >= 2) ? 3 : 0), 1);
     cta_sync();
     const int idx = s_next;
     cta_sync();
     int b = idx;
     if (natural) {
       if (idx >= bt.B) { if (bt.queue == 2) { natural = false; continue; } break; }
-      if (bt.queue == 2 && bt.hard[idx]) continue;       // on the hard list
+      if (bt.queue >= 2 && bt.hard[idx]) continue;       // on the hard list
     } else {
-      if (idx >= *bt.nhard) break;
+      if (idx >= *bt.nhard) { if (bt.queue == 3) { natural = true; continue; } break; }
       b = bt.order[idx];
     }
     qp.run_cta(bt, b, warp, &s_flag, s_cmd);
@@ -144,7 +150,12 @@ typedef void (*SolveKernel)(const Shape, const Settings, const Batch, int, int*)
 #define MPCQP_FAST_R_LIST X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #endif
 // want: 2 = CTA kernel if available, 1 = warp-fast kernel if available, 0 = generic.  *mode returns what was picked.
-static SolveKernel pick_kernel(int NS, int R, int want, int* mode, bool assist = false) {
+static SolveKernel pick_kernel(int NS, int R, int want, int* mode, bool assist = false, bool* wide = nullptr, bool force_wide = false) {
+  if (wide) *wide = false;
+  if (NS == 30 && want == kModeCta && wide && (R > 8 || (force_wide && R > 0)) && R <= kWideMax) {   // run-time obstacle count, rows in shared memory
+    *mode = kModeCta; *wide = true;
+    return mpcqp_solve_cta_kernel<kWideR, true>;
+  }
   if (NS == 30 && want == kModeCta) {
     *mode = kModeCta;
     switch (R) {
@@ -196,8 +207,9 @@ struct mpcqp_engine {
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0;
+  const int32_t* nobs_host = nullptr;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
@@ -268,6 +280,7 @@ extern "C" int64_t mpcqp_engine_last_launches(const mpcqp_engine* e) { return e 
 extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->last_fast : -1; }
 extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
 extern "C" int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->dyn_per_instance = on ? 1 : 0; return MPCQP_OK; }
+extern "C" int mpcqp_engine_num_obs_per_instance(mpcqp_engine* e, const int32_t* nobs) { if (!e) return MPCQP_ERR_ARG; e->nobs_host = nobs; return MPCQP_OK; }
 extern "C" int mpcqp_engine_use_history(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->use_history = on ? 1 : 0; if (!on) e->hist_B = 0; return MPCQP_OK; }
 #ifdef MPCQP_PHASE_TIMING
 extern "C" int mpcqp_debug_phase_clocks(mpcqp_engine* e, long long* out, int B) {   // development builds only
@@ -334,9 +347,11 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   // force_generic: 0 = best available (CTA kernel), 1 = generic kernel, 2 = warp-fast kernel
   const int want = e->force_generic == 1 ? kModeGeneric : (e->force_generic == 2 ? kModeWarp : kModeCta);
   e->no_assist = e->force_generic == 3;           // 3 = CTA kernel without the assistant warps (A/B tests)
-  SolveKernel kern = pick_kernel(sh.NS, sh.R, want, &mode);
-  const int threads = mode == kModeCta ? 128 : 32;
-  const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, mode) * sizeof(double);
+  bool wide = false;
+  SolveKernel kern = pick_kernel(sh.NS, sh.R, want, &mode, false, &wide, bt.nobs != nullptr);
+  if (bt.nobs && !wide) { e->err = "per-instance obstacle counts need horizon 30 and 1 <= num_obs <= 32"; return MPCQP_ERR_ARG; }
+  const int threads = mode == kModeCta ? (wide ? 224 : 128) : 32;
+  const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, mode, wide) * sizeof(double);
   if ((long long)smem > (long long)e->max_smem_optin) {
     e->err = "problem does not fit shared memory: horizon/num_obs too large (" + std::to_string(smem) + " B needed)";
     return MPCQP_ERR_ARG;
@@ -353,6 +368,17 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   e->last_fast = mode;
   bt.queue = 0; bt.nhard = nullptr;
   if (mode != kModeCta) { bt.order = nullptr; bt.hard = nullptr; }
+  if (mode == kModeCta && wide) {
+    // one CTA (4 solver warps + 3 PCR assistants) per SM; instances flagged hard first, then the rest
+    CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
+    bt.ws = e->ws.as<double>();
+    if (bt.order) { bt.queue = 3; bt.nhard = e->counter.as<int>() + 1; }
+    CK(cudaEventRecord(e->evs, e->stream));
+    kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+    CK(cudaGetLastError());
+    e->last_launches += 1;
+    return MPCQP_OK;
+  }
   if (mode == kModeCta) {
     // A CTA that has an SM to itself iterates ~1.5x faster than two sharing one.  Small batches therefore run one CTA
     // per SM (the launch asks for the whole shared memory of the SM).  Larger batches run as two concurrent launches:
@@ -437,6 +463,14 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   a.x0 = x0; a.xref = xref; a.obs_c = obs_c; a.obs_semi = obs_semi; a.obs_yaw = obs_yaw; a.lin_pt = lin_pt;
   a.q = e->q.as<double>(); a.x0s = e->x0s.as<double>(); a.g = e->g.as<double>(); a.low = e->low.as<double>();
   a.hard = e->hard.as<int>();
+  a.nobs = nullptr;
+  if (e->nobs_host) {                                  // per-instance obstacle counts: R is the array stride
+    if (R < 1) { e->err = "per-instance obstacle counts need num_obs >= 1 (the array stride)"; return MPCQP_ERR_ARG; }
+    for (int b = 0; b < B; ++b) if (e->nobs_host[b] < 0 || e->nobs_host[b] > R) { e->err = "num_obs per instance out of [0, num_obs]"; return MPCQP_ERR_ARG; }
+    CK(e->nobs.need((size_t)B * sizeof(int)));
+    CK(cudaMemcpyAsync(e->nobs.p, e->nobs_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    a.nobs = e->nobs.as<int>();
+  }
   a.hist = (e->use_history && e->hist_B == B && e->hist_R == R) ? e->hist.as<int>() : nullptr;
   a.hist_thresh = 500;
   CK(cudaMemsetAsync(e->hard.p, 0, (size_t)B * sizeof(int), e->stream));
@@ -453,6 +487,7 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
     e->last_launches += 2;
   }
   Batch bt; memset(&bt, 0, sizeof bt);
+  bt.nobs = a.nobs;
   bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.slack_stride = e->dyn_per_instance ? N * R : 0; bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
   bt.warm_x = warm_x; bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates;
   bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>(); bt.hard = e->hard.as<int>();

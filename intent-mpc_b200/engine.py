@@ -175,6 +175,9 @@ class Engine:
         x0, xref, oc, os_, oy, lp, wx = map(f, (mb.x0, mb.xref, mb.obs_c, mb.obs_semi, mb.obs_yaw, mb.lin_pt, mb.warm_x))
         od = np.ascontiguousarray(mb.obs_dyn, dtype=np.int32)
         self._check(self.lib.mpcqp_engine_obs_dyn_per_instance(self.h, C.c_int(1 if od.ndim == 3 else 0)))
+        nobs = getattr(mb, "nobs", None)
+        nobs = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
+        self._check(self.lib.mpcqp_engine_num_obs_per_instance(self.h, _ip(nobs)))
         if out is None:
             out = dict(x=np.empty((B, n)), y=np.empty((B, m)) if want_y else None, status=np.empty(B, np.int32),
                        iter=np.empty(B, np.int32), rho_updates=np.empty(B, np.int32), obj=np.empty(B),
@@ -184,6 +187,7 @@ class Engine:
                                                  _dp(out["x"]), _dp(out["y"]), _ip(out["status"]), _ip(out["iter"]),
                                                  _ip(out["rho_updates"]), _dp(out["obj"]), _dp(out["pri_res"]),
                                                  _dp(out["dua_res"]))
+        self.lib.mpcqp_engine_num_obs_per_instance(self.h, None)
         self._check(rc)
         return out
 

@@ -54,6 +54,7 @@ class MpcBatch:
     obs_dyn: np.ndarray   # [N,numObs] int32: 1 -> slack input 3 (dynamic), 0 -> slack input 4 (static)
     lin_pt: np.ndarray    # [B,N,3] linearisation point (previous plan, unshifted, or currPos)
     warm_x: np.ndarray    # [B,n] primal warm start (previous plan or zeros); dual warm start is always 0
+    nobs: np.ndarray | None = None   # [B] int32 obstacle rows per stage of each instance (<= numObs, the array stride), or None
 
     @property
     def B(self) -> int:
@@ -65,7 +66,8 @@ class MpcBatch:
 
     def slice(self, lo, hi) -> "MpcBatch":
         return MpcBatch(self.params, self.x0[lo:hi], self.xref[lo:hi], self.obs_c[lo:hi], self.obs_semi[lo:hi],
-                        self.obs_yaw[lo:hi], self.obs_dyn, self.lin_pt[lo:hi], self.warm_x[lo:hi])
+                        self.obs_yaw[lo:hi], self.obs_dyn if self.obs_dyn.ndim == 2 else self.obs_dyn[lo:hi],
+                        self.lin_pt[lo:hi], self.warm_x[lo:hi], None if self.nobs is None else self.nobs[lo:hi])
 
 
 GOAL = np.array([105.0, 0.0, 2.0])   # end of ref_trajectory_dynus_benchmark.txt line (mpcNavigation.cpp:201-216)
@@ -276,3 +278,34 @@ def sweep_groups(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = No
     meta = dict(instances=Bt, capped=int((c["in_range"] > SWEEP_CAP).sum()), cap=SWEEP_CAP,
                 obstacle_rows_hist=np.bincount(R_i, minlength=SWEEP_CAP + 1))
     return groups, meta
+
+
+def sweep_batches(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = None):
+    """The same instances as sweep_groups(lo, hi), packed for the engine's per-instance obstacle counts: ONE batch per
+    (max_vel, max_acc) pair, obstacle arrays padded to SWEEP_CAP rows per stage, `nobs` = rows each instance really has.
+    Returns (batches, meta): batches = list of (index array, MpcBatch)."""
+    groups, meta = sweep_groups(lo, hi, seed0, params)
+    out = []
+    for li, (vm, am) in enumerate(SWEEP_LIMITS):
+        gs = [(idx, mb) for idx, mb in groups if mb.params.max_vel == vm and mb.params.max_acc == am]
+        if not gs:
+            continue
+        p = gs[0][1].params
+        N, Rm = p.N, SWEEP_CAP
+        B = sum(mb.B for _, mb in gs)
+        idx = np.concatenate([i for i, _ in gs])
+        cat = lambda name: np.concatenate([getattr(mb, name) for _, mb in gs])
+        obs_c = np.zeros((B, N, Rm, 3)); obs_semi = np.ones((B, N, Rm, 3)); obs_yaw = np.zeros((B, N, Rm))
+        obs_dyn = np.zeros((B, N, Rm), dtype=np.int32); nobs = np.zeros(B, dtype=np.int32)
+        at = 0
+        for _, mb in gs:
+            R = mb.num_obs
+            obs_c[at:at + mb.B, :, :R] = mb.obs_c; obs_semi[at:at + mb.B, :, :R] = mb.obs_semi
+            obs_yaw[at:at + mb.B, :, :R] = mb.obs_yaw; obs_dyn[at:at + mb.B, :, :R] = mb.obs_dyn
+            nobs[at:at + mb.B] = R
+            at += mb.B
+        order = np.argsort(idx, kind="stable")
+        mbp = MpcBatch(p, cat("x0")[order], cat("xref")[order], obs_c[order], obs_semi[order], obs_yaw[order], obs_dyn[order],
+                       cat("lin_pt")[order], cat("warm_x")[order], nobs[order])
+        out.append((idx[order], mbp))
+    return out, meta

@@ -2,6 +2,8 @@ import sys, time; sys.path.insert(0, ".")
 import numpy as np
 from intent_mpc_b200 import engine, workloads as W
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+if len(sys.argv) > 2:
+    import os; engine.LIB_PATH = os.path.abspath(sys.argv[2])
 groups, meta = W.sweep_groups(0, n)
 eng = engine.Engine(0)
 for rep in range(2):

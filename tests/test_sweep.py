@@ -83,6 +83,21 @@ def test_sweep_gpu_matches_oracle():
             assert np.abs((out["obj"] - ref["obj"]) / ref["obj"]).max() < TOL
             n += mb.B
         assert n == 384
+        # the same instances packed three launches wide (per-instance obstacle counts, arrays padded to the cap)
+        refs = {}
+        for idx, mb in groups:
+            r = oracle_solve(orc, mb)
+            for j, i in enumerate(idx):
+                refs[int(i)] = {k: r[k][j] for k in ("status", "iter", "rho_updates", "x", "obj")}
+        batches, _ = W.sweep_batches(0, 384)
+        assert len(batches) == 3
+        for idx, mb in batches:
+            out = eng.solve_mpc_batch(mb, want_y=True)
+            assert eng.last_path == "cta"
+            for j, i in enumerate(idx):
+                r = refs[int(i)]
+                assert out["status"][j] == r["status"] and out["iter"][j] == r["iter"] and out["rho_updates"][j] == r["rho_updates"]
+                assert rel_inf(out["x"][j], r["x"]) < TOL and abs((out["obj"][j] - r["obj"]) / r["obj"]) < TOL
         # per-instance flags and a shared pattern are the same thing when the patterns agree
         mb = W.static_batch(32, num_obs=4, seed0=300)
         a = eng.solve_mpc_batch(mb)
@@ -101,13 +116,12 @@ def test_sweep_properties_at_larger_size():
     from intent_mpc_b200 import engine
     eng = engine.Engine(0)
     try:
-        groups, meta = W.sweep_groups(0, 8192)
+        groups, meta = W.sweep_batches(0, 8192)
         total = 0; solved = 0
         for idx, mb in groups:
             a = eng.solve_mpc_batch(mb)
-            if mb.B >= 64:
-                b = eng.solve_mpc_batch(mb)
-                assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["iter"], b["iter"])
+            b = eng.solve_mpc_batch(mb)
+            assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["iter"], b["iter"])
             assert np.isin(a["status"], [1, 2, -2]).all()
             assert ((a["iter"] % 25 == 0) & (a["iter"] > 0) & (a["iter"] <= 4000)).all()
             p = mb.params; N, NS = p.N, p.N + 1
@@ -118,13 +132,15 @@ def test_sweep_properties_at_larger_size():
             X = a["x"][ok]
             st = X[:, :8 * NS].reshape(-1, NS, 8); u = X[:, 8 * NS:].reshape(-1, N, 5)
             ts = float(np.float32(p.ts)); h = float(np.float32(0.5 * p.ts ** 2))
-            scale = 1e-2 * (1 + np.abs(st[:, :, 0:3]).max())
-            assert np.abs(st[:, :-1, 0:3] + ts * st[:, :-1, 3:6] + h * u[:, :, 0:3] - st[:, 1:, 0:3]).max() < scale
-            assert np.abs(st[:, :-1, 3:6] + ts * u[:, :, 0:3] - st[:, 1:, 3:6]).max() < scale
-            # OSQP's primal tolerance is eps_abs + eps_rel * max(|Ax|, |z|) ~ 1e-3 * (1 + 105 m): bounds hold to that
-            tol_box = 2e-3 * (1 + np.abs(st[:, :, 0:3]).max())
-            assert np.abs(u[:, :, 0:3]).max() <= p.max_acc + tol_box
-            assert np.abs(st[:, :, 3:6]).max() <= p.max_vel + tol_box
+            pos_gap = np.abs(st[:, :-1, 0:3] + ts * st[:, :-1, 3:6] + h * u[:, :, 0:3] - st[:, 1:, 0:3]).max(axis=(1, 2))
+            assert (pos_gap <= a["pri_res"][ok] + 1e-9).all()
+            # OSQP accepts |Ax - z|_inf <= eps_abs + eps_rel * max(|Ax|, |z|), and |Ax| is large here (obstacle gradients
+            # times positions), so "solved" trajectories overshoot their limits by up to the reported primal residual
+            pr = a["pri_res"][ok]
+            assert (np.abs(u[:, :, 0:3]).max(axis=(1, 2)) <= p.max_acc + pr + 1e-9).all()
+            assert (np.abs(st[:, :, 3:6]).max(axis=(1, 2)) <= p.max_vel + pr + 1e-9).all()
+            dyn_gap = np.abs(st[:, :-1, 3:6] + ts * u[:, :, 0:3] - st[:, 1:, 3:6]).max(axis=(1, 2))
+            assert (dyn_gap <= pr + 1e-9).all()
         assert total == 8192 and solved / total > 0.85
     finally:
         eng.close()
