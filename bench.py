@@ -326,6 +326,13 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None                                   # ncu dram__bytes of one step of this workload (committed capture), if it is this workload
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
+        if B == 1024 and R == 4:
+            traffic = int(tj["bytes_per_step"])
+    except Exception:
+        pass
     hbm_ach = algorithmic_bytes(N, R) * B / (solve_avg_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -341,7 +348,8 @@ def run_b200(args, rank, world, local_rank):
         "p50_latency_ms": float(np.median(solve_ms)),
         "status_hist": _hist(status),
         "roofline": {"bound": "fp64_fma", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                     "traffic": None, "kernel": "mpcqp_solve_kernel", "kernel_ms": solve_avg_ms,
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per step (both solve launches), ncu capture in profiles/; algorithmic: %d" % int(algorithmic_bytes(N, R) * B),
+                     "kernel": "mpcqp_solve_cta_kernel (hard-queue launch with PCR assistants + two-per-SM launch)", "kernel_ms": solve_avg_ms,
                      "peak_source": "fp64 DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "algorithmic_flops_per_launch": flops,
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
