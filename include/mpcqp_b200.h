@@ -140,6 +140,26 @@ int mpcqp_solve_mpc_batch_device(mpcqp_engine* e, const mpcqp_mpc_params* p, con
                                  int32_t* iter, int32_t* rho_updates, double* obj, double* pri_res,
                                  double* dua_res);
 
+/* ---- (2b) candidate scoring and selection ----------------------------------------------------------- *
+ * Device pointers, asynchronous on the engine's stream.  Replace, for the candidates of many scenarios at once,
+ * getTrajectoryScore (consistency / detour / safety, mpcPlanner.cpp:771-852) and evaluateTraj (:854-887).
+ *   x         [B][n]        candidate solutions from the batched entry point
+ *   prev_plan [B][n] / NULL the plan each candidate is compared with (currentStatesSol_; the warm start array); NULL on
+ *                           the first control step (consistency score 0, :783-785)
+ *   xref, obs_c, obs_semi   as given to the solve; the first n_dynamic rows of a stage are dynamic obstacles (full-size
+ *                           xy diagonal + dynamicSafetyDist_), the rest static (half-size diagonal + staticSafetyDist_);
+ *                           stage N is scored against the obstacle positions of stage N-1 (the last the solve holds)
+ *   score     [B][3]        (consistency, detour, safety)
+ * select: scenario s has C candidates, rows cand[s][c] of `score` / `x_all`, with weights weight[s][c] (the intent
+ * probabilities in the order evaluateTraj indexes them).  best[s] = argmax_c weight * (avg_c/c_c + avg_d/d_c + s_c/avg_s),
+ * first maximum, NaN never wins; weighted [S][C] (optional) receives the values; plan [S][n] (optional) the chosen x. */
+int mpcqp_score_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t B, int32_t num_obs, int32_t n_dynamic,
+                                  const double* x, const double* prev_plan, const double* xref, const double* obs_c,
+                                  const double* obs_semi, double* score);
+int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_t C, int32_t n, const int32_t* cand,
+                                   const double* weight, const double* score, const double* x_all, int32_t* best,
+                                   double* weighted, double* plan);
+
 /* ---- (3) OSQP-shaped single problem (explicit CSC) -------------------------------------------------- *
  * mpcqp_setup replaces osqp_setup (osqp.h:58): data is copied, the caller's arrays may die afterwards.
  * P is upper-triangular CSC (n x n), A is CSC (m x n), indices int64 like OSQP's c_int (glob_opts.h:80).

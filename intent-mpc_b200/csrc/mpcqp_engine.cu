@@ -609,6 +609,128 @@ extern "C" int mpcqp_fp64_fma_peak(mpcqp_engine* e, double* tflops) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// (2b) candidate scoring and selection on the device: getTrajectoryScore / getConsistencyScore / getDetourScore /
+// getSafetyScore / evaluateTraj (mpcPlanner.cpp:771-887) for the candidates of many scenarios at once, so that the six
+// solves of makePlanWithPred (mpcPlanner.cpp:609-644), their scoring and the choice of the plan need no host round trip.
+// ------------------------------------------------------------------------------------------------
+namespace mpcqp {
+// one warp per candidate, lane = stage (strided for longer horizons)
+__global__ void __launch_bounds__(128) mpc_score_kernel(int B, int NS, int R, int n_dynamic, int n, double dyn_safety, double stat_safety,
+                                                         const double* __restrict__ x, const double* __restrict__ prev,
+                                                         const double* __restrict__ xref, const double* __restrict__ obs_c,
+                                                         const double* __restrict__ obs_semi, double* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int N = NS - 1;
+  const double k05 = 0.54930614433405484570;             // atanh(0.5), mpcPlanner.cpp:830,840
+  for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const double* xb = x + b * n;
+    double cons = 0.0, det = 0.0, saf = 0.0;
+    for (int k = lane; k < NS; k += 32) {
+      const double px = xb[8 * k], py = xb[8 * k + 1], pz = xb[8 * k + 2];
+      if (prev && k < 10) {                                // numConsistencyStep = 10 (mpcPlanner.cpp:781)
+        const double* pv = prev + b * n + 8 * k;
+        const double dx = pv[0] - px, dy = pv[1] - py, dz = pv[2] - pz;
+        cons += sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      {
+        const double* rf = xref + (b * NS + k) * 3;
+        const double dx = rf[0] - px, dy = rf[1] - py, dz = rf[2] - pz;
+        det += sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      if (R > 0) {
+        // obstacle rows exist for stages 0..N-1; stage N is scored against the last prediction held
+        const int ko = k < N ? k : N - 1;
+        double dist = 0.0, tw = 0.0;
+        for (int o = 0; o < R; ++o) {
+          const long long u = ((b * N + ko) * R + o) * 3;
+          const bool dynamic = o < n_dynamic;
+          const double sd = dynamic ? dyn_safety : stat_safety;
+          // dynamic: maxSize = |full size (x, y)|; static: |half size (x, y)|   (mpcPlanner.cpp:828,838); semi = size/2 + safety
+          const double hx = obs_semi[u] - sd, hy = obs_semi[u + 1] - sd;
+          const double ms = (dynamic ? 2.0 : 1.0) * sqrt(hx * hx + hy * hy);
+          const double ex = px - obs_c[u], ey = py - obs_c[u + 1];
+          const double d = sqrt(ex * ex + ey * ey);
+          const double w = 1.0 - tanh(k05 / (sd + ms) * d);
+          dist += d * w; tw += w;
+        }
+        saf += dist / tw;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cons += __shfl_xor_sync(0xffffffffu, cons, o); det += __shfl_xor_sync(0xffffffffu, det, o); saf += __shfl_xor_sync(0xffffffffu, saf, o);
+    }
+    if (lane == 0) {
+      const int steps = NS < 10 ? NS : 10;
+      score[b * 3] = prev ? fmax(cons / steps, 0.1) : 0.0;
+      score[b * 3 + 1] = fmax(det / NS, 0.1);
+      score[b * 3 + 2] = R > 0 ? saf / NS : nan("");       // no obstacles: 0/0 in the reference
+    }
+  }
+}
+
+// one thread per scenario: evaluateTraj (mpcPlanner.cpp:854-887) over its C candidates, best plan copied out
+__global__ void mpc_select_kernel(int S, int C, int n, const int* __restrict__ cand, const double* __restrict__ weight,
+                                  const double* __restrict__ score, const double* __restrict__ x_all, int* __restrict__ best,
+                                  double* __restrict__ weighted, double* __restrict__ plan) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    double avg[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < C; ++c) { const double* sc = score + (long long)cand[s * C + c] * 3; avg[0] += sc[0]; avg[1] += sc[1]; avg[2] += sc[2]; }
+    avg[0] /= C; avg[1] /= C; avg[2] /= C;
+    int bi = 0; double bv = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      const double* sc = score + (long long)cand[s * C + c] * 3;
+      double w = weight[s * C + c] * (avg[0] / sc[0] + avg[1] / sc[1] + sc[2] / avg[2]);
+      if (w != w) w = -INFINITY;                           // NaN never wins maxCoeff's comparison chain
+      if (weighted) weighted[s * C + c] = w;
+      if (w > bv) { bv = w; bi = c; }
+    }
+    best[s] = bi;
+  }
+  (void)x_all; (void)plan; (void)n;
+}
+__global__ void mpc_gather_plan_kernel(int S, int C, int n, const int* __restrict__ cand, const int* __restrict__ best,
+                                       const double* __restrict__ x_all, double* __restrict__ plan) {
+  const long long total = (long long)S * n;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / n), j = (int)(t - (long long)s * n);
+    plan[t] = x_all[(long long)cand[s * C + best[s]] * n + j];
+  }
+}
+}  // namespace mpcqp
+
+extern "C" int mpcqp_score_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t B, int32_t R, int32_t n_dynamic,
+                                             const double* x, const double* prev_plan, const double* xref, const double* obs_c,
+                                             const double* obs_semi, double* score) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (!p || B <= 0 || R < 0 || n_dynamic < 0 || n_dynamic > R || !x || !xref || !score || (R > 0 && (!obs_c || !obs_semi))) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
+  CK(cudaSetDevice(e->device));
+  const int NS = p->horizon, n = 8 * NS + 5 * (NS - 1);
+  long long blocks = ((long long)B + 3) / 4; const long long cap = (long long)e->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  mpc_score_kernel<<<(unsigned)blocks, 128, 0, e->stream>>>(B, NS, R, n_dynamic, n, p->dynamic_safety_dist, p->static_safety_dist, x, prev_plan,
+                                                              xref, obs_c, obs_semi, score);
+  CK(cudaGetLastError());
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_t C, int32_t n, const int32_t* cand, const double* weight,
+                                              const double* score, const double* x_all, int32_t* best, double* weighted, double* plan) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (S <= 0 || C <= 0 || !cand || !weight || !score || !best || (plan && (!x_all || n <= 0))) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
+  CK(cudaSetDevice(e->device));
+  mpc_select_kernel<<<(unsigned)((S + 127) / 128), 128, 0, e->stream>>>(S, C, n, cand, weight, score, x_all, best, weighted, nullptr);
+  CK(cudaGetLastError());
+  if (plan) {
+    long long blocks = ((long long)S * n + 255) / 256; const long long cap = (long long)e->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    mpc_gather_plan_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(S, C, n, cand, best, x_all, plan);
+    CK(cudaGetLastError());
+  }
+  return MPCQP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // (3) OSQP-shaped single problem with explicit CSC data (what OsqpEigen::Solver hands to osqp_setup,
 // OsqpEigen/Data.tpp:38-39,77; osqp.h:58).  The problem must have the mpcPlanner stage structure
 // (mpcPlanner.cpp:932-1146); it is parsed on the host into the structured form the kernels take and solved

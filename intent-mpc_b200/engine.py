@@ -206,3 +206,19 @@ class Engine:
                 g("obs_semi"), g("obs_yaw"), _ip(od), g("lin_pt"), g("warm_x"), g("x"), g("y"), g("status"), g("iter"),
                 g("rho_updates"), g("obj"), g("pri_res"), g("dua_res"))
         self._check(rc)
+
+    # ---- candidate scoring / selection on the device (getTrajectoryScore, evaluateTraj) --------------------------
+    def score_candidates_ptr(self, params, B: int, R: int, n_dynamic: int, ptrs: dict):
+        """ptrs: device addresses for x, prev_plan (0 = first control step), xref, obs_c, obs_semi, score.  Asynchronous."""
+        p = params_to_c(params)
+        g = lambda k: C.c_void_p(ptrs.get(k) or None)
+        self._check(self.lib.mpcqp_score_candidates_device(self.h, C.byref(p), C.c_int32(B), C.c_int32(R), C.c_int32(n_dynamic),
+                                                           g("x"), g("prev_plan"), g("xref"), g("obs_c"), g("obs_semi"), g("score")))
+
+    def select_candidates_ptr(self, S: int, Cn: int, n: int, ptrs: dict):
+        """ptrs: device addresses for cand [S][C] int32, weight [S][C], score, x_all, best [S] int32, weighted (optional),
+        plan (optional).  Asynchronous on the engine stream."""
+        g = lambda k: C.c_void_p(ptrs.get(k) or None)
+        self._check(self.lib.mpcqp_select_candidates_device(self.h, C.c_int32(S), C.c_int32(Cn), C.c_int32(n), g("cand"), g("weight"),
+                                                            g("score"), g("x_all"), g("best"), g("weighted"), g("plan")))
+

@@ -82,3 +82,56 @@ def test_receding_horizon_full_size_properties():
         assert np.abs(u[:, :, 0:3]).max() <= p.max_acc + 0.2              # input box to the solver tolerance
         assert (out["pri_res"][ok] < 1e-3 + 1e-3 * 1e3).all()                # solved => primal residual within eps_abs + eps_rel*|Ax|
     eng.close()
+
+
+@pytest.mark.gpu
+def test_device_scoring_and_selection_match_host_logic():
+    """§8(f) row 1: getTrajectoryScore / evaluateTraj (mpcPlanner.cpp:771-887) as device kernels
+    (mpcqp_score_candidates_device, mpcqp_select_candidates_device) against the numpy restatement that drives the
+    receding-horizon tests above: same scores, same weighted values, same chosen candidate and plan, every step."""
+    import torch
+    from intent_mpc_b200 import engine
+    from intent_mpc_b200.receding import IntentSweep
+    eng = engine.Engine(0)
+    dev = torch.device("cuda", 0)
+    try:
+        sw = IntentSweep(48, seed0=123)
+        sw.step(eng.solve_mpc_batch)                       # first control step: one obstacle-free QP per scenario
+        for step in range(4):
+            prev_first = sw.first
+            batches, meta = sw.candidates()
+            outs = [eng.solve_mpc_batch(mb) for mb in batches]
+            cand_x, status, iters, weighted, best = sw.select(batches, meta, outs)
+            p = sw.p; S = sw.S; n = p.n
+            xs = torch.from_numpy(np.concatenate([o["x"] for o in outs])).to(dev)
+            score = torch.empty((xs.shape[0], 3), dtype=torch.float64, device=dev)
+            off = 0
+            keep = []
+            for mb, out in zip(batches, outs):
+                B, R = mb.B, mb.num_obs
+                t = {k: torch.from_numpy(np.ascontiguousarray(getattr(mb, k))).to(dev) for k in ("xref", "obs_c", "obs_semi", "warm_x")}
+                keep.append(t)
+                eng.score_candidates_ptr(p, B, R, R, {"x": xs[off:off + B].data_ptr(), "prev_plan": 0 if prev_first else t["warm_x"].data_ptr(),
+                                                      "xref": t["xref"].data_ptr(), "obs_c": t["obs_c"].data_ptr(), "obs_semi": t["obs_semi"].data_ptr(),
+                                                      "score": score[off:off + B].data_ptr()})
+                off += B
+            cand = np.zeros((S, 6), dtype=np.int32)
+            off = 0
+            for mt in meta:
+                cand[mt[:, 0], mt[:, 1]] = off + np.arange(len(mt))
+                off += len(mt)
+            d_cand = torch.from_numpy(cand).to(dev); d_w = torch.from_numpy(np.ascontiguousarray(sw.last["w"])).to(dev)
+            d_best = torch.empty(S, dtype=torch.int32, device=dev); d_wd = torch.empty((S, 6), dtype=torch.float64, device=dev)
+            d_plan = torch.empty((S, n), dtype=torch.float64, device=dev)
+            eng.select_candidates_ptr(S, 6, n, {"cand": d_cand.data_ptr(), "weight": d_w.data_ptr(), "score": score.data_ptr(), "x_all": xs.data_ptr(),
+                                                "best": d_best.data_ptr(), "weighted": d_wd.data_ptr(), "plan": d_plan.data_ptr()})
+            eng.sync()
+            wd = d_wd.cpu().numpy()
+            fin = np.isfinite(weighted)
+            assert np.array_equal(np.isfinite(wd), fin)
+            assert np.abs(wd[fin] - weighted[fin]).max() <= 1e-9 * np.abs(weighted[fin]).max()
+            assert np.array_equal(d_best.cpu().numpy(), best.astype(np.int32))
+            assert np.array_equal(d_plan.cpu().numpy(), cand_x[np.arange(S), best])
+            sw.advance(cand_x, best)
+    finally:
+        eng.close()
