@@ -2074,6 +2074,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           const double r11d = XR[k], r11st = XR[NS + k];
           const double sgd = hasu ? dgi[0] * (r11d - fs[0] * yp0 - fs[1] * yp1 - fs[2] * yp2) : 0.0;     // slack inputs of this stage
           const double sgs = hasu ? dgi[1] * (r11st - fs[3] * yp0 - fs[4] * yp1 - fs[5] * yp2) : 0.0;
+#pragma unroll 4
           for (int o = warp; o < R; o += 4) {
             const bool st_ = (slmask >> o) & 1u;
             const double g0 = OG3[(3 * o) * NS + k], g1 = OG3[(3 * o + 1) * NS + k], g2 = OG3[(3 * o + 2) * NS + k];

@@ -1,0 +1,18 @@
+import sys, ctypes as C; sys.path.insert(0, ".")
+import numpy as np
+from intent_mpc_b200 import engine, workloads as W
+engine.LIB_PATH = "scratch/libmpcqp_timing.so"
+eng = engine.Engine(0)
+names = ["setup", "leaf+rhs(warp0)", "pcr_factor", "load", "iterate", "info+check", "park+adapt", "store", "pcr:init", "pcr:invert", "pcr:products", "pcr:final", "setup:ruiz"]
+b, _ = W.sweep_batches(0, 4096)
+for idx, mb in b[-1:]:
+    for sub in (mb.slice(0, 100), mb):
+        out = eng.solve_mpc_batch(sub); out = eng.solve_mpc_batch(sub)
+        buf = np.zeros((sub.B, 16), dtype=np.int64)
+        eng.lib.mpcqp_debug_phase_clocks(eng.h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int(sub.B))
+        it = out["iter"]; nf = 1 + out["rho_updates"]
+        tot = buf.sum(axis=0)
+        print(f"B={sub.B}: kernel ms {eng.last_kernel_ms:.2f} iters {it.sum()} (max {it.max()}) factorizations {nf.sum()} checks {np.ceil(it/25).sum():.0f} mean R {sub.nobs.mean():.1f}")
+        for i, n in enumerate(names):
+            per = {"iterate": it.sum(), "leaf+rhs(warp0)": nf.sum(), "pcr_factor": nf.sum(), "pcr:init": nf.sum(), "pcr:invert": nf.sum(), "pcr:products": nf.sum(), "pcr:final": nf.sum(), "load": nf.sum(), "info+check": np.ceil(it / 25).sum(), "park+adapt": max(out["rho_updates"].sum(), 1)}.get(n, sub.B)
+            print(f"   {n:18s} total {tot[i]/1e6:9.2f} Mcycles  share {100*tot[i]/tot[:8].sum():5.1f}%   per event {tot[i]/per:9.0f} cycles")
