@@ -1,0 +1,80 @@
+// mpcqp_kernels.cuh — the solve kernels (bodies in mpcqp_core.cuh) and the table through which the host code reaches
+// their instantiations.  Every instantiation is a separate translation unit of mpcqp_kernels.cu (one nvcc process per
+// obstacle count, see __graft_entry__.build), so that the library builds in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include "mpcqp_core.cuh"
+
+namespace mpcqp {
+
+typedef void (*SolveKernel)(const Shape, const Settings, const Batch, int, int*);
+// Fast-path instantiations (compile-time dims, register-resident iterates); anything else runs the generic kernel.
+#ifndef MPCQP_FAST_R_LIST
+#define MPCQP_FAST_R_LIST X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#endif
+// getters defined by the translation units of mpcqp_kernels.cu
+#define X(r) SolveKernel mpcqp_kernel_cta_##r(bool assist); SolveKernel mpcqp_kernel_warp_##r();
+MPCQP_FAST_R_LIST
+#undef X
+SolveKernel mpcqp_kernel_cta_wide();
+SolveKernel mpcqp_kernel_generic();
+
+#ifdef MPCQP_KERNEL_BODIES
+// ------------------------------------------------------------------------------------------------
+// solve kernel: persistent, one warp (= one CTA) per QP at a time, work fetched from a global counter
+// ------------------------------------------------------------------------------------------------
+template <int NST, int RT>
+__global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+                                                         const __grid_constant__ Batch bt, int ws_stride, int* counter) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x;
+  Qp<NST, RT> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= bt.B) break;
+    qp.run(bt, b);
+  }
+}
+
+// CTA kernel: persistent, one 4-warp CTA per QP at a time (mode 2 of mpcqp_core.cuh), two CTAs per SM.  ASSIST: the
+// block has the SM to itself and carries three more warps that keep the PCR matrices of levels 1..3 in registers.
+template <int RT, bool ASSIST>
+__global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+                                                                                        const __grid_constant__ Batch bt, int ws_stride, int* counter) {
+  extern __shared__ double smem[];
+  __shared__ int s_next, s_flag, s_cmd[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Qp<30, RT, kModeCta, ASSIST> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  if constexpr (ASSIST) {
+    if (warp >= 4) { qp.assist_role(warp - 4, s_cmd); return; }
+  }
+  // queue 0: all instances in natural order.  queue 1: the hard list only.  queue 2: everything not flagged hard, then
+  // whatever is left of the hard list (so an over-long hard list does not serialise on the one-per-SM launch).
+  // queue 3: the hard list first, then everything else (one launch; used when every CTA has an SM to itself anyway).
+  bool natural = bt.queue != 1 && bt.queue != 3;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(counter + ((natural && bt.queue >= 2) ? 3 : 0), 1);
+    cta_sync();
+    const int idx = s_next;
+    cta_sync();
+    int b = idx;
+    if (natural) {
+      if (idx >= bt.B) { if (bt.queue == 2) { natural = false; continue; } break; }
+      if (bt.queue >= 2 && bt.hard[idx]) continue;       // on the hard list
+    } else {
+      if (idx >= *bt.nhard) { if (bt.queue == 3) { natural = true; continue; } break; }
+      b = bt.order[idx];
+    }
+    qp.run_cta(bt, b, warp, &s_flag, s_cmd);
+  }
+  if constexpr (ASSIST) {                                  // release the assistants
+    if (threadIdx.x == 0) s_cmd[0] = -1;
+    asm volatile("bar.sync 5, 224;" ::: "memory");
+  }
+}
+
+#endif  // MPCQP_KERNEL_BODIES
+
+}  // namespace mpcqp

@@ -135,3 +135,35 @@ def test_device_scoring_and_selection_match_host_logic():
             sw.advance(cand_x, best)
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_receding_horizon_100_steps_warm_started():
+    """BASELINE.json configs[2]'s loop length: 100 control steps, every candidate QP warm-started from the plan chosen one
+    step earlier.  64 scenarios x 6 candidates per step on the GPU; every 10th step is re-solved by the oracle on the
+    identical inputs (status, iterations, 1e-5 on x); the scenarios must keep advancing along the reference line."""
+    from intent_mpc_b200 import engine
+    eng = engine.Engine(0)
+    try:
+        sw = receding.IntentSweep(S=64, D=4, seed0=77)
+        x_start = sw.pos[:, 0].copy()
+        total_q = 0; it_sum = 0
+        for step in range(100):
+            r = sw.step(lambda mb: eng.solve_mpc_batch(mb))
+            for mb, out in zip(r["batches"], r["outs"]):
+                assert np.isin(out["status"], [1, 2, -2]).all()
+                total_q += mb.B; it_sum += int(out["iter"].sum())
+                if step % 10 == 9:
+                    ref = _oracle_solve(mb)
+                    assert (out["status"] == ref["status"]).all() and (out["iter"] == ref["iter"]).all(), f"step {step}"
+                    assert rel_inf(out["x"], ref["x"]).max() < TOL
+        assert total_q == 64 + 99 * 384
+        assert np.isfinite(sw.states).all()
+        assert (sw.pos[:, 0] >= x_start - 1e-6).all() and (sw.pos[:, 0] - x_start).mean() > 5.0     # >= 5 m of progress in 10 s
+        # warm start pays: a cold solve of the last step's QPs needs more iterations than the warm one did
+        mb = r["batches"][0]
+        warm_it = int(r["outs"][0]["iter"].sum())
+        cold = receding.MpcBatch(mb.params, mb.x0, mb.xref, mb.obs_c, mb.obs_semi, mb.obs_yaw, mb.obs_dyn, mb.lin_pt, np.zeros_like(mb.warm_x))
+        assert int(eng.solve_mpc_batch(cold)["iter"].sum()) > warm_it
+    finally:
+        eng.close()
