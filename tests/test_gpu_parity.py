@@ -143,3 +143,51 @@ def test_bitwise_determinism_under_cold_caches_and_scheduling(eng):
     for i in list(long_ones) + [0, 1]:
         one = eng.solve_mpc_batch(mb.slice(int(i), int(i) + 1))
         assert np.array_equal(one["x"][0], ref["x"][i])
+
+
+@pytest.mark.parametrize("horizon,num_obs,kw", [
+    (20, 3, {}),                                       # the code default of mpcPlanner::initParam (mpcPlanner.cpp:19-173)
+    (25, 2, {}),                                       # 8*horizon % 5 != 0: the R[i % numControls] rotation of castMPCToQPHessian (:945)
+    (45, 1, {"velocity_weight": 2.5}),                 # non-zero velocity weights: P gains entries (:941-942)
+    (30, 4, {"max_vel": 1.5, "max_acc": 1.5, "z_min": 1.0, "z_max": 3.0, "acceleration_weight": 1.0, "position_weight": 50.0}),
+])
+def test_shapes_weights_and_hessian_quirk(eng, horizon, num_obs, kw):
+    """Horizons / weights other than the demo's, through whichever kernel the dispatch picks, against the oracle."""
+    p = W.MpcParams(horizon=horizon, **kw)
+    mb = W.static_batch(24, num_obs=num_obs, params=p, seed0=4000 + horizon)
+    out = eng.solve_mpc_batch(mb)
+    ref = _oracle().solve_batch(to_qp_batch(mb), want_y=False)
+    assert (out["status"] == ref["status"]).all() and (out["iter"] == ref["iter"]).all()
+    assert (out["rho_updates"] == ref["rho_updates"]).all()
+    assert rel_inf(out["x"], ref["x"]).max() < TOL
+    assert np.abs((out["obj"] - ref["obj"]) / ref["obj"]).max() < TOL
+
+
+def test_ragged_batches_and_mixed_rows(eng):
+    """Edge cases of the batched entry point: a single QP, a batch that is not a multiple of anything, instances with
+    zero obstacle rows inside a padded batch, mixed dynamic / static flags per instance — all against the oracle."""
+    from tests.helpers import oracle_solve
+    orc = _oracle()
+    for B in (1, 3, 149):
+        mb = W.static_batch(B, num_obs=4, seed0=6000 + B)
+        out = eng.solve_mpc_batch(mb)
+        ref = orc.solve_batch(to_qp_batch(mb), want_y=False)
+        assert (out["status"] == ref["status"]).all() and (out["iter"] == ref["iter"]).all()
+        assert rel_inf(out["x"], ref["x"]).max() < TOL
+    # per-instance obstacle counts 0..6 in one call (stride 6), per-instance dynamic/static flags
+    rng = np.random.default_rng(5)
+    base = W.static_batch(40, num_obs=6, seed0=7000)
+    nobs = rng.integers(0, 7, size=40).astype(np.int32); nobs[:3] = (0, 6, 1)
+    flags = (rng.uniform(size=(40, 1, 6)) < 0.5).astype(np.int32) * np.ones((1, base.params.N, 1), dtype=np.int32)
+    mb = W.MpcBatch(base.params, base.x0, base.xref, base.obs_c, base.obs_semi, base.obs_yaw, np.ascontiguousarray(flags),
+                    base.lin_pt, base.warm_x, nobs)
+    out = eng.solve_mpc_batch(mb, want_y=True)
+    for b in range(40):
+        R = int(nobs[b])
+        one = W.MpcBatch(base.params, base.x0[b:b + 1], base.xref[b:b + 1], base.obs_c[b:b + 1, :, :R], base.obs_semi[b:b + 1, :, :R],
+                         base.obs_yaw[b:b + 1, :, :R], np.ascontiguousarray(flags[b, :, :R]), base.lin_pt[b:b + 1], base.warm_x[b:b + 1])
+        ref = orc.solve_batch(to_qp_batch(one), want_y=True)
+        assert out["status"][b] == ref["status"][0] and out["iter"][b] == ref["iter"][0], (b, R)
+        assert rel_inf(out["x"][b], ref["x"][0]) < TOL
+        m_b = base.params.m(R)
+        assert np.abs(out["y"][b, :m_b] - ref["y"][0]).max() <= 1e-4 * max(1.0, np.abs(ref["y"][0]).max())
