@@ -191,7 +191,11 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0, 128;" :::
 
 MQ_HD double limit_scaling(double v) { v = v < kMinScaling ? 1.0 : v; return v > kMaxScaling ? kMaxScaling : v; }
 // 1/sqrt(v) of scaling.h's scale_data (sqrt then reciprocal, as OSQP computes it)
+#if MQ_DEV
+MQ_HD double rsqrt_scaling(double v) { return rsqrt(v); }      // <= 1 ulp from 1/sqrt: below every tolerance that is compared
+#else
 MQ_HD double rsqrt_scaling(double v) { return 1.0 / sqrt(v); }
+#endif
 
 // In-place inverse of a symmetric positive definite 6x6 (Gauss-Jordan, no pivoting).
 MQ_HD void inv6(double* a) {

@@ -4,7 +4,7 @@ from intent_mpc_b200 import engine, workloads as W
 engine.LIB_PATH = "scratch/libmpcqp_timing.so"
 eng = engine.Engine(0)
 names = ["setup", "leaf+rhs(warp0)", "pcr_factor", "load", "iterate", "info+check", "park+adapt", "store", "pcr:init", "pcr:invert", "pcr:products", "pcr:final", "setup:ruiz", "-", "-", "-"]
-for B in (1, 1024):
+for B in (1, 1024, 16384):
     mb = W.static_batch(max(B, 1024), num_obs=4).slice(25, 26) if B == 1 else W.static_batch(B, num_obs=4)
     eng.use_history(False)
     out = eng.solve_mpc_batch(mb); out = eng.solve_mpc_batch(mb)
