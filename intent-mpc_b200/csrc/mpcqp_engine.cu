@@ -147,7 +147,7 @@ struct mpcqp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 8;
   const int32_t* nobs_host = nullptr;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs;
@@ -338,6 +338,18 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       CK(cudaEventRecord(e->evs, e->stream));
       if (solo) kern_solo<<<(unsigned)grid, threads_solo, smem_solo, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
       else kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+      CK(cudaGetLastError());
+      e->last_launches += 1;
+      return MPCQP_OK;
+    }
+    if (bt.B >= (long long)e->large_batch_factor * grid) {
+      // Large batch: every SM stays busy with two CTAs to the end anyway, and a one-per-SM launch would only halve the
+      // occupancy of the SMs it takes.  One launch, two CTAs per SM, the hard list first.
+      CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
+      bt.ws = e->ws.as<double>();
+      bt.queue = 3; bt.nhard = e->counter.as<int>() + 1;
+      CK(cudaEventRecord(e->evs, e->stream));
+      kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
       CK(cudaGetLastError());
       e->last_launches += 1;
       return MPCQP_OK;
