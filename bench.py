@@ -288,9 +288,9 @@ def run_b200(args, rank, world, local_rank):
         lat = np.sort(np.array(lat))
         extras["single_qp_latency_ms"] = {"p50": float(lat[len(lat) // 2]), "p90": float(lat[int(0.9 * len(lat))]), "max": float(lat[-1]), "samples": len(lat)}
         # BASELINE.json configs[4]: a slice of the Monte-Carlo sweep (per-instance obstacle counts up to 32 rows per stage,
-        # three launches: one per velocity/acceleration limit pair), device kernels only; the CPU reference on a sample of it
+        # one launch with per-instance velocity/acceleration limits), device kernels only; the CPU reference on a sample of it
         Bs = 16384
-        sb, smeta = W.sweep_batches(rank * Bs, (rank + 1) * Bs)
+        sb, smeta = W.sweep_batches(rank * Bs, (rank + 1) * Bs, one_launch=True)
         for _ in range(2):
             sms = 0.0; sit = 0; shist = {}
             for _, smb in sb:
@@ -299,7 +299,7 @@ def run_b200(args, rank, world, local_rank):
                     shist[k_] = shist.get(k_, 0) + v_
         sw = {"instances_per_gpu": Bs, "value": Bs / (sms * 1e-3), "unit": UNIT, "ms": sms, "iterations_total": sit, "launches": len(sb),
               "rows_per_stage_cap": smeta["cap"], "capped_instances": smeta["capped"], "status_hist": shist,
-              "note": "configs[4] slice; every instance has its own obstacle count (7..32) and dynamic/static mix; device kernels only"}
+              "note": "configs[4] slice; every instance has its own obstacle count (7..32), dynamic/static mix and velocity/acceleration limits; device kernels only"}
         if not args.no_cpu_baseline:
             from oracle import bindings as OB2
             from tests.helpers import oracle_solve

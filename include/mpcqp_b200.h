@@ -104,6 +104,10 @@ int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on);
  * read), its QP has m_b = 16*horizon + 5*N + nobs[b]*N constraints laid out compactly at y + b*m (m from num_obs).
  * Needs horizon 30 and 1 <= num_obs <= 32.  The pointer is read at every call until it is replaced. */
 int mpcqp_engine_num_obs_per_instance(mpcqp_engine* e, const int32_t* nobs);
+/* Per-instance velocity / acceleration limits: limits = host array [B][2] = (max_vel, max_acc) of each instance, replacing
+ * p->max_vel / p->max_acc in the state and input boxes (updateMaxVel / updateMaxAcc per scenario, mpcPlanner.cpp:243-255), or
+ * NULL to switch back.  Needs horizon 30 and num_obs <= 32 (the CTA kernels).  Read at every call until replaced. */
+int mpcqp_engine_limits_per_instance(mpcqp_engine* e, const double* limits);
 /* Wait for the engine's stream (needed after a *_device call before reading results / last_kernel_ms). */
 int mpcqp_engine_sync(mpcqp_engine* e);
 /* FP64 FMA-pipe microbenchmark (all SMs, 8 independent DFMA chains per thread): the measured roofline

@@ -85,6 +85,7 @@ struct Batch {              // device pointers
   const int* nhard;             // number of hard instances (device scalar), or nullptr
   int queue;                    // 0: one queue over all B; 1: hard instances only; 2: the others only
   int slack_stride;             // 0: one slack pattern for the batch; (NS-1)*R: one per instance
+  const double* limits;         // [B][2] per-instance (max_vel, max_acc) replacing the batch-uniform box on v and a (CTA kernels), or nullptr
   const int* nobs;              // [B] obstacle rows per stage of each instance (wide CTA kernel only; R is then the stride of
                                 // g / low / slack and m the stride of y), or nullptr
   long long* dbg;               // [B][8] per-phase clock64 totals (only with MPCQP_PHASE_TIMING), or nullptr
@@ -231,6 +232,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   // slots mid+1..N.
   MQ_HD int cslot(int k) const { return k <= NS / 2 ? k : (NS / 2 + 1) + (N - k); }
   Mem m; const Shape& sh; const Settings& st; int lane;
+  double lim_v = 0.0, lim_a = 0.0; bool has_lim = false;   // per-instance limits (CTA kernels, Batch::limits)
   int Rs;                                        // stride of the obstacle-row inputs (= R unless instances carry their own count)
   double *smem0, *ws0;
   const double* pd; const unsigned char* slack; const double* x0p;
@@ -304,10 +306,19 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 #endif
   }
 
+  // box on variable j of a stage (MP.cpp:904-921); CTA kernels may carry per-instance velocity / acceleration limits
+  MQ_HD double box_lo(int j) const {
+    if constexpr (kCta) { if (has_lim) { if (j >= 3 && j < 6) return -lim_v; if (j >= 8 && j < 11) return -lim_a; } }
+    return sh.blo[j];
+  }
+  MQ_HD double box_hi(int j) const {
+    if constexpr (kCta) { if (has_lim) { if (j >= 3 && j < 6) return lim_v; if (j >= 8 && j < 11) return lim_a; } }
+    return sh.bhi[j];
+  }
   // ---- un-scaled bounds of row i of stage k (MP.cpp:1074-1146) -----------------------------
   MQ_HD void row_bounds(int k, int i, double& lo, double& hi) const {
     if (i < 8) { double v = (k == 0) ? -x0p[i] : 0.0; lo = v; hi = v; }
-    else if (i < NBR) { lo = sh.blo[i - 8]; hi = sh.bhi[i - 8]; }
+    else if (i < NBR) { lo = box_lo(i - 8); hi = box_hi(i - 8); }
     else { lo = LO_(i - NBR, k); hi = INFINITY; }
   }
   // rho class on SCALED bounds (auxil.h: set_rho_vec): -1 loose, 1 equality, 0 inequality
@@ -893,7 +904,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           double z = Z_(8 + j, k), u = U_(8 + j, k);
           if (MODE != 1) {
             double v = al * xo[j] + om * z + u;
-            z = fmin(fmax(v, sh.blo[j]), sh.bhi[j]);
+            z = fmin(fmax(v, box_lo(j)), box_hi(j));
             double un = v - z;
             if (MODE == 2) WSDY_(8 + j, k) = RH_(8 + j, k) * (un - u);
             u = un;
@@ -1819,7 +1830,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         const int j = vj(e);
         x[e] = X_(j, k); zb[e] = Z_(8 + j, k); ub[e] = U_(8 + j, k); b[e] = B_(j, k); rhb[e] = RH_(8 + j, k);
         sd[e] = SD_(j, k); cq[e] = CQ_(j, k);
-        if constexpr (AX) { lo[e] = sh.blo[j]; hi[e] = sh.bhi[j]; }
+        if constexpr (AX) { lo[e] = box_lo(j); hi[e] = box_hi(j); }
       }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -2448,6 +2459,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 
   MQ_HD void run_cta(const Batch& bt, int b, int warp, volatile int* flag, volatile int* cmd = nullptr) {
     x0p = bt.x0 + (size_t)b * 8;
+    if (bt.limits) { lim_v = bt.limits[2 * (size_t)b]; lim_a = bt.limits[2 * (size_t)b + 1]; has_lim = true; }
     slack = bt.slack + (size_t)b * bt.slack_stride;
     if constexpr (kWide) {
       if (bt.nobs) { Dm::R = bt.nobs[b]; Dm::MK = NBR + Dm::R; map_memory(m, smem0, ws0, NS, Dm::R, QMODE); }

@@ -148,9 +148,9 @@ struct mpcqp_engine {
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 8;
-  const int32_t* nobs_host = nullptr;
+  const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
@@ -222,6 +222,7 @@ extern "C" int mpcqp_engine_last_path(const mpcqp_engine* e) { return e ? e->las
 extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->force_generic = on; return MPCQP_OK; }
 extern "C" int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->dyn_per_instance = on ? 1 : 0; return MPCQP_OK; }
 extern "C" int mpcqp_engine_num_obs_per_instance(mpcqp_engine* e, const int32_t* nobs) { if (!e) return MPCQP_ERR_ARG; e->nobs_host = nobs; return MPCQP_OK; }
+extern "C" int mpcqp_engine_limits_per_instance(mpcqp_engine* e, const double* limits) { if (!e) return MPCQP_ERR_ARG; e->limits_host = limits; return MPCQP_OK; }
 extern "C" int mpcqp_engine_use_history(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->use_history = on ? 1 : 0; if (!on) e->hist_B = 0; return MPCQP_OK; }
 #ifdef MPCQP_PHASE_TIMING
 extern "C" int mpcqp_debug_phase_clocks(mpcqp_engine* e, long long* out, int B) {   // development builds only
@@ -290,6 +291,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   e->no_assist = e->force_generic == 3;           // 3 = CTA kernel without the assistant warps (A/B tests)
   bool wide = false;
   SolveKernel kern = pick_kernel(sh.NS, sh.R, want, &mode, false, &wide, bt.nobs != nullptr);
+  if (bt.limits && mode != kModeCta) { e->err = "per-instance limits need a CTA kernel (horizon 30, num_obs <= 32)"; return MPCQP_ERR_ARG; }
   if (bt.nobs && !wide) { e->err = "per-instance obstacle counts need horizon 30 and 1 <= num_obs <= 32"; return MPCQP_ERR_ARG; }
   const int threads = mode == kModeCta ? (wide ? 224 : 128) : 32;
   const size_t smem = (size_t)smem_doubles(sh.NS, sh.R, mode, wide) * sizeof(double);
@@ -441,6 +443,12 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
   }
   Batch bt; memset(&bt, 0, sizeof bt);
   bt.nobs = a.nobs;
+  if (e->limits_host) {
+    for (int b = 0; b < 2 * B; ++b) if (!(e->limits_host[b] > 0.0)) { e->err = "per-instance limits must be positive"; return MPCQP_ERR_ARG; }
+    CK(e->limits.need((size_t)B * 2 * sizeof(double)));
+    CK(cudaMemcpyAsync(e->limits.p, e->limits_host, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    bt.limits = e->limits.as<double>();
+  }
   bt.pd = e->pd.as<double>(); bt.slack = e->slack.as<unsigned char>(); bt.slack_stride = e->dyn_per_instance ? N * R : 0; bt.q = a.q; bt.x0 = a.x0s; bt.g = a.g; bt.low = a.low;
   bt.warm_x = warm_x; bt.x = x; bt.y = y; bt.status = status; bt.iter = iter; bt.rho_updates = rho_updates;
   bt.obj = obj; bt.pri_res = pri_res; bt.dua_res = dua_res; bt.B = B; bt.order = e->order.as<int>(); bt.hard = e->hard.as<int>();

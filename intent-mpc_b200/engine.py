@@ -178,6 +178,9 @@ class Engine:
         nobs = getattr(mb, "nobs", None)
         nobs = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
         self._check(self.lib.mpcqp_engine_num_obs_per_instance(self.h, _ip(nobs)))
+        lim = getattr(mb, "limits", None)
+        lim = None if lim is None else np.ascontiguousarray(lim, dtype=np.float64)
+        self._check(self.lib.mpcqp_engine_limits_per_instance(self.h, _dp(lim)))
         if out is None:
             out = dict(x=np.empty((B, n)), y=np.empty((B, m)) if want_y else None, status=np.empty(B, np.int32),
                        iter=np.empty(B, np.int32), rho_updates=np.empty(B, np.int32), obj=np.empty(B),
@@ -188,6 +191,7 @@ class Engine:
                                                  _ip(out["rho_updates"]), _dp(out["obj"]), _dp(out["pri_res"]),
                                                  _dp(out["dua_res"]))
         self.lib.mpcqp_engine_num_obs_per_instance(self.h, None)
+        self.lib.mpcqp_engine_limits_per_instance(self.h, None)
         self._check(rc)
         return out
 

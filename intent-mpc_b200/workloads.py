@@ -55,6 +55,7 @@ class MpcBatch:
     lin_pt: np.ndarray    # [B,N,3] linearisation point (previous plan, unshifted, or currPos)
     warm_x: np.ndarray    # [B,n] primal warm start (previous plan or zeros); dual warm start is always 0
     nobs: np.ndarray | None = None   # [B] int32 obstacle rows per stage of each instance (<= numObs, the array stride), or None
+    limits: np.ndarray | None = None  # [B,2] per-instance (max_vel, max_acc) overriding params (one launch for a whole sweep), or None
 
     @property
     def B(self) -> int:
@@ -67,7 +68,8 @@ class MpcBatch:
     def slice(self, lo, hi) -> "MpcBatch":
         return MpcBatch(self.params, self.x0[lo:hi], self.xref[lo:hi], self.obs_c[lo:hi], self.obs_semi[lo:hi],
                         self.obs_yaw[lo:hi], self.obs_dyn if self.obs_dyn.ndim == 2 else self.obs_dyn[lo:hi],
-                        self.lin_pt[lo:hi], self.warm_x[lo:hi], None if self.nobs is None else self.nobs[lo:hi])
+                        self.lin_pt[lo:hi], self.warm_x[lo:hi], None if self.nobs is None else self.nobs[lo:hi],
+                        None if self.limits is None else self.limits[lo:hi])
 
 
 GOAL = np.array([105.0, 0.0, 2.0])   # end of ref_trajectory_dynus_benchmark.txt line (mpcNavigation.cpp:201-216)
@@ -280,9 +282,10 @@ def sweep_groups(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = No
     return groups, meta
 
 
-def sweep_batches(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = None):
+def sweep_batches(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = None, one_launch: bool = False):
     """The same instances as sweep_groups(lo, hi), packed for the engine's per-instance obstacle counts: ONE batch per
     (max_vel, max_acc) pair, obstacle arrays padded to SWEEP_CAP rows per stage, `nobs` = rows each instance really has.
+    one_launch=True: a single batch for the whole range, with per-instance limits (`MpcBatch.limits`).
     Returns (batches, meta): batches = list of (index array, MpcBatch)."""
     groups, meta = sweep_groups(lo, hi, seed0, params)
     out = []
@@ -308,4 +311,13 @@ def sweep_batches(lo: int, hi: int, seed0: int = 0, params: MpcParams | None = N
         mbp = MpcBatch(p, cat("x0")[order], cat("xref")[order], obs_c[order], obs_semi[order], obs_yaw[order], obs_dyn[order],
                        cat("lin_pt")[order], cat("warm_x")[order], nobs[order])
         out.append((idx[order], mbp))
+    if one_launch and out:
+        # per-instance limits: the whole range as a single batch (index order), params of the first group for the rest
+        idx = np.concatenate([i for i, _ in out]); order = np.argsort(idx, kind="stable")
+        cat = lambda name: np.concatenate([getattr(mb, name) for _, mb in out])[order]
+        lim = np.concatenate([np.tile([[mb.params.max_vel, mb.params.max_acc]], (mb.B, 1)) for _, mb in out])[order]
+        mb0 = out[0][1]
+        one = MpcBatch(mb0.params, cat("x0"), cat("xref"), cat("obs_c"), cat("obs_semi"), cat("obs_yaw"), cat("obs_dyn"), cat("lin_pt"),
+                       cat("warm_x"), cat("nobs"), lim)
+        return [(idx[order], one)], meta
     return out, meta

@@ -98,6 +98,14 @@ def test_sweep_gpu_matches_oracle():
                 r = refs[int(i)]
                 assert out["status"][j] == r["status"] and out["iter"][j] == r["iter"] and out["rho_updates"][j] == r["rho_updates"]
                 assert rel_inf(out["x"][j], r["x"]) < TOL and abs((out["obj"][j] - r["obj"]) / r["obj"]) < TOL
+        # ... and as ONE launch with per-instance velocity / acceleration limits
+        (idx, mb), = W.sweep_batches(0, 384, one_launch=True)[0]
+        assert mb.B == 384 and mb.limits.shape == (384, 2)
+        out = eng.solve_mpc_batch(mb)
+        for j, i in enumerate(idx):
+            r = refs[int(i)]
+            assert out["status"][j] == r["status"] and out["iter"][j] == r["iter"] and out["rho_updates"][j] == r["rho_updates"]
+            assert rel_inf(out["x"][j], r["x"]) < TOL and abs((out["obj"][j] - r["obj"]) / r["obj"]) < TOL
         # per-instance flags and a shared pattern are the same thing when the patterns agree
         mb = W.static_batch(32, num_obs=4, seed0=300)
         a = eng.solve_mpc_batch(mb)
