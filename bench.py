@@ -41,6 +41,11 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
     ap.add_argument("--num-obs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="static", choices=["static", "sweep"],
+                    help="static: configs[1], the bench line the driver reads (default).  sweep: configs[4], --instances Monte-Carlo "
+                         "instances sharded by index over the ranks (strong scaling), one JSON line of the same shape")
+    ap.add_argument("--instances", type=int, default=1000000, help="--workload sweep: total instances over all ranks")
+    ap.add_argument("--chunk", type=int, default=32768, help="--workload sweep: instances per engine call")
     return ap.parse_args()
 
 
@@ -363,12 +368,59 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: --instances sweep instances (intent-mpc_b200/workloads.py:sweep_batches), contiguous index
+    shards over the ranks, no collective on the solve path.  Each rank generates its shard chunk by chunk on the host
+    (untimed), solves every chunk through the host entry point (e2e: pinned-free numpy buffers, copies inside) and sums the
+    device time of its kernels (`value`); the job's time is the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from intent_mpc_b200 import engine, workloads as W, sharding
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = engine.Engine(local_rank)
+    eng.use_history(False)                              # independent instances: slot history means nothing here
+    lo, hi = sharding.shard_bounds(args.instances, world)[rank]
+    dev_ms = 0.0; wall = 0.0; iters = 0; hist = {}; launches = 0; capped = 0
+    warm = W.sweep_batches(lo, min(lo + 2048, hi), one_launch=True)[0]
+    eng.solve_mpc_batch(warm[0][1])                    # warm-up (kernel load, buffers)
+    for c0 in range(lo, hi, args.chunk):
+        (idx, mb), = W.sweep_batches(c0, min(c0 + args.chunk, hi), one_launch=True)[0]
+        t0 = time.perf_counter()
+        out = eng.solve_mpc_batch(mb)
+        wall += time.perf_counter() - t0
+        dev_ms += eng.last_kernel_ms; launches += eng.last_launches; iters += int(out["iter"].sum())
+        for k_, v_ in _hist(out["status"]).items():
+            hist[k_] = hist.get(k_, 0) + v_
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    agg = torch.tensor([float(iters), float(hi - lo)], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+        n = int(agg[1])
+        line = {"metric": METRIC, "value": n / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"configs[4]: {n} Monte-Carlo sweep instances (run_mpc_benchmark grid: 50/100/200 obstacles, 65 % dynamic, "
+                                       f"limits (1.5,1.5)/(3,3)/(5,20)), up to {W.SWEEP_CAP} obstacle rows per stage, sharded by index",
+                           "chunk": args.chunk, "pins": "adaptive_rho_interval=25,time_limit=0", "iterations_total": int(agg[0]),
+                           "status_hist_rank0": hist},
+                "e2e": {"value": n / (wall_ms * 1e-3), "unit": UNIT, "ms": wall_ms, "note": "host numpy buffers through mpcqp_solve_mpc_batch_host, copies inside; generation of the instances untimed"},
+                "gpu_launches": int(launches)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "sweep":
+        run_sweep(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 
