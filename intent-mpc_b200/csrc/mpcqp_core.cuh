@@ -1752,10 +1752,17 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   // CTA-wide reduction of NM maxima and NS_ sums; every thread ends with the same values (fixed combination order).
   template <int NM, int NS_> MQ_HD void cta_reduce(double (&mx)[NM], double (&sm)[NS_], int warp) {
     static_assert(4 * (NM + NS_) <= 6 * NST, "reduction scratch is the y buffer");
+    // maxima: the values are non-negative and never NaN (see the callers' `up`), so IEEE order is the order of the bit
+    // patterns: two integer warp reductions (high word, then low word among the lanes that hold the maximal high word)
+#pragma unroll
+    for (int e = 0; e < NM; ++e) {
+      const unsigned hi = (unsigned)__double2hiint(mx[e]);
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)__double2loint(mx[e]) : 0u);
+      mx[e] = __hiloint2double((int)mh, (int)ml);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int e = 0; e < NM; ++e) { const double v = __shfl_xor_sync(0xffffffffu, mx[e], o); mx[e] = v > mx[e] ? v : mx[e]; }
 #pragma unroll
       for (int e = 0; e < NS_; ++e) sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], o);
     }
