@@ -319,6 +319,23 @@ def run_b200(args, rank, world, local_rank):
                 sw["cpu_reference"] = {"value": nq / (time.perf_counter() - t0), "unit": UNIT, "cores": os.cpu_count() or 1,
                                        "sample": f"{nq} instances with {smeta['cap']} rows per stage out of the first 2048, assembly by pattern group + libosqp one QP per thread (includes the numpy assembly)"}
         extras["sweep"] = sw
+        # BASELINE.json configs[2]: 10,923 scenarios x 6 intent candidates = 65,538 QPs per control step, warm-started from the
+        # plan chosen one step earlier (candidate enumeration / scoring on the host, intent-mpc_b200/receding.py; untimed)
+        if rank == 0:
+            from intent_mpc_b200 import receding
+            rs = receding.IntentSweep(S=10923, D=4, seed0=5)
+            rs.step(eng.solve_mpc_batch)
+            per = []
+            for _ in range(3):
+                ms_ = [0.0]; its_ = [0]; nq_ = [0]
+                def solve_(mb_):
+                    o_ = eng.solve_mpc_batch(mb_); ms_[0] += eng.last_kernel_ms; its_[0] += int(o_["iter"].sum()); nq_[0] += mb_.B
+                    return o_
+                rs.step(solve_)
+                per.append((nq_[0], ms_[0], its_[0]))
+            extras["receding_horizon"] = {"qps_per_step": per[-1][0], "value": per[-1][0] / (per[-1][1] * 1e-3), "unit": UNIT,
+                                          "ms_per_step": [p_[1] for p_ in per], "iterations_per_step": [p_[2] for p_ in per],
+                                          "note": "configs[2] at full size, control steps 2-4 of a warm-started loop; device kernels of the two solve calls per step"}
     except Exception as ex:
         extras["error"] = repr(ex)
 
