@@ -94,6 +94,10 @@ int mpcqp_engine_force_generic(mpcqp_engine* e, int on);
  * the next call has the same batch size and num_obs (a receding-horizon loop: slot b is the same scenario one control
  * step later), starts the slots that ran long first, one per SM.  Results never depend on it.  0 switches it off. */
 int mpcqp_engine_use_history(mpcqp_engine* e, int on);
+/* Migration (default on): in batches larger than the SM count, an instance that is still iterating after 300 iterations
+ * parks its state and is resumed — bit-identically — by a follow-up launch (on an SM of its own for small batches), so
+ * that instances nobody could predict to be long do not form the tail of the batch.  Results never depend on it. */
+int mpcqp_engine_use_migration(mpcqp_engine* e, int on);
 /* Layout of the obs_dyn argument of the batched entry point: 0 (default) = one [N][R] pattern shared by the batch (the
  * candidates of one control step), 1 = [B][N][R], one pattern per instance (Monte-Carlo sweeps where every instance has
  * its own mix of dynamic and static obstacles; updateObstacleParam's flags, mpcPlanner.cpp:1148-1197). */

@@ -47,7 +47,8 @@ constexpr double kMinScaling = 1e-04, kMaxScaling = 1e+04, kInfty = 1e30;
 constexpr double kOsqpNan = 2143289344.0;  // constants.h:95-97: (c_float)0x7fc00000UL is this NUMBER
 enum Status : int {                         // constants.h:18-30
   kDualInfInacc = 4, kPrimInfInacc = 3, kSolvedInacc = 2, kSolved = 1, kMaxIter = -2,
-  kPrimInf = -3, kDualInf = -4, kNonCvx = -7, kUnsolved = -10
+  kPrimInf = -3, kDualInf = -4, kNonCvx = -7, kUnsolved = -10,
+  kSuspended = -100                         // internal: parked for another launch to resume (never reported)
 };
 
 constexpr int NX = 8, NU = 5, NV = 13;      // mpcPlanner.h:42-43
@@ -85,6 +86,11 @@ struct Batch {              // device pointers
   const int* nhard;             // number of hard instances (device scalar), or nullptr
   int queue;                    // 0: one queue over all B; 1: hard instances only; 2: the others only
   int slack_stride;             // 0: one slack pattern for the batch; (NS-1)*R: one per instance
+  // migration of long-running instances (CTA kernels): an instance that is still running after `suspend_at` iterations
+  // parks its state in slot s = (*susp_count)++ (if s < susp_cap) of susp_cold / susp_scal / susp_list and a later launch
+  // (queue 4) resumes it, bit-identically, where it stopped
+  int suspend_at, susp_cap, susp_stride;
+  double* susp_cold; double* susp_scal; int* susp_list; int* susp_count;
   const double* limits;         // [B][2] per-instance (max_vel, max_acc) replacing the batch-uniform box on v and a (CTA kernels), or nullptr
   const int* nobs;              // [B] obstacle rows per stage of each instance (wide CTA kernel only; R is then the stride of
                                 // g / low / slack and m the stride of y), or nullptr
@@ -233,6 +239,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   MQ_HD int cslot(int k) const { return k <= NS / 2 ? k : (NS / 2 + 1) + (N - k); }
   Mem m; const Shape& sh; const Settings& st; int lane;
   double lim_v = 0.0, lim_a = 0.0; bool has_lim = false;   // per-instance limits (CTA kernels, Batch::limits)
+  // suspend / resume (Batch::suspend_at)
+  bool allow_suspend_ = false, resume_ = false, resume_soft_ = false, susp_refactor_ = false;
+  int susp_K_ = 0, susp_cap_ = 0, susp_slot_ = -1, resume_iter_ = 0, resume_rho_updates_ = 0;
+  int* susp_count_ = nullptr;
   int Rs;                                        // stride of the obstacle-row inputs (= R unless instances carry their own count)
   double *smem0, *ws0;
   const double* pd; const unsigned char* slack; const double* x0p;
@@ -2328,8 +2338,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     };
 
     // ---- osqp_solve (osqp.h:78): same control flow as solve() below
-    status = kUnsolved; rho_updates = 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
-    int iter = 0;
+    status = kUnsolved; rho_updates = resume_ ? resume_rho_updates_ : 0; info_iter = 0; obj = 0.0; pri_res = 0.0; dua_res = 0.0;
+    int iter = resume_ ? resume_iter_ : 0;
+    // a resumed instance re-creates the factorisation from its parked rho vector; unless a rho update was pending when it
+    // was parked, it then continues from the parked right-hand side (soft) exactly as if it had never stopped
+    bool soft = resume_ && resume_soft_;
     bool refactor = true, last_checked = false, approx = false, reload = false;
     for (;;) {
       bool do_info, do_check, do_adapt = false;
@@ -2339,13 +2352,20 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           cta_sync();                                // parked iterates / new Rh of all warps are visible to warp 0
           MQ_T0();
           if (warp == 0) {
-            factor(); rows_phase<1>(); rhs_finish();      // leaf elimination + T blocks; whole right-hand side into B_
-            MQ_FOR_STAGES(kk) { OG_(0, kk) = 0.0; OG_(1, kk) = 0.0; OG_(2, kk) = 0.0; }
+            factor();                                     // leaf elimination + T blocks
+            if (!soft) {
+              rows_phase<1>(); rhs_finish();              // whole right-hand side into B_
+              MQ_FOR_STAGES(kk) { OG_(0, kk) = 0.0; OG_(1, kk) = 0.0; OG_(2, kk) = 0.0; }
+            }
           }
           MQ_T(1);
           pcr_factor_cta(warp);                           // starts and ends with a CTA barrier
           MQ_T(2);
           load();
+          if (soft) {                                     // parked obstacle parts of the right-hand side (see the suspend exit)
+            if constexpr (AX) ogp = TD_(cc, k); else { ps[0] = TD_(3, k); ps[1] = TD_(4, k); }
+            soft = false;
+          }
           MQ_T(3);
           refactor = false; reload = true;
         }
@@ -2410,8 +2430,41 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           MQ_T(6);
         }
       }
+      if (allow_suspend_ && iter == susp_K_ && iter < st.max_iter) {
+        // still running after K iterations: hand the instance to a later launch if a slot is free
+        cta_sync();
+        if (warp == 0 && lane == 0) *flag = atomicAdd(susp_count_, 1);
+        cta_sync();
+        const int slot = *flag;
+        cta_sync();
+        if (slot < susp_cap_) { susp_slot_ = slot; susp_refactor_ = refactor; status = kSuspended; break; }
+        allow_suspend_ = false;
+      }
     }
     park();
+    if (status == kSuspended && live) {
+      if constexpr (AX) TD_(cc, k) = ogp; else { TD_(3, k) = ps[0]; TD_(4, k) = ps[1]; }
+    }
+  }
+
+  // Resume the instance parked in `slot` by another launch (run_cta's suspend exit): same state, same arithmetic from here on.
+  MQ_HD void run_cta_resume(const Batch& bt, int slot, int warp, volatile int* flag, volatile int* cmd = nullptr) {
+    const int b = bt.susp_list[slot];
+    x0p = bt.x0 + (size_t)b * 8;
+    if (bt.limits) { lim_v = bt.limits[2 * (size_t)b]; lim_a = bt.limits[2 * (size_t)b + 1]; has_lim = true; }
+    slack = bt.slack + (size_t)b * bt.slack_stride;
+    const double* src = bt.susp_cold + (size_t)slot * bt.susp_stride;
+    for (int i = threadIdx.x; i < cold_slots(R) * NS; i += 128) m.E[i] = src[i];
+    const double* sc = bt.susp_scal + (size_t)slot * 8;
+    c = sc[0]; cinv = sc[1]; rho = sc[2]; nq = sc[3]; nq_s = sc[4];
+    resume_ = true; resume_rho_updates_ = (int)sc[5]; resume_soft_ = sc[6] == 0.0; resume_iter_ = (int)sc[7];
+    allow_suspend_ = false;
+    cta_sync();
+    if (warp < 3) solve_role<true>(warp, flag, cmd); else solve_role<false>(warp, flag, cmd);
+    resume_ = false;
+    cta_sync();
+    if (warp == 0) store(bt, b);
+    cta_sync();
   }
 
   // PCR assistant (threads 128..223 of an ASSIST block): axis warp `a` keeps its rows of the level 1..3 matrices in
@@ -2483,9 +2536,21 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
       cta_sync();
       MQ_T(0);
     }
+    allow_suspend_ = bt.suspend_at > 0 && bt.suspend_at < st.max_iter && !kWide;
+    susp_K_ = bt.suspend_at; susp_cap_ = bt.susp_cap; susp_count_ = bt.susp_count; resume_ = false;
     if (warp < 3) solve_role<true>(warp, flag, cmd); else solve_role<false>(warp, flag, cmd);
     cta_sync();
-    {
+    if (status == kSuspended) {                            // park the cold block and the scalars in the slot; no result yet
+      double* dst = bt.susp_cold + (size_t)susp_slot_ * bt.susp_stride;
+      for (int i = threadIdx.x; i < cold_slots(R) * NS; i += 128) dst[i] = m.E[i];
+      if (threadIdx.x == 0) {
+        double* sc = bt.susp_scal + (size_t)susp_slot_ * 8;
+        sc[0] = c; sc[1] = cinv; sc[2] = rho; sc[3] = nq; sc[4] = nq_s; sc[5] = (double)rho_updates; sc[6] = susp_refactor_ ? 1.0 : 0.0;
+        sc[7] = (double)susp_K_;
+        bt.susp_list[susp_slot_] = b;
+      }
+      cta_sync();
+    } else {
       MQ_T0();
       if (warp == 0) store(bt, b);
       cta_sync();

@@ -147,10 +147,10 @@ struct mpcqp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 8;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 8; int migrate = 1, suspend_at = 300, hist_active = 0;
   const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_ctr;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
@@ -223,6 +223,7 @@ extern "C" int mpcqp_engine_force_generic(mpcqp_engine* e, int on) { if (!e) ret
 extern "C" int mpcqp_engine_obs_dyn_per_instance(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->dyn_per_instance = on ? 1 : 0; return MPCQP_OK; }
 extern "C" int mpcqp_engine_num_obs_per_instance(mpcqp_engine* e, const int32_t* nobs) { if (!e) return MPCQP_ERR_ARG; e->nobs_host = nobs; return MPCQP_OK; }
 extern "C" int mpcqp_engine_limits_per_instance(mpcqp_engine* e, const double* limits) { if (!e) return MPCQP_ERR_ARG; e->limits_host = limits; return MPCQP_OK; }
+extern "C" int mpcqp_engine_use_migration(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->migrate = on ? 1 : 0; return MPCQP_OK; }
 extern "C" int mpcqp_engine_use_history(mpcqp_engine* e, int on) { if (!e) return MPCQP_ERR_ARG; e->use_history = on ? 1 : 0; if (!on) e->hist_B = 0; return MPCQP_OK; }
 #ifdef MPCQP_PHASE_TIMING
 extern "C" int mpcqp_debug_phase_clocks(mpcqp_engine* e, long long* out, int B) {   // development builds only
@@ -344,7 +345,26 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       e->last_launches += 1;
       return MPCQP_OK;
     }
+    // Migration of long-running instances: whoever is still iterating after suspend_at iterations in a two-per-SM launch
+    // parks its state; a follow-up launch resumes these instances (bit-identically) — on SMs of their own for small
+    // batches, evenly spread for large ones — so that an instance nobody could predict to be long does not form the tail.
+    const bool migrate = e->migrate && e->suspend_at > 0 && e->suspend_at < st.max_iter;
+    if (migrate) {
+      const int cap = bt.B < 8192 ? bt.B : 8192;
+      const int stride = cold_slots(sh.R) * sh.NS;
+      CK(e->susp_cold.need((size_t)cap * stride * sizeof(double)));
+      CK(e->susp_scal.need((size_t)cap * 8 * sizeof(double)));
+      CK(e->susp_list.need((size_t)cap * sizeof(int)));
+      CK(e->susp_ctr.need(sizeof(int)));
+      CK(cudaMemsetAsync(e->susp_ctr.p, 0, sizeof(int), e->stream));
+      bt.suspend_at = e->suspend_at; bt.susp_cap = cap; bt.susp_stride = stride;
+      bt.susp_cold = e->susp_cold.as<double>(); bt.susp_scal = e->susp_scal.as<double>();
+      bt.susp_list = e->susp_list.as<int>(); bt.susp_count = e->susp_ctr.as<int>();
+    }
     if (bt.B >= (long long)e->large_batch_factor * grid) {
+      // (migration: the follow-up launch only starts when this one has drained, so it pays only where nothing is known
+      // about the instances — no iteration history — and the batch is long enough to amortise the second launch)
+      if (e->hist_active || bt.B < 32 * grid) bt.suspend_at = 0;
       // Large batch: every SM stays busy with two CTAs to the end anyway, and a one-per-SM launch would only halve the
       // occupancy of the SMs it takes.  One launch, two CTAs per SM, the hard list first.
       CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
@@ -354,20 +374,32 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
       CK(cudaGetLastError());
       e->last_launches += 1;
+      if (bt.suspend_at > 0) {                             // the parked instances, again two per SM over the whole GPU
+        Batch br = bt; br.queue = 4; br.suspend_at = 0;
+        kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, br, wsd, e->counter.as<int>());
+        CK(cudaGetLastError());
+        e->last_launches += 1;
+      }
       return MPCQP_OK;
     }
     const long long gh = e->num_sms < bt.B ? e->num_sms : bt.B;
-    CK(e->ws.need((size_t)(grid + gh) * wsd * sizeof(double)));
+    CK(e->ws.need((size_t)(grid + 2 * gh) * wsd * sizeof(double)));
     bt.nhard = e->counter.as<int>() + 1;
     CK(cudaEventRecord(e->evs, e->stream));
     CK(cudaEventRecord(e->evf, e->stream));
     CK(cudaStreamWaitEvent(e->stream2, e->evf, 0));
-    Batch bh = bt; bh.queue = 1; bh.ws = e->ws.as<double>();
+    Batch bh = bt; bh.queue = 1; bh.ws = e->ws.as<double>(); bh.suspend_at = 0;
     kern_solo<<<(unsigned)gh, threads_solo, smem_solo, e->stream>>>(sh, st, bh, wsd, e->counter.as<int>());
     CK(cudaGetLastError());
     Batch bn = bt; bn.queue = 2; bn.ws = e->ws.as<double>() + (size_t)gh * wsd;
     kern<<<(unsigned)grid, threads, smem, e->stream2>>>(sh, st, bn, wsd, e->counter.as<int>());
     CK(cudaGetLastError());
+    if (migrate) {                                         // the parked instances, one per SM (with assistants), behind the second launch
+      Batch br = bt; br.queue = 4; br.suspend_at = 0; br.ws = e->ws.as<double>() + (size_t)(gh + grid) * wsd;
+      kern_solo<<<(unsigned)gh, threads_solo, smem_solo, e->stream2>>>(sh, st, br, wsd, e->counter.as<int>());
+      CK(cudaGetLastError());
+      e->last_launches += 1;
+    }
     CK(cudaEventRecord(e->evj, e->stream2));
     CK(cudaStreamWaitEvent(e->stream, e->evj, 0));
     e->last_launches += 2;
@@ -427,6 +459,7 @@ static int solve_mpc_device(mpcqp_engine* e, const mpcqp_mpc_params* p, const mp
     a.nobs = e->nobs.as<int>();
   }
   a.hist = (e->use_history && e->hist_B == B && e->hist_R == R) ? e->hist.as<int>() : nullptr;
+  e->hist_active = a.hist != nullptr;
   a.hist_thresh = 500;
   CK(cudaMemsetAsync(e->hard.p, 0, (size_t)B * sizeof(int), e->stream));
   CK(cudaMemsetAsync(e->counter.p, 0, 4 * sizeof(int), e->stream));

@@ -53,6 +53,17 @@ __global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solv
   // queue 0: all instances in natural order.  queue 1: the hard list only.  queue 2: everything not flagged hard, then
   // whatever is left of the hard list (so an over-long hard list does not serialise on the one-per-SM launch).
   // queue 3: the hard list first, then everything else (one launch; used when every CTA has an SM to itself anyway).
+  if (bt.queue == 4) {                                     // resume the instances parked by an earlier launch
+    int n = *bt.susp_count; if (n > bt.susp_cap) n = bt.susp_cap;
+    for (;;) {
+      if (threadIdx.x == 0) s_next = atomicAdd(counter + 2, 1);
+      cta_sync();
+      const int slot = s_next;
+      cta_sync();
+      if (slot >= n) break;
+      qp.run_cta_resume(bt, slot, warp, &s_flag, s_cmd);
+    }
+  } else {
   bool natural = bt.queue != 1 && bt.queue != 3;
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(counter + ((natural && bt.queue >= 2) ? 3 : 0), 1);
@@ -68,6 +79,7 @@ __global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solv
       b = bt.order[idx];
     }
     qp.run_cta(bt, b, warp, &s_flag, s_cmd);
+  }
   }
   if constexpr (ASSIST) {                                  // release the assistants
     if (threadIdx.x == 0) s_cmd[0] = -1;

@@ -151,6 +151,9 @@ class Engine:
         """Scheduling hint from the previous call's iteration counts (mpcqp_engine_use_history)."""
         self._check(self.lib.mpcqp_engine_use_history(self.h, C.c_int(1 if on else 0)))
 
+    def use_migration(self, on: bool = True):
+        self._check(self.lib.mpcqp_engine_use_migration(self.h, C.c_int(1 if on else 0)))
+
     def fp64_fma_peak_tflops(self) -> float:
         tf = C.c_double()
         self._check(self.lib.mpcqp_fp64_fma_peak(self.h, C.byref(tf)))

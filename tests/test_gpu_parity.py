@@ -139,6 +139,15 @@ def test_bitwise_determinism_under_cold_caches_and_scheduling(eng):
             assert np.array_equal(out["iter"], ref["iter"]) and np.array_equal(out["x"], ref["x"]), f"repeat {rep} differs"
     finally:
         eng.use_history(True)
+    # migration of long-running instances to a follow-up launch (default on) against everything solved where it started
+    for hist in (False, True):
+        eng.use_history(hist); eng.use_migration(False)
+        off = eng.solve_mpc_batch(mb)
+        eng.use_migration(True)
+        on = eng.solve_mpc_batch(mb)
+        for k in ("x", "iter", "status", "rho_updates", "obj", "pri_res", "dua_res"):
+            assert np.array_equal(off[k], ref[k]) and np.array_equal(on[k], ref[k]), (hist, k)
+    eng.use_history(True)
     long_ones = np.argsort(ref["iter"])[-3:]
     for i in list(long_ones) + [0, 1]:
         one = eng.solve_mpc_batch(mb.slice(int(i), int(i) + 1))
