@@ -41,9 +41,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
     ap.add_argument("--num-obs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="static", choices=["static", "sweep"],
+    ap.add_argument("--workload", default="static", choices=["static", "sweep", "receding"],
                     help="static: configs[1], the bench line the driver reads (default).  sweep: configs[4], --instances Monte-Carlo "
-                         "instances sharded by index over the ranks (strong scaling), one JSON line of the same shape")
+                         "instances sharded by index over the ranks (strong scaling), one JSON line of the same shape.  receding: "
+                         "configs[2], 10,923 scenarios x 6 intent candidates per rank, --steps warm-started control steps")
     ap.add_argument("--instances", type=int, default=1000000, help="--workload sweep: total instances over all ranks")
     ap.add_argument("--chunk", type=int, default=32768, help="--workload sweep: instances per engine call")
     return ap.parse_args()
@@ -430,6 +431,54 @@ def run_sweep(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_receding(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: per rank 10,923 scenarios x 6 intent candidates = 65,538 QPs per control step, --steps
+    control steps of the warm-started receding-horizon loop (intent-mpc_b200/receding.py; enumeration / scoring on the host,
+    untimed).  `value` = QPs per second of device kernel time, summed over the steps; the max over ranks is the job's time."""
+    import torch
+    import torch.distributed as dist
+    from intent_mpc_b200 import engine, receding
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = engine.Engine(local_rank)
+    S = 10923
+    rs = receding.IntentSweep(S=S, D=4, seed0=1000 * rank + 5)
+    rs.step(eng.solve_mpc_batch)                        # first control step: obstacle-free QPs (mpcPlanner.cpp:598-602)
+    ms = [0.0]; its = [0]; nq = [0]; wall = [0.0]; hist = {}
+    def solve_(mb_):
+        t0 = time.perf_counter()
+        o_ = eng.solve_mpc_batch(mb_)
+        wall[0] += time.perf_counter() - t0
+        ms[0] += eng.last_kernel_ms; its[0] += int(o_["iter"].sum()); nq[0] += mb_.B
+        for k_, v_ in _hist(o_["status"]).items():
+            hist[k_] = hist.get(k_, 0) + v_
+        return o_
+    per_step = []
+    for _ in range(args.steps):
+        m0 = ms[0]
+        rs.step(solve_)
+        per_step.append(ms[0] - m0)
+    dev = torch.device("cuda", local_rank)
+    t = torch.tensor([ms[0], wall[0] * 1e3], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(nq[0]), float(its[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        line = {"metric": METRIC, "value": float(agg[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 1,
+                "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"configs[2]: {S} scenarios x 6 intent candidates = {6 * S} QPs per control step per GPU, {args.steps} warm-started "
+                                       "receding-horizon steps (4 dynamic obstacles with 4 intent predictions each; candidates 4, 5 carry the closest obstacle twice)",
+                           "pins": "adaptive_rho_interval=25,time_limit=0", "iterations_total": int(agg[1]), "status_hist_rank0": hist,
+                           "ms_per_step_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
+                           "progress_m_rank0": float((rs.pos[:, 0]).mean())},
+                "e2e": {"value": float(agg[0]) / (float(t[1]) * 1e-3), "unit": UNIT, "ms": float(t[1]),
+                        "note": "the solve calls with host numpy buffers (copies inside); candidate enumeration and scoring on the host are untimed"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -438,6 +487,8 @@ def main():
         run_reference(args, rank, world)
     elif args.workload == "sweep":
         run_sweep(args, rank, world, local_rank)
+    elif args.workload == "receding":
+        run_receding(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 

@@ -116,26 +116,29 @@ class IntentSweep:
         if not self.first and self.states is not None:
             warm[:, : 8 * NS] = self.states.reshape(S, -1); warm[:, 8 * NS:] = self.controls.reshape(S, -1)
         x0 = np.concatenate([self.pos, self.vel], axis=1)
-        groups = {D: [], D + 1: []}
-        for s in range(S):
-            others = [j for j in range(D) if j != ob[s]]
-            for pos_i in range(6):
-                combo = COMBOS[order[s, pos_i]]
-                tr = [(ob[s], it) for it in combo] + [(j, maxint[s, j]) for j in others]
-                groups[len(tr)].append((s, pos_i, tr))
+        # vectorised over scenarios: candidate (s, sorted position) -> obstacle list [closest with each intent of the combo,
+        # then every other obstacle (ascending index) with its most likely intent]
+        others = np.array([[j for j in range(D) if j != o] for o in range(D)], dtype=np.int64)[ob]      # [S, D-1]
+        c_int = np.full((6, 2), -1, dtype=np.int64)
+        for ci, combo in enumerate(COMBOS):
+            c_int[ci, : len(combo)] = combo
+        ncomb = np.array([len(c) for c in COMBOS])[order]                                            # [S, 6] intents per sorted candidate
+        groups = {}
         batches, meta = [], []
-        for R in (D, D + 1):
-            g = groups[R]
-            B = len(g)
-            oc = np.zeros((B, N, R, 3)); osz = np.zeros((B, N, R, 3)); oy = np.zeros((B, N, R))
-            sidx = np.array([e[0] for e in g], dtype=np.int64)
-            for b, (s, pos_i, tr) in enumerate(g):
-                for i, (j, it) in enumerate(tr):
-                    oc[b, :, i, :] = pp[s, j, it, :N, :]
-                    osz[b, :, i, :] = ps[s, j, it, :N, :] / 2 + p.dynamic_safety_dist
+        sN = np.arange(N)
+        for R, nc in ((D, 1), (D + 1, 2)):
+            s_i, pos_i = np.nonzero(ncomb == nc)                                                      # row-major: scenario, then sorted position
+            B = len(s_i)
+            cid = order[s_i, pos_i]
+            oj = np.concatenate([np.repeat(ob[s_i, None], nc, axis=1), others[s_i]], axis=1)           # [B, R] obstacle index of each row
+            it = np.concatenate([c_int[cid, :nc], maxint[s_i[:, None], others[s_i]]], axis=1)          # [B, R] intent of each row
+            oc = pp[s_i[:, None, None], oj[:, None, :], it[:, None, :], sN[None, :, None], :]          # [B, N, R, 3]
+            osz = ps[s_i[:, None, None], oj[:, None, :], it[:, None, :], sN[None, :, None], :] / 2 + p.dynamic_safety_dist
             od = np.ones((N, R), dtype=np.int32)                    # all dynamic, no static obstacles: isDyamic = 1
-            batches.append(MpcBatch(p, x0[sidx], xref[sidx], oc, osz, oy, od, np.ascontiguousarray(lin[sidx]), warm[sidx]))
-            meta.append(np.array([(e[0], e[1]) for e in g], dtype=np.int64))
+            batches.append(MpcBatch(p, x0[s_i], xref[s_i], np.ascontiguousarray(oc), np.ascontiguousarray(osz), np.zeros((B, N, R)), od,
+                                    np.ascontiguousarray(lin[s_i]), warm[s_i]))
+            meta.append(np.stack([s_i, pos_i], axis=1).astype(np.int64))
+            groups[R] = (s_i, pos_i)
         self.last = dict(pp=pp, ps=ps, ob=ob, w=w, order=order, xref=xref, groups=groups)
         return batches, meta
 
