@@ -1756,6 +1756,89 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
       }
     }
     cta_sync();
+    // Levels 3 (stride 8) and 4 (stride 16, fused with D'^-1) are applied as ONE operator in the solve: with r the level-2
+    // result, kq the level-4 partner, A/G the level-3 alpha/gamma,
+    //   y_k = Di_k r_k - Di_k A_k r_{k-8} - Di_k G_k r_{k+8} - DM_k (r_kq - A_kq r_{kq-8} - G_kq r_{kq+8}),
+    // and all these stages lie on the chain c0 = k mod 8, c0 + 8, c0 + 16, c0 + 24.  W[p] (this thread's two rows) is the
+    // coefficient of the chain's p-th stage; the 24 pairs replace the level-3 / level-4 entries of the PCR store.
+    {
+      const double2* const L3 = reinterpret_cast<const double2*>(m.PCR) + (kPcrLevels - 2) * (kPcrLevelDoubles / 2);
+      double2* const L34 = reinterpret_cast<double2*>(m.PCR) + (kPcrLevels - 2) * (kPcrLevelDoubles / 2);
+      double W[4][12];
+      const int c0 = k & 7, pk = k >> 3;
+      const int kq = k >= 16 ? k - 16 : (k + 16 <= N ? k + 16 : -1);
+      if (warp < 3) {
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+          for (int e = 0; e < 12; ++e) W[p_][e] = 0.0;
+        const double2* const P4 = L3 + (kPcrLevelDoubles / 2) + (warp * 12) * NS + k;
+        double di[12], dm[12];
+#pragma unroll
+        for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+          for (int bp = 0; bp < 3; ++bp) {
+            const double2 a_ = P4[(ar * 3 + bp) * NS], b_ = P4[(6 + ar * 3 + bp) * NS];
+            di[ar * 6 + 2 * bp] = a_.x; di[ar * 6 + 2 * bp + 1] = a_.y; dm[ar * 6 + 2 * bp] = b_.x; dm[ar * 6 + 2 * bp + 1] = b_.y;
+          }
+        // full 6x6 level-3 matrix (alpha: g = 0, gamma: g = 6) of stage t from the store (rows spread over the three warps)
+        auto mat3 = [&](int t, int g, double (&X)[36]) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int bp = 0; bp < 3; ++bp) {
+              const double2 v = L3[((r >> 1) * 12 + g + (r & 1) * 3 + bp) * NS + t];
+              X[r * 6 + 2 * bp] = v.x; X[r * 6 + 2 * bp + 1] = v.y;
+            }
+        };
+        // W[p] += sgn * rows . X
+        auto acc = [&](int p_, const double (&rows)[12], const double (&X)[36], double sgn) {
+#pragma unroll
+          for (int q_ = 0; q_ < 4; ++q_) if (q_ == p_) {
+#pragma unroll
+            for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                double sm_ = 0.0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) sm_ = fma(rows[ar * 6 + t], X[t * 6 + j], sm_);
+                W[q_][ar * 6 + j] += sgn * sm_;
+              }
+          }
+        };
+        auto accv = [&](int p_, const double (&rows)[12], double sgn) {
+#pragma unroll
+          for (int q_ = 0; q_ < 4; ++q_) if (q_ == p_) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) W[q_][e] += sgn * rows[e];
+          }
+        };
+        double X[36];
+        accv(pk, di, 1.0);
+        if (k - 8 >= 0) { mat3(k, 0, X); acc(pk - 1, di, X, -1.0); }
+        if (k + 8 <= N) { mat3(k, 6, X); acc(pk + 1, di, X, -1.0); }
+        if (kq >= 0) {
+          const int pq = kq >> 3;
+          accv(pq, dm, -1.0);
+          if (kq - 8 >= 0) { mat3(kq, 0, X); acc(pq - 1, dm, X, 1.0); }
+          if (kq + 8 <= N) { mat3(kq, 6, X); acc(pq + 1, dm, X, 1.0); }
+        }
+      }
+      cta_sync();                                  // every thread has read what it needs of levels 3, 4
+      if (warp < 3 && live) {
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+          for (int ar = 0; ar < 2; ++ar)
+#pragma unroll
+            for (int bp = 0; bp < 3; ++bp) {
+              const int e = p_ * 6 + ar * 3 + bp;
+              L34[(e / 12) * (kPcrLevelDoubles / 2) + (warp * 12 + e % 12) * NS + k] = make_double2(W[p_][ar * 6 + 2 * bp], W[p_][ar * 6 + 2 * bp + 1]);
+            }
+      }
+      (void)c0;
+    }
+    cta_sync();
     MQ_T(11);
   }
 
@@ -1983,8 +2066,8 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
           bar_sync(kBarAll, 128);
           r0 += m.RS[k * 4 + cc];
-          // ---- PCR levels 0..3 (with assistants: level 0 only; they run levels 1..3 from registers)
-          constexpr int kRowLevels = ASSIST ? 1 : kPcrLevels - 1;
+          // ---- PCR levels 0..2 (with assistants: level 0 only; they run levels 1, 2 and the final operator from registers)
+          constexpr int kRowLevels = ASSIST ? 1 : kPcrLevels - 2;
 #pragma unroll
           for (int l = 0; l < kRowLevels; ++l) {
             const int s = 1 << l, cur = l & 1;
@@ -2006,11 +2089,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
             if constexpr (ASSIST) {
               if (live) RA2[(1 - cur) * 3 * NS + k * 3 + cc] = make_double2(r0, r1);
-              bar_arrive(kBarH1, 192);                     // hand over to the assistants; fetch the last level meanwhile
-              const double2* mn = M + (kPcrLevels - 1) * (kPcrLevelDoubles / 2);
-#pragma unroll
-              for (int h = 0; h < 12; ++h) mt[h] = mn[h * NS];
-              bar_sync(kBarH2, 192);                       // level 3 is in buffer 0
+              bar_arrive(kBarH1, 192);                     // hand over to the assistants: they deliver y
             } else {
               // next level's matrices: issued before the barrier, consumed after it
               const double2* mn = M + (l + 1) * (kPcrLevelDoubles / 2);
@@ -2020,21 +2099,38 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
               bar_sync(kBarAxis, 96);
             }
           }
-          // ---- last level fused with D'^-1:  y = D'^-1 r_k - (D'^-1 M) r_partner   (buffer 0 holds the level-4 input)
+          // ---- levels 3 and 4 as one operator over the stride-8 chain of this stage (pcr_factor_cta): y = sum_p W_p r_{c0+8p},
+          // r = the level-2 result (buffer 1); the second half of W is fetched while the first is applied
           double y0, y1;
-          {
-            const double2 a0 = RA2[k * 3], a1 = RA2[k * 3 + 1], a2 = RA2[k * 3 + 2];
-            const double2 c0 = RA2[kq * 3], c1 = RA2[kq * 3 + 1], c2 = RA2[kq * 3 + 2];
-            double sa0 = mt[0].x * a0.x, sa1 = mt[3].x * a0.x, sg0 = mt[6].x * c0.x, sg1 = mt[9].x * c0.x;
-            sa0 = fma(mt[0].y, a0.y, sa0); sa1 = fma(mt[3].y, a0.y, sa1); sg0 = fma(mt[6].y, c0.y, sg0); sg1 = fma(mt[9].y, c0.y, sg1);
+          if constexpr (!ASSIST) {
+            const double2* const rb = RA2 + 3 * NS;
+            const int c0 = k & 7;
+            const int t0 = c0, t1 = c0 + 8, t2 = c0 + 16, t3 = c0 + 24 <= N ? c0 + 24 : c0;       // (W_3 = 0 where the chain has three stages)
+            double2 a0 = rb[t0 * 3], a1 = rb[t0 * 3 + 1], a2 = rb[t0 * 3 + 2];
+            double2 c0_ = rb[t1 * 3], c1 = rb[t1 * 3 + 1], c2 = rb[t1 * 3 + 2];
+            const double2* mn = M + (kPcrLevels - 1) * (kPcrLevelDoubles / 2);
+            double2 m2[12];
+#pragma unroll
+            for (int h = 0; h < 12; ++h) m2[h] = mn[h * NS];
+            double sa0 = mt[0].x * a0.x, sa1 = mt[3].x * a0.x, sg0 = mt[6].x * c0_.x, sg1 = mt[9].x * c0_.x;
+            sa0 = fma(mt[0].y, a0.y, sa0); sa1 = fma(mt[3].y, a0.y, sa1); sg0 = fma(mt[6].y, c0_.y, sg0); sg1 = fma(mt[9].y, c0_.y, sg1);
             sa0 = fma(mt[1].x, a1.x, sa0); sa1 = fma(mt[4].x, a1.x, sa1); sg0 = fma(mt[7].x, c1.x, sg0); sg1 = fma(mt[10].x, c1.x, sg1);
             sa0 = fma(mt[1].y, a1.y, sa0); sa1 = fma(mt[4].y, a1.y, sa1); sg0 = fma(mt[7].y, c1.y, sg0); sg1 = fma(mt[10].y, c1.y, sg1);
             sa0 = fma(mt[2].x, a2.x, sa0); sa1 = fma(mt[5].x, a2.x, sa1); sg0 = fma(mt[8].x, c2.x, sg0); sg1 = fma(mt[11].x, c2.x, sg1);
             sa0 = fma(mt[2].y, a2.y, sa0); sa1 = fma(mt[5].y, a2.y, sa1); sg0 = fma(mt[8].y, c2.y, sg0); sg1 = fma(mt[11].y, c2.y, sg1);
-            y0 = sa0 - sg0; y1 = sa1 - sg1;
+            a0 = rb[t2 * 3]; a1 = rb[t2 * 3 + 1]; a2 = rb[t2 * 3 + 2];
+            c0_ = rb[t3 * 3]; c1 = rb[t3 * 3 + 1]; c2 = rb[t3 * 3 + 2];
+            sa0 = fma(m2[0].x, a0.x, sa0); sa1 = fma(m2[3].x, a0.x, sa1); sg0 = fma(m2[6].x, c0_.x, sg0); sg1 = fma(m2[9].x, c0_.x, sg1);
+            sa0 = fma(m2[0].y, a0.y, sa0); sa1 = fma(m2[3].y, a0.y, sa1); sg0 = fma(m2[6].y, c0_.y, sg0); sg1 = fma(m2[9].y, c0_.y, sg1);
+            sa0 = fma(m2[1].x, a1.x, sa0); sa1 = fma(m2[4].x, a1.x, sa1); sg0 = fma(m2[7].x, c1.x, sg0); sg1 = fma(m2[10].x, c1.x, sg1);
+            sa0 = fma(m2[1].y, a1.y, sa0); sa1 = fma(m2[4].y, a1.y, sa1); sg0 = fma(m2[7].y, c1.y, sg0); sg1 = fma(m2[10].y, c1.y, sg1);
+            sa0 = fma(m2[2].x, a2.x, sa0); sa1 = fma(m2[5].x, a2.x, sa1); sg0 = fma(m2[8].x, c2.x, sg0); sg1 = fma(m2[11].x, c2.x, sg1);
+            sa0 = fma(m2[2].y, a2.y, sa0); sa1 = fma(m2[5].y, a2.y, sa1); sg0 = fma(m2[8].y, c2.y, sg0); sg1 = fma(m2[11].y, c2.y, sg1);
+            y0 = sa0 + sg0; y1 = sa1 + sg1;
+            if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
           }
-          if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
-          bar_sync(kBarY, 128);
+          bar_sync(kBarY, (ASSIST || kWide) ? 224 : 128);
+          if constexpr (ASSIST) { const double2 yv = YB2[k * 3 + cc]; y0 = yv.x; y1 = yv.y; }
           if constexpr (kRows) { yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4]; }
           // ---- leaf backward: acceleration of this axis
           xt[0] = y0; xt[1] = y1;
@@ -2058,7 +2154,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           // iteration (or by the prologue); once every warp is past its obstacle rows, their part is added to r11
           bar_sync(kBarAll, 128);
           if (it > 0) { slack_obstacle_sums(); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
-          bar_sync(kBarY, 128);
+          bar_sync(kBarY, ASSIST ? 224 : 128);
           yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4];
           // ---- leaf backward: slack inputs, then slack states
           double xp[2];
@@ -2467,51 +2563,78 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     cta_sync();
   }
 
-  // PCR assistant (threads 128..223 of an ASSIST block): axis warp `a` keeps its rows of the level 1..3 matrices in
-  // registers (144 of them) and runs those levels of every solve; the row warps hand the level-0 result over in
-  // buffer 1 (kBarH1) and take the level-3 result back from buffer 0 (kBarH2).  Commands arrive through cmd[]:
+  // PCR assistant (threads 128..223 of an ASSIST block): axis warp `a` keeps its rows of the level 1, 2 matrices and of the
+  // final operator (levels 3 + 4 composed) in registers (192 of them) and runs them in every solve; the row warps hand
+  // the level-0 result over in buffer 1 (kBarH1) and find y in the y buffer at kBarY.  Commands arrive through cmd[]:
   // cmd[0] = iterations of the next burst (< 0: the block is done), cmd[1] = the factorisation changed.
   MQ_HD void assist_role(const int a, volatile int* cmd) {
     const int k = lane < NS ? lane : NS - 1;
     const bool live = lane < NS;
     double2* const RA2 = reinterpret_cast<double2*>(m.RA);
+    double2* const YB2 = reinterpret_cast<double2*>(m.YB);
     const double2* const M = reinterpret_cast<const double2*>(m.PCR) + (a * 12) * NS + k;
-    double2 mt[3][12];
+    const int c0 = k & 7;
+    const int t0 = c0, t1 = c0 + 8, t2 = c0 + 16, t3 = c0 + 24 <= N ? c0 + 24 : c0;     // the stage's stride-8 chain (W_3 = 0 if it has three stages)
+    double2 mt[2][12], wt[24];
 #pragma unroll
-    for (int l = 0; l < 3; ++l)
+    for (int l = 0; l < 2; ++l)
 #pragma unroll
       for (int h = 0; h < 12; ++h) mt[l][h] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int h = 0; h < 24; ++h) wt[h] = make_double2(0.0, 0.0);
     for (;;) {
       bar_sync(kBarCmd, 224);
       const int n = cmd[0], rl = cmd[1];
       if (n < 0) break;
       if (rl) {
 #pragma unroll
-        for (int l = 0; l < 3; ++l)
+        for (int l = 0; l < 2; ++l)
 #pragma unroll
           for (int h = 0; h < 12; ++h) mt[l][h] = M[(l + 1) * (kPcrLevelDoubles / 2) + h * NS];
+#pragma unroll
+        for (int h = 0; h < 24; ++h) wt[h] = M[(3 + h / 12) * (kPcrLevelDoubles / 2) + (h % 12) * NS];
       }
       for (int it = 0; it < n; ++it) {
         bar_sync(kBarH1, 192);
         double r0, r1;
         { const double2 own = RA2[3 * NS + k * 3 + a]; r0 = own.x; r1 = own.y; }
 #pragma unroll
-        for (int l = 1; l < kPcrLevels - 1; ++l) {
+        for (int l = 1; l < kPcrLevels - 2; ++l) {
           const int s = 1 << l, cur = l & 1;
           const int kmm = k - s >= 0 ? k - s : k, kpp = k + s <= N ? k + s : k;
           const double2* ra = RA2 + cur * 3 * NS;
           const double2 a0 = ra[kmm * 3], a1 = ra[kmm * 3 + 1], a2 = ra[kmm * 3 + 2];
-          const double2 c0 = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
+          const double2 c0_ = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
           const double2* w = mt[l - 1];
-          double sa0 = w[0].x * a0.x, sa1 = w[3].x * a0.x, sg0 = w[6].x * c0.x, sg1 = w[9].x * c0.x;
-          sa0 = fma(w[0].y, a0.y, sa0); sa1 = fma(w[3].y, a0.y, sa1); sg0 = fma(w[6].y, c0.y, sg0); sg1 = fma(w[9].y, c0.y, sg1);
+          double sa0 = w[0].x * a0.x, sa1 = w[3].x * a0.x, sg0 = w[6].x * c0_.x, sg1 = w[9].x * c0_.x;
+          sa0 = fma(w[0].y, a0.y, sa0); sa1 = fma(w[3].y, a0.y, sa1); sg0 = fma(w[6].y, c0_.y, sg0); sg1 = fma(w[9].y, c0_.y, sg1);
           sa0 = fma(w[1].x, a1.x, sa0); sa1 = fma(w[4].x, a1.x, sa1); sg0 = fma(w[7].x, c1.x, sg0); sg1 = fma(w[10].x, c1.x, sg1);
           sa0 = fma(w[1].y, a1.y, sa0); sa1 = fma(w[4].y, a1.y, sa1); sg0 = fma(w[7].y, c1.y, sg0); sg1 = fma(w[10].y, c1.y, sg1);
           sa0 = fma(w[2].x, a2.x, sa0); sa1 = fma(w[5].x, a2.x, sa1); sg0 = fma(w[8].x, c2.x, sg0); sg1 = fma(w[11].x, c2.x, sg1);
           sa0 = fma(w[2].y, a2.y, sa0); sa1 = fma(w[5].y, a2.y, sa1); sg0 = fma(w[8].y, c2.y, sg0); sg1 = fma(w[11].y, c2.y, sg1);
           r0 = (r0 - sa0) - sg0; r1 = (r1 - sa1) - sg1;
           if (live) RA2[(1 - cur) * 3 * NS + k * 3 + a] = make_double2(r0, r1);
-          if (l < kPcrLevels - 2) bar_sync(kBarA, 96); else bar_arrive(kBarH2, 192);
+          bar_sync(kBarA, 96);
+        }
+        // levels 3 and 4 as one operator over the chain (level-2 result in buffer 1): y = sum_p W_p r_{c0+8p}
+        {
+          const double2* const rb = RA2 + 3 * NS;
+          double sa0 = 0.0, sa1 = 0.0, sg0 = 0.0, sg1 = 0.0;
+          const int ts_[4] = {t0, t1, t2, t3};
+#pragma unroll
+          for (int p_ = 0; p_ < 4; p_ += 2) {
+            const double2 a0 = rb[ts_[p_] * 3], a1 = rb[ts_[p_] * 3 + 1], a2 = rb[ts_[p_] * 3 + 2];
+            const double2 c0_ = rb[ts_[p_ + 1] * 3], c1 = rb[ts_[p_ + 1] * 3 + 1], c2 = rb[ts_[p_ + 1] * 3 + 2];
+            const double2* w = wt + 6 * p_;
+            sa0 = fma(w[0].x, a0.x, sa0); sa1 = fma(w[3].x, a0.x, sa1); sg0 = fma(w[6].x, c0_.x, sg0); sg1 = fma(w[9].x, c0_.x, sg1);
+            sa0 = fma(w[0].y, a0.y, sa0); sa1 = fma(w[3].y, a0.y, sa1); sg0 = fma(w[6].y, c0_.y, sg0); sg1 = fma(w[9].y, c0_.y, sg1);
+            sa0 = fma(w[1].x, a1.x, sa0); sa1 = fma(w[4].x, a1.x, sa1); sg0 = fma(w[7].x, c1.x, sg0); sg1 = fma(w[10].x, c1.x, sg1);
+            sa0 = fma(w[1].y, a1.y, sa0); sa1 = fma(w[4].y, a1.y, sa1); sg0 = fma(w[7].y, c1.y, sg0); sg1 = fma(w[10].y, c1.y, sg1);
+            sa0 = fma(w[2].x, a2.x, sa0); sa1 = fma(w[5].x, a2.x, sa1); sg0 = fma(w[8].x, c2.x, sg0); sg1 = fma(w[11].x, c2.x, sg1);
+            sa0 = fma(w[2].y, a2.y, sa0); sa1 = fma(w[5].y, a2.y, sa1); sg0 = fma(w[8].y, c2.y, sg0); sg1 = fma(w[11].y, c2.y, sg1);
+          }
+          if (live) YB2[k * 3 + a] = make_double2(sa0 + sg0, sa1 + sg1);
+          bar_arrive(kBarY, 224);
         }
       }
     }
