@@ -200,3 +200,25 @@ def test_ragged_batches_and_mixed_rows(eng):
         assert rel_inf(out["x"][b], ref["x"][0]) < TOL
         m_b = base.params.m(R)
         assert np.abs(out["y"][b, :m_b] - ref["y"][0]).max() <= 1e-4 * max(1.0, np.abs(ref["y"][0]).max())
+
+
+def test_migration_with_duals_and_other_settings(eng):
+    """Instances parked after 300 iterations and resumed by the follow-up launch: duals requested, a check interval other
+    than the default, a batch in the two-launch regime — bit-identical to the run without migration, and equal to the oracle."""
+    st = engine.default_settings(max_iter=1500, check_termination=50)
+    mb = W.static_batch(400, num_obs=4, seed0=12000)
+    eng.use_history(False)
+    try:
+        eng.use_migration(False)
+        off = eng.solve_mpc_batch(mb, settings=st, want_y=True)
+        eng.use_migration(True)
+        on = eng.solve_mpc_batch(mb, settings=st, want_y=True)
+    finally:
+        eng.use_history(True); eng.use_migration(True)
+    assert (off["iter"] > 300).sum() >= 5                      # something was there to migrate
+    for k in ("x", "y", "iter", "status", "rho_updates", "obj", "pri_res", "dua_res"):
+        assert np.array_equal(off[k], on[k]), k
+    ref = _oracle().solve_batch(to_qp_batch(mb), want_y=True, max_iter=1500, check_termination=50)
+    assert (on["status"] == ref["status"]).all() and (on["iter"] == ref["iter"]).all()
+    assert rel_inf(on["x"], ref["x"]).max() < TOL
+    assert np.abs(on["y"] - ref["y"]).max() <= 1e-4 * max(1.0, np.abs(ref["y"]).max())
