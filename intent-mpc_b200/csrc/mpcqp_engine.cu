@@ -7,6 +7,7 @@
 // There is no host solve path in this library.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <chrono>
@@ -147,7 +148,7 @@ struct mpcqp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 8; int migrate = 1, suspend_at = 300, hist_active = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int migrate = 1, suspend_at = 300, hist_active = 0;
   const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_ctr;
@@ -193,6 +194,9 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
       cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->evf, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->evj, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreate(&e->evs) != cudaSuccess) { delete e; return MPCQP_ERR_CUDA; }
+  // development knobs (scheduling only; results never depend on them)
+  if (const char* v = getenv("MPCQP_LARGE_BATCH_FACTOR")) { const int f = atoi(v); if (f >= 0) e->large_batch_factor = f; }
+  if (const char* v = getenv("MPCQP_SUSPEND_AT")) { const int f = atoi(v); if (f >= 0) e->suspend_at = f; }
   *out = e;
   return MPCQP_OK;
 }
@@ -361,10 +365,13 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       bt.susp_cold = e->susp_cold.as<double>(); bt.susp_scal = e->susp_scal.as<double>();
       bt.susp_list = e->susp_list.as<int>(); bt.susp_count = e->susp_ctr.as<int>();
     }
-    if (bt.B >= (long long)e->large_batch_factor * grid) {
+    // measured crossovers (configs[1]-shaped batches): with a history the single launch wins from ~13 x 296 instances, without
+    // one (nothing known about the instances) the two launches + migration win up to ~40 x 296
+    const int lb_factor = e->large_batch_factor > 0 ? e->large_batch_factor : (e->hist_active ? 13 : 40);
+    if (bt.B >= (long long)lb_factor * grid) {
       // (migration: the follow-up launch only starts when this one has drained, so it pays only where nothing is known
       // about the instances — no iteration history — and the batch is long enough to amortise the second launch)
-      if (e->hist_active || bt.B < 32 * grid) bt.suspend_at = 0;
+      if (e->hist_active) bt.suspend_at = 0;
       // Large batch: every SM stays busy with two CTAs to the end anyway, and a one-per-SM launch would only halve the
       // occupancy of the SMs it takes.  One launch, two CTAs per SM, the hard list first.
       CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
