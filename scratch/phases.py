@@ -6,7 +6,7 @@ eng = engine.Engine(0)
 names = ["setup", "leaf+rhs(warp0)", "pcr_factor", "load", "iterate", "info+check", "park+adapt", "store", "pcr:init", "pcr:invert", "pcr:products", "pcr:final", "setup:ruiz", "-", "-", "-"]
 for B in (1, 1024, 16384):
     mb = W.static_batch(max(B, 1024), num_obs=4).slice(25, 26) if B == 1 else W.static_batch(B, num_obs=4)
-    eng.use_history(False)
+    eng.use_history(False); eng.use_migration(False)
     out = eng.solve_mpc_batch(mb); out = eng.solve_mpc_batch(mb)
     buf = np.zeros((mb.B, 16), dtype=np.int64)
     eng.lib.mpcqp_debug_phase_clocks(eng.h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int(mb.B))
