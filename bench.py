@@ -363,7 +363,7 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(B, R), "batch_per_gpu": B, "num_obs": R, "horizon": p.horizon,
                    "pins": "adaptive_rho_interval=25,time_limit=0", "l2": "flushed between steps (256 MiB write)",
-                   "schedule": "slots that ran >= 500 iterations in the previous call start first, one per SM (receding-horizon hint; results do not depend on it)",
+                   "schedule": "slots that ran >= 500 iterations in the previous call start first, one per SM with three PCR assistant warps (receding-horizon hint); anything else still running after 300 iterations is parked and resumed bit-identically by a follow-up one-per-SM launch; results do not depend on either (extras.headline_without_history = the first, history-less call)",
                    "kernel_path": eng.last_path, "iterations_total": int(iters.sum()), "iterations_max": int(iters.max())},
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / K},
