@@ -222,3 +222,30 @@ def test_migration_with_duals_and_other_settings(eng):
     assert (on["status"] == ref["status"]).all() and (on["iter"] == ref["iter"]).all()
     assert rel_inf(on["x"], ref["x"]).max() < TOL
     assert np.abs(on["y"] - ref["y"]).max() <= 1e-4 * max(1.0, np.abs(ref["y"]).max())
+
+
+def test_per_instance_limits_on_the_register_row_kernels(eng):
+    """mpcqp_engine_limits_per_instance with a compiled obstacle count (R = 4: CTA kernels with the rows in registers,
+    two-launch regime incl. migration): every instance against the oracle solving it with its own max_vel / max_acc."""
+    import dataclasses
+    B = 300
+    base = W.static_batch(B, num_obs=4, seed0=15000)
+    lims = np.array([(1.5, 1.5), (3.0, 3.0), (5.0, 20.0)])[np.arange(B) % 3]
+    base.x0[:, 3:6] *= (lims[:, 0:1] / 5.0)                       # keep the start inside each instance's velocity box
+    warm_x, lin_pt = W._const_vel_plan(base.params, base.x0)
+    mb = W.MpcBatch(base.params, base.x0, base.xref, base.obs_c, base.obs_semi, base.obs_yaw, base.obs_dyn, lin_pt, warm_x, None, lims)
+    eng.use_history(False)
+    try:
+        out = eng.solve_mpc_batch(mb)
+    finally:
+        eng.use_history(True)
+    assert eng.last_path == "cta"
+    orc = _oracle()
+    for g, (vm, am) in enumerate([(1.5, 1.5), (3.0, 3.0), (5.0, 20.0)]):
+        sel = np.nonzero(np.arange(B) % 3 == g)[0]
+        p = dataclasses.replace(base.params, max_vel=vm, max_acc=am)
+        sub = W.MpcBatch(p, mb.x0[sel], mb.xref[sel], mb.obs_c[sel], mb.obs_semi[sel], mb.obs_yaw[sel], mb.obs_dyn, mb.lin_pt[sel], mb.warm_x[sel])
+        ref = orc.solve_batch(to_qp_batch(sub), want_y=False)
+        assert (out["status"][sel] == ref["status"]).all() and (out["iter"][sel] == ref["iter"]).all(), (vm, am)
+        assert (out["rho_updates"][sel] == ref["rho_updates"]).all()
+        assert rel_inf(out["x"][sel], ref["x"]).max() < TOL
