@@ -161,6 +161,19 @@ int mpcqp_solve_mpc_batch_device(mpcqp_engine* e, const mpcqp_mpc_params* p, con
  * select: scenario s has C candidates, rows cand[s][c] of `score` / `x_all`, with weights weight[s][c] (the intent
  * probabilities in the order evaluateTraj indexes them).  best[s] = argmax_c weight * (avg_c/c_c + avg_d/d_c + s_c/avg_s),
  * first maximum, NaN never wins; weighted [S][C] (optional) receives the values; plan [S][n] (optional) the chosen x. */
+/* Candidate enumeration (getIntentComb + findClosestObstacle, mpcPlanner.cpp:663-769) for S scenarios with D predicted
+ * obstacles each:  pred_pos / pred_size [S][D][4 intents][NP >= N][3] (intent order FORWARD, LEFT, RIGHT, STOP of
+ * dynamic_predictor/utils.h:15-20), prob [S][D][4], prev_plan [S][n] or NULL on the first step (then pos [S][3] is used).
+ * The six hypotheses of a scenario, sorted by descending weight, become rows of two solve batches: scen_a [4S] / obs_c_a,
+ * obs_semi_a [4S][N][D][3] (one intent for the closest obstacle) and scen_b [2S] / obs_c_b, obs_semi_b [2S][N][D+1][3] (two
+ * intents: the closest obstacle twice); cand [S][6] = row of sorted candidate c in the concatenation (batch a, then b),
+ * weight [S][6] as evaluateTraj indexes it.  mpcqp_gather_rows_device replicates scenario-level arrays (x0, xref, lin_pt,
+ * warm_x) per row: dst[b] = src[idx[b]]. */
+int mpcqp_intent_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t S, int32_t D, int32_t NP,
+                                   const double* pred_pos, const double* pred_size, const double* prob, const double* prev_plan,
+                                   const double* pos, int32_t* scen_a, int32_t* scen_b, double* obs_c_a, double* obs_semi_a,
+                                   double* obs_c_b, double* obs_semi_b, double* weight, int32_t* cand);
+int mpcqp_gather_rows_device(mpcqp_engine* e, int64_t B, int32_t width, const int32_t* idx, const double* src, double* dst);
 int mpcqp_score_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t B, int32_t num_obs, int32_t n_dynamic,
                                   const double* x, const double* prev_plan, const double* xref, const double* obs_c,
                                   const double* obs_semi, double* score);

@@ -151,7 +151,7 @@ struct mpcqp_engine {
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int migrate = 1, suspend_at = 300, hist_active = 0;
   const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_ctr;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_ctr, cand_tab;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
@@ -522,6 +522,7 @@ extern "C" int mpcqp_engine_sync(mpcqp_engine* e) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms;
   if (cudaEventElapsedTime(&ms, e->evs, e->ev1) == cudaSuccess) e->last_solve_ms = ms;
+  (void)cudaGetLastError();          // events not recorded yet (no solve so far) leave an error behind: not ours to report later
   return MPCQP_OK;
 }
 
@@ -699,6 +700,123 @@ __global__ void mpc_gather_plan_kernel(int S, int C, int n, const int* __restric
   }
 }
 }  // namespace mpcqp
+
+namespace mpcqp {
+// getIntentComb / findClosestObstacle (mpcPlanner.cpp:663-769), one thread per scenario: the closest obstacle (direction-
+// weighted distance on the previous plan, plain distance on the first step), the six intent hypotheses for it sorted by
+// descending weight (std::sort on (weight, index) pairs taken from the back, :728, :753-756), every other obstacle with its
+// most likely intent.  Output: for sorted candidate c of scenario s the obstacle / intent of each of its rows, its row in
+// the 4S-row batch (one intent: D rows per stage) or the 2S-row batch (two intents: the closest obstacle twice, D+1 rows).
+__global__ void mpc_intent_enumerate_kernel(int S, int D, int NP, int n, const double* __restrict__ pp, const double* __restrict__ prob,
+                                            const double* __restrict__ prev_plan, const double* __restrict__ pos,
+                                            int* __restrict__ row_ob, int* __restrict__ row_it, int* __restrict__ scen_a, int* __restrict__ scen_b,
+                                            double* __restrict__ weight, int* __restrict__ cand) {
+  constexpr int FORWARD = 0, LEFT = 1, RIGHT = 2, STOP = 3;          // dynamic_predictor/utils.h:15-20
+  const int combo_it[6][2] = {{STOP, -1}, {LEFT, -1}, {RIGHT, -1}, {FORWARD, -1}, {LEFT, FORWARD}, {RIGHT, FORWARD}};
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    // closest obstacle: positions "now" are the FORWARD predictions at step 0
+    int ob = 0; double best = INFINITY;
+    double s0[3], ta = 0.0;
+    if (prev_plan) {
+      const double* pl = prev_plan + (long long)s * n;
+      s0[0] = pl[0]; s0[1] = pl[1]; s0[2] = pl[2];
+      ta = atan2(pl[8 + 1] - pl[1], pl[8] - pl[0]);
+    } else { s0[0] = pos[s * 3]; s0[1] = pos[s * 3 + 1]; s0[2] = pos[s * 3 + 2]; }
+    for (int j = 0; j < D; ++j) {
+      const double* o = pp + ((((long long)s * D + j) * 4 + FORWARD) * NP) * 3;
+      const double dx = s0[0] - o[0], dy = s0[1] - o[1], dz = s0[2] - o[2];
+      double w = sqrt(dx * dx + dy * dy + dz * dz);
+      if (prev_plan) w *= 3.0 - cos(ta - atan2(o[1] - s0[1], o[0] - s0[0]));
+      if (w < best) { best = w; ob = j; }
+    }
+    const double* pr = prob + ((long long)s * D + ob) * 4;
+    double w6[6] = {pr[STOP], pr[LEFT], pr[RIGHT], pr[FORWARD], fmax(pr[LEFT], pr[FORWARD]), fmax(pr[RIGHT], pr[FORWARD])};
+    int ord[6] = {0, 1, 2, 3, 4, 5};
+    for (int a = 1; a < 6; ++a) {                      // descending by (weight, index)
+      const int v = ord[a]; int b = a - 1;
+      while (b >= 0 && (w6[ord[b]] < w6[v] || (w6[ord[b]] == w6[v] && ord[b] < v))) { ord[b + 1] = ord[b]; --b; }
+      ord[b + 1] = v;
+    }
+    int na = 0, nb = 0;
+    for (int c = 0; c < 6; ++c) {
+      weight[s * 6 + c] = w6[c];                       // ORIGINAL combo order: evaluateTraj indexes it with the sorted position (:866-880)
+      const int id = ord[c], two = id >= 4;
+      const int row = two ? 4 * S + 2 * s + nb : 4 * s + na;
+      if (two) { scen_b[2 * s + nb] = s; ++nb; } else { scen_a[4 * s + na] = s; ++na; }
+      cand[s * 6 + c] = row;
+      int* ro = row_ob + (long long)row * (D + 1); int* ri = row_it + (long long)row * (D + 1);
+      int r = 0;
+      ro[r] = ob; ri[r] = combo_it[id][0]; ++r;
+      if (two) { ro[r] = ob; ri[r] = combo_it[id][1]; ++r; }
+      for (int j = 0; j < D; ++j) if (j != ob) {
+        const double* pj = prob + ((long long)s * D + j) * 4;
+        int mi = 0; for (int t = 1; t < 4; ++t) if (pj[t] > pj[mi]) mi = t;
+        ro[r] = j; ri[r] = mi; ++r;
+      }
+    }
+  }
+}
+// the obstacle rows of every candidate: centre = predicted position, semi-axes = predicted size / 2 + dynamicSafetyDist_
+__global__ void mpc_intent_fill_kernel(int S, int D, int NP, int N, double safety, const double* __restrict__ pp, const double* __restrict__ ps,
+                                       const int* __restrict__ row_ob, const int* __restrict__ row_it, const int* __restrict__ scen_a,
+                                       const int* __restrict__ scen_b, double* __restrict__ ca, double* __restrict__ sa,
+                                       double* __restrict__ cb, double* __restrict__ sb) {
+  const long long na = (long long)4 * S * N * D, nb = (long long)2 * S * N * (D + 1);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < na + nb; t += (long long)gridDim.x * blockDim.x) {
+    const bool two = t >= na;
+    const long long u = two ? t - na : t;
+    const int R = two ? D + 1 : D;
+    const int o = (int)(u % R); const long long bk = u / R; const int k = (int)(bk % N); const int b = (int)(bk / N);
+    const int row = two ? 4 * S + b : b;
+    const int s = two ? scen_b[b] : scen_a[b];
+    const int j = row_ob[(long long)row * (D + 1) + o], it = row_it[(long long)row * (D + 1) + o];
+    const long long src = ((((long long)s * D + j) * 4 + it) * NP + k) * 3;
+    double* c = (two ? cb : ca) + u * 3; double* m = (two ? sb : sa) + u * 3;
+    c[0] = pp[src]; c[1] = pp[src + 1]; c[2] = pp[src + 2];
+    m[0] = ps[src] / 2 + safety; m[1] = ps[src + 1] / 2 + safety; m[2] = ps[src + 2] / 2 + safety;
+  }
+}
+// dst[b][:] = src[idx[b]][:]  (scenario-level inputs replicated per candidate: x0, xref, lin_pt, warm_x)
+__global__ void mpc_gather_rows_kernel(long long B, int w, const int* __restrict__ idx, const double* __restrict__ src, double* __restrict__ dst) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < B * w; t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / w; dst[t] = src[(long long)idx[b] * w + (t - b * w)];
+  }
+}
+}  // namespace mpcqp
+
+extern "C" int mpcqp_intent_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t S, int32_t D, int32_t NP,
+                                              const double* pred_pos, const double* pred_size, const double* prob, const double* prev_plan,
+                                              const double* pos, int32_t* scen_a, int32_t* scen_b, double* obs_c_a, double* obs_semi_a,
+                                              double* obs_c_b, double* obs_semi_b, double* weight, int32_t* cand) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (!p || S <= 0 || D <= 0 || D > 31 || NP < p->horizon - 1 || !pred_pos || !pred_size || !prob || (!prev_plan && !pos) || !scen_a || !scen_b ||
+      !obs_c_a || !obs_semi_a || !obs_c_b || !obs_semi_b || !weight || !cand) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
+  CK(cudaSetDevice(e->device));
+  const int NS = p->horizon, N = NS - 1, n = 8 * NS + 5 * N;
+  CK(e->cand_tab.need((size_t)6 * S * (D + 1) * 2 * sizeof(int)));
+  int* row_ob = e->cand_tab.as<int>(); int* row_it = row_ob + (size_t)6 * S * (D + 1);
+  mpc_intent_enumerate_kernel<<<(unsigned)((S + 127) / 128), 128, 0, e->stream>>>(S, D, NP, n, pred_pos, prob, prev_plan, pos, row_ob, row_it,
+                                                                                    scen_a, scen_b, weight, cand);
+  CK(cudaGetLastError());
+  const long long total = (long long)4 * S * N * D + (long long)2 * S * N * (D + 1);
+  long long blocks = (total + 255) / 256; const long long cap = (long long)e->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  mpc_intent_fill_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(S, D, NP, N, p->dynamic_safety_dist, pred_pos, pred_size, row_ob, row_it,
+                                                                   scen_a, scen_b, obs_c_a, obs_semi_a, obs_c_b, obs_semi_b);
+  CK(cudaGetLastError());
+  return MPCQP_OK;
+}
+
+extern "C" int mpcqp_gather_rows_device(mpcqp_engine* e, int64_t B, int32_t width, const int32_t* idx, const double* src, double* dst) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (B <= 0 || width <= 0 || !idx || !src || !dst) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
+  CK(cudaSetDevice(e->device));
+  long long blocks = (B * width + 255) / 256; const long long cap = (long long)e->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  mpc_gather_rows_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(B, width, idx, src, dst);
+  CK(cudaGetLastError());
+  return MPCQP_OK;
+}
 
 extern "C" int mpcqp_score_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t B, int32_t R, int32_t n_dynamic,
                                              const double* x, const double* prev_plan, const double* xref, const double* obs_c,

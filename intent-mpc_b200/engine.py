@@ -229,3 +229,16 @@ class Engine:
         self._check(self.lib.mpcqp_select_candidates_device(self.h, C.c_int32(S), C.c_int32(Cn), C.c_int32(n), g("cand"), g("weight"),
                                                             g("score"), g("x_all"), g("best"), g("weighted"), g("plan")))
 
+    def intent_candidates_ptr(self, params, S: int, D: int, NP: int, ptrs: dict):
+        """ptrs: device addresses for pred_pos, pred_size, prob, prev_plan (0 on the first step), pos, scen_a, scen_b, obs_c_a,
+        obs_semi_a, obs_c_b, obs_semi_b, weight, cand.  Asynchronous on the engine stream."""
+        p = params_to_c(params)
+        g = lambda k: C.c_void_p(ptrs.get(k) or None)
+        self._check(self.lib.mpcqp_intent_candidates_device(self.h, C.byref(p), C.c_int32(S), C.c_int32(D), C.c_int32(NP), g("pred_pos"),
+                                                            g("pred_size"), g("prob"), g("prev_plan"), g("pos"), g("scen_a"), g("scen_b"),
+                                                            g("obs_c_a"), g("obs_semi_a"), g("obs_c_b"), g("obs_semi_b"), g("weight"), g("cand")))
+
+    def gather_rows_ptr(self, B: int, width: int, idx_ptr: int, src_ptr: int, dst_ptr: int):
+        self._check(self.lib.mpcqp_gather_rows_device(self.h, C.c_int64(B), C.c_int32(width), C.c_void_p(idx_ptr), C.c_void_p(src_ptr),
+                                                      C.c_void_p(dst_ptr)))
+

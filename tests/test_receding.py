@@ -167,3 +167,58 @@ def test_receding_horizon_100_steps_warm_started():
         assert int(eng.solve_mpc_batch(cold)["iter"].sum()) > warm_it
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_device_candidate_enumeration_matches_host_logic():
+    """§8(f) row 1, first half: getIntentComb / findClosestObstacle (mpcPlanner.cpp:663-769) as device kernels
+    (mpcqp_intent_candidates_device + mpcqp_gather_rows_device) against the numpy restatement: same closest obstacle, same
+    sorted hypotheses, same rows in the two solve batches, same weights — on the first step and with a previous plan."""
+    import torch
+    from intent_mpc_b200 import engine
+    from intent_mpc_b200.receding import IntentSweep
+    eng = engine.Engine(0)
+    dev = torch.device("cuda", 0)
+    try:
+        sw = IntentSweep(300, seed0=321)
+        for step in range(3):
+            if step == 0:
+                sw.first = False                              # exercise the enumeration on the very first step too (no plan yet)
+            first = sw.states is None
+            batches, meta = sw.candidates()
+            p, S, D = sw.p, sw.S, sw.D
+            N, n = p.N, p.n
+            pp, ps = sw.last["pp"], sw.last["ps"]
+            d = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+            t_pp, t_ps, t_prob, t_pos = d(pp), d(ps), d(sw.prob), d(sw.pos)
+            t_plan = None if first else d(batches[0].warm_x[np.unique(meta[0][:, 0], return_index=True)[1]])
+            out = {"scen_a": torch.empty(4 * S, dtype=torch.int32, device=dev), "scen_b": torch.empty(2 * S, dtype=torch.int32, device=dev),
+                   "obs_c_a": torch.empty((4 * S, N, D, 3), dtype=torch.float64, device=dev), "obs_semi_a": torch.empty((4 * S, N, D, 3), dtype=torch.float64, device=dev),
+                   "obs_c_b": torch.empty((2 * S, N, D + 1, 3), dtype=torch.float64, device=dev), "obs_semi_b": torch.empty((2 * S, N, D + 1, 3), dtype=torch.float64, device=dev),
+                   "weight": torch.empty((S, 6), dtype=torch.float64, device=dev), "cand": torch.empty((S, 6), dtype=torch.int32, device=dev)}
+            ptrs = {k: v.data_ptr() for k, v in out.items()}
+            ptrs.update(pred_pos=t_pp.data_ptr(), pred_size=t_ps.data_ptr(), prob=t_prob.data_ptr(), pos=t_pos.data_ptr(),
+                        prev_plan=0 if first else t_plan.data_ptr())
+            eng.intent_candidates_ptr(p, S, D, pp.shape[3], ptrs)
+            # scenario-level arrays replicated per row of batch a
+            t_x0 = d(np.concatenate([sw.pos, sw.vel], axis=1)); g_x0 = torch.empty((4 * S, 6), dtype=torch.float64, device=dev)
+            eng.gather_rows_ptr(4 * S, 6, out["scen_a"].data_ptr(), t_x0.data_ptr(), g_x0.data_ptr())
+            eng.sync()
+            assert np.array_equal(out["scen_a"].cpu().numpy(), meta[0][:, 0]) and np.array_equal(out["scen_b"].cpu().numpy(), meta[1][:, 0])
+            assert np.array_equal(out["obs_c_a"].cpu().numpy(), batches[0].obs_c) and np.array_equal(out["obs_semi_a"].cpu().numpy(), batches[0].obs_semi)
+            assert np.array_equal(out["obs_c_b"].cpu().numpy(), batches[1].obs_c) and np.array_equal(out["obs_semi_b"].cpu().numpy(), batches[1].obs_semi)
+            assert np.array_equal(out["weight"].cpu().numpy(), sw.last["w"])
+            cand = np.zeros((S, 6), dtype=np.int32); off = 0
+            for mt in meta:
+                cand[mt[:, 0], mt[:, 1]] = off + np.arange(len(mt)); off += len(mt)
+            assert np.array_equal(out["cand"].cpu().numpy(), cand)
+            assert np.array_equal(g_x0.cpu().numpy(), batches[0].x0)
+            if step == 0:
+                sw.first = True
+                sw.step(eng.solve_mpc_batch)                 # the real first step (obstacle-free QPs), then continue with plans
+            else:
+                outs = [eng.solve_mpc_batch(mb) for mb in batches]
+                cand_x, status, iters, weighted, best = sw.select(batches, meta, outs)
+                sw.advance(cand_x, best)
+    finally:
+        eng.close()
