@@ -47,6 +47,8 @@ def parse():
                          "configs[2], 10,923 scenarios x 6 intent candidates per rank, --steps warm-started control steps")
     ap.add_argument("--instances", type=int, default=1000000, help="--workload sweep: total instances over all ranks")
     ap.add_argument("--chunk", type=int, default=32768, help="--workload sweep: instances per engine call")
+    ap.add_argument("--device-loop", action="store_true", help="--workload receding: enumeration, gather, scoring and choice on the device too "
+                                                                "(intent-mpc_b200/receding_device.py); e2e is then the wall clock of the whole control steps")
     return ap.parse_args()
 
 
@@ -444,6 +446,39 @@ def run_receding(args, rank, world, local_rank):
     eng = engine.Engine(local_rank)
     S = 10923
     rs = receding.IntentSweep(S=S, D=4, seed0=1000 * rank + 5)
+    if args.device_loop:
+        from intent_mpc_b200.receding_device import DeviceIntentSweep
+        ds = DeviceIntentSweep(eng, rs, device=local_rank)
+        ds.step(); ds.step()                            # first (obstacle-free) step and one warm-up step with candidates
+        ds.kernel_ms = 0.0
+        per_step = []; its = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m0 = ds.kernel_ms
+            ds.step()
+            per_step.append(ds.kernel_ms - m0); its += int(ds.buf["iter"].sum().item())
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev = torch.device("cuda", local_rank)
+        t = torch.tensor([ds.kernel_ms, wall_ms], dtype=torch.float64, device=dev)
+        agg = torch.tensor([float(6 * S * args.steps), float(its)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            line = {"metric": METRIC, "value": float(agg[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2,
+                    "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": f"configs[2], device-resident loop: {S} scenarios x 6 intent candidates = {6 * S} QPs per control step per GPU, {args.steps} "
+                                           "warm-started receding-horizon steps; enumeration, gather, solves, scoring and choice are engine calls on device arrays",
+                               "pins": "adaptive_rho_interval=25,time_limit=0", "iterations_total": int(agg[1]),
+                               "ms_per_step_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
+                               "progress_m_rank0": float(ds.pos[:, 0].mean().item())},
+                    "e2e": {"value": float(agg[0]) / (float(t[1]) * 1e-3), "unit": UNIT, "ms": float(t[1]), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                            "note": "wall clock of the whole control steps (predictions, enumeration, gather, two solves, scoring, choice, state update), nothing crosses PCIe"}}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     rs.step(eng.solve_mpc_batch)                        # first control step: obstacle-free QPs (mpcPlanner.cpp:598-602)
     ms = [0.0]; its = [0]; nq = [0]; wall = [0.0]; hist = {}
     def solve_(mb_):

@@ -222,3 +222,32 @@ def test_device_candidate_enumeration_matches_host_logic():
                 sw.advance(cand_x, best)
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_control_loop_tracks_the_host_loop():
+    """makePlanWithPred as a chain of engine calls with every array on the GPU (intent-mpc_b200/receding_device.py):
+    enumeration -> gather -> two solves -> scoring -> choice -> next state.  Run beside the host-logic loop from the same
+    initial scenarios: same chosen candidates and the same UAV states step after step (predictions are evaluated with torch
+    on one side and numpy on the other, so inputs agree to rounding, not bitwise)."""
+    from intent_mpc_b200 import engine
+    from intent_mpc_b200.receding import IntentSweep
+    from intent_mpc_b200.receding_device import DeviceIntentSweep
+    eng = engine.Engine(0)
+    try:
+        host = IntentSweep(256, seed0=4242)
+        devs = DeviceIntentSweep(eng, IntentSweep(256, seed0=4242))
+        for step in range(6):
+            r = host.step(eng.solve_mpc_batch)
+            best_d = devs.step()
+            pos_d = devs.pos.cpu().numpy()
+            close = np.abs(pos_d - host.pos).max(axis=1) < 1e-6
+            assert close.mean() >= 0.98, (step, close.mean())
+            if r["best"] is not None:
+                same = best_d.cpu().numpy() == r["best"]
+                assert same.mean() >= 0.98, (step, same.mean())
+                st_d = devs.buf["status"].cpu().numpy()
+                assert np.isin(st_d, [1, 2, -2]).all()
+        assert devs.kernel_ms > 0
+    finally:
+        eng.close()
