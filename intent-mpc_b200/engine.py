@@ -200,18 +200,24 @@ class Engine:
 
     # ---- batched entry point, raw pointers (device-resident or pinned host) ----------------------
     def solve_mpc_batch_ptr(self, params, settings: Settings, B: int, R: int, ptrs: dict, obs_dyn: np.ndarray,
-                            device: bool):
+                            device: bool, nobs: np.ndarray | None = None, limits: np.ndarray | None = None):
         """ptrs: name -> integer address for x0,xref,obs_c,obs_semi,obs_yaw,lin_pt,warm_x,x,y,status,iter,
         rho_updates,obj,pri_res,dua_res (0 / missing = NULL).  device=True: device pointers, asynchronous on the
         engine stream (call sync()); device=False: host pointers, synchronous."""
         p = params_to_c(params)
         od = np.ascontiguousarray(obs_dyn, dtype=np.int32)
         self._check(self.lib.mpcqp_engine_obs_dyn_per_instance(self.h, C.c_int(1 if od.ndim == 3 else 0)))
+        nobs = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)       # host arrays [B] / [B][2], see the header
+        limits = None if limits is None else np.ascontiguousarray(limits, dtype=np.float64)
+        self._check(self.lib.mpcqp_engine_num_obs_per_instance(self.h, _ip(nobs)))
+        self._check(self.lib.mpcqp_engine_limits_per_instance(self.h, _dp(limits)))
         g = lambda k: C.c_void_p(ptrs.get(k) or None)
         fn = self.lib.mpcqp_solve_mpc_batch_device if device else self.lib.mpcqp_solve_mpc_batch_host
         rc = fn(self.h, C.byref(p), C.byref(settings), C.c_int32(B), C.c_int32(R), g("x0"), g("xref"), g("obs_c"),
                 g("obs_semi"), g("obs_yaw"), _ip(od), g("lin_pt"), g("warm_x"), g("x"), g("y"), g("status"), g("iter"),
                 g("rho_updates"), g("obj"), g("pri_res"), g("dua_res"))
+        self.lib.mpcqp_engine_num_obs_per_instance(self.h, None)
+        self.lib.mpcqp_engine_limits_per_instance(self.h, None)
         self._check(rc)
 
     # ---- candidate scoring / selection on the device (getTrajectoryScore, evaluateTraj) --------------------------
