@@ -64,7 +64,7 @@ def _oracle():
     return OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
 
 
-@pytest.mark.parametrize("num_obs,B,seed0", [(4, 1024, 0), (0, 128, 5000), (16, 64, 7000), (1, 64, 9000)])
+@pytest.mark.parametrize("num_obs,B,seed0", [(4, 1024, 0), (0, 128, 5000), (16, 64, 7000), (1, 64, 9000), (32, 24, 11000), (40, 8, 13000)])
 def test_gpu_matches_oracle_on_seeded_batches(eng, num_obs, B, seed0):
     """configs[1] (B=1024, static obstacles only) at full size, plus an obstacle-count sweep."""
     mb = W.static_batch(B, num_obs=num_obs, seed0=seed0)
