@@ -2543,6 +2543,28 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     }
   }
 
+  // Setup only (scaling.h: scale_data, auxil.h: set_rho_vec, warm start) for instance b, by a CTA of a dedicated high-occupancy
+  // kernel: the cold block is built in shared memory (`smem0`: cold_slots(R) * NS doubles + 8 of reduction scratch) and left in
+  // slot `slot` exactly as a parked instance at iteration 0 with a factorisation pending, for run_cta_resume to pick up.
+  MQ_HD void run_setup_only(const Batch& bt, int b, int slot, int warp) {
+    x0p = bt.x0 + (size_t)b * 8;
+    if (bt.limits) { lim_v = bt.limits[2 * (size_t)b]; lim_a = bt.limits[2 * (size_t)b + 1]; has_lim = true; }
+    slack = bt.slack + (size_t)b * bt.slack_stride;
+    const Mem keep = m;
+    map_cold(m, smem0, NS, R);
+    m.YB = smem0 + cold_slots(R) * NS;
+    load_and_scale<4>(bt, b, warp);
+    double* dst = bt.susp_cold + (size_t)slot * bt.susp_stride;
+    for (int i = threadIdx.x; i < cold_slots(R) * NS; i += 128) dst[i] = smem0[i];
+    if (threadIdx.x == 0) {
+      double* sc = bt.susp_scal + (size_t)slot * 8;
+      sc[0] = c; sc[1] = cinv; sc[2] = rho; sc[3] = nq; sc[4] = nq_s; sc[5] = 0.0; sc[6] = 1.0; sc[7] = 0.0;
+      bt.susp_list[slot] = b;
+    }
+    m = keep;
+    cta_sync();
+  }
+
   // Resume the instance parked in `slot` by another launch (run_cta's suspend exit): same state, same arithmetic from here on.
   MQ_HD void run_cta_resume(const Batch& bt, int slot, int warp, volatile int* flag, volatile int* cmd = nullptr) {
     const int b = bt.susp_list[slot];

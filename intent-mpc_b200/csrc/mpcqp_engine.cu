@@ -119,6 +119,14 @@ static SolveKernel pick_kernel(int NS, int R, int want, int* mode, bool assist =
   *mode = kModeGeneric;
   return mpcqp_kernel_generic();
 }
+static SolveKernel pick_setup_kernel(int R) {
+  switch (R) {
+#define X(r) case r: return mpcqp_kernel_setup_##r();
+    MPCQP_FAST_R_LIST
+#undef X
+    default: return nullptr;
+  }
+}
 
 }  // namespace mpcqp
 
@@ -148,7 +156,7 @@ struct mpcqp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int migrate = 1, suspend_at = 300, hist_active = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int split_setup = 1; int migrate = 1, suspend_at = 300, hist_active = 0;
   const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
   DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_ctr, cand_tab;
@@ -196,6 +204,7 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
       cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreate(&e->evs) != cudaSuccess) { delete e; return MPCQP_ERR_CUDA; }
   // development knobs (scheduling only; results never depend on them)
   if (const char* v = getenv("MPCQP_LARGE_BATCH_FACTOR")) { const int f = atoi(v); if (f >= 0) e->large_batch_factor = f; }
+  if (const char* v = getenv("MPCQP_SPLIT_SETUP")) e->split_setup = atoi(v) != 0;
   if (const char* v = getenv("MPCQP_SUSPEND_AT")) { const int f = atoi(v); if (f >= 0) e->suspend_at = f; }
   *out = e;
   return MPCQP_OK;
@@ -365,15 +374,46 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       bt.susp_cold = e->susp_cold.as<double>(); bt.susp_scal = e->susp_scal.as<double>();
       bt.susp_list = e->susp_list.as<int>(); bt.susp_count = e->susp_ctr.as<int>();
     }
-    // measured crossovers (configs[1]-shaped batches): with a history the single launch wins from ~13 x 296 instances, without
-    // one (nothing known about the instances) the two launches + migration win up to ~40 x 296
-    const int lb_factor = e->large_batch_factor > 0 ? e->large_batch_factor : (e->hist_active ? 13 : 40);
+    // measured crossovers (configs[1]-shaped batches): with a history the single launch (setup split off into its own kernel)
+    // wins from ~13 x 296 instances, without one (nothing known about the instances) the two launches + migration win up to ~20 x 296
+    const int lb_factor = e->large_batch_factor > 0 ? e->large_batch_factor : (e->hist_active ? 13 : (e->split_setup ? 20 : 40));
     if (bt.B >= (long long)lb_factor * grid) {
       // (migration: the follow-up launch only starts when this one has drained, so it pays only where nothing is known
       // about the instances — no iteration history — and the batch is long enough to amortise the second launch)
       if (e->hist_active) bt.suspend_at = 0;
       // Large batch: every SM stays busy with two CTAs to the end anyway, and a one-per-SM launch would only halve the
       // occupancy of the SMs it takes.  One launch, two CTAs per SM, the hard list first.
+      SolveKernel kset = e->split_setup ? pick_setup_kernel(sh.R) : nullptr;
+      if (kset) {
+        // Setup (Ruiz scaling, rho vector, warm start) in its own kernel, three CTAs per SM with only the cold block in shared
+        // memory; it leaves every instance parked at iteration 0 and the solve launch resumes them all (hard list first).
+        const int stride = cold_slots(sh.R) * sh.NS;
+        const size_t smem_set = ((size_t)stride + 8) * sizeof(double);
+        CK(e->susp_cold.need((size_t)bt.B * stride * sizeof(double)));
+        CK(e->susp_scal.need((size_t)bt.B * 8 * sizeof(double)));
+        CK(e->susp_list.need((size_t)bt.B * sizeof(int)));
+        CK(e->susp_ctr.need(sizeof(int)));
+        CK(cudaMemsetAsync(e->susp_ctr.p, 0, sizeof(int), e->stream));
+        CK(cudaFuncSetAttribute(kset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_set));
+        int occ_s = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, kset, 128, smem_set));
+        if (occ_s < 1) { e->err = "setup kernel cannot be resident"; return MPCQP_ERR_CUDA; }
+        const long long gs = (long long)e->num_sms * occ_s;
+        CK(e->ws.need((size_t)(grid > gs ? grid : gs) * wsd * sizeof(double)));
+        bt.ws = e->ws.as<double>();
+        bt.suspend_at = 0; bt.susp_cap = bt.B; bt.susp_stride = stride;
+        bt.susp_cold = e->susp_cold.as<double>(); bt.susp_scal = e->susp_scal.as<double>();
+        bt.susp_list = e->susp_list.as<int>(); bt.susp_count = e->susp_ctr.as<int>();
+        bt.nhard = e->counter.as<int>() + 1;
+        CK(cudaEventRecord(e->evs, e->stream));
+        kset<<<(unsigned)gs, 128, smem_set, e->stream>>>(sh, st, bt, wsd, e->counter.as<int>());
+        CK(cudaGetLastError());
+        Batch br = bt; br.queue = 4;
+        kern<<<(unsigned)grid, threads, smem, e->stream>>>(sh, st, br, wsd, e->counter.as<int>());
+        CK(cudaGetLastError());
+        e->last_launches += 2;
+        return MPCQP_OK;
+      }
       CK(e->ws.need((size_t)grid * wsd * sizeof(double)));
       bt.ws = e->ws.as<double>();
       bt.queue = 3; bt.nhard = e->counter.as<int>() + 1;

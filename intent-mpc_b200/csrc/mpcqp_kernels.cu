@@ -9,7 +9,8 @@
 namespace mpcqp {
 #ifdef MPCQP_GROUP_R_LIST
 #define X(r) SolveKernel mpcqp_kernel_cta_##r(bool assist) { return assist ? mpcqp_solve_cta_kernel<r, true> : mpcqp_solve_cta_kernel<r, false>; } \
-             SolveKernel mpcqp_kernel_warp_##r() { return mpcqp_solve_kernel<30, r>; }
+             SolveKernel mpcqp_kernel_warp_##r() { return mpcqp_solve_kernel<30, r>; } \
+             SolveKernel mpcqp_kernel_setup_##r() { return mpcqp_setup_kernel<r>; }
 MPCQP_GROUP_R_LIST
 #undef X
 #endif

@@ -13,7 +13,7 @@ typedef void (*SolveKernel)(const Shape, const Settings, const Batch, int, int*)
 #define MPCQP_FAST_R_LIST X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #endif
 // getters defined by the translation units of mpcqp_kernels.cu
-#define X(r) SolveKernel mpcqp_kernel_cta_##r(bool assist); SolveKernel mpcqp_kernel_warp_##r();
+#define X(r) SolveKernel mpcqp_kernel_cta_##r(bool assist); SolveKernel mpcqp_kernel_warp_##r(); SolveKernel mpcqp_kernel_setup_##r();
 MPCQP_FAST_R_LIST
 #undef X
 SolveKernel mpcqp_kernel_cta_wide();
@@ -87,6 +87,37 @@ __global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solv
   }
 }
 
+// Setup kernel: persistent, one 4-warp CTA per instance at a time, three CTAs per SM (the cold block in shared memory is all it
+// needs); instances are taken hard list first, then the rest, and slot numbers are handed out in that order so that the solve
+// launch that follows (queue 4) starts the long ones first.  counter[0]: fetch, counter[3]: natural fetch, susp_count: slots.
+template <int RT>
+__global__ void __launch_bounds__(128, 3) mpcqp_setup_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+                                                             const __grid_constant__ Batch bt, int ws_stride, int* counter) {
+  extern __shared__ double smem[];
+  __shared__ int s_next, s_slot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Qp<30, RT, kModeCta, false> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  bool natural = bt.nhard == nullptr;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(counter + (natural ? 3 : 0), 1);
+    cta_sync();
+    const int idx = s_next;
+    cta_sync();
+    int b = idx;
+    if (natural) {
+      if (idx >= bt.B) break;
+      if (bt.nhard && bt.hard[idx]) continue;
+    } else {
+      if (idx >= *bt.nhard) { natural = true; continue; }
+      b = bt.order[idx];
+    }
+    if (threadIdx.x == 0) s_slot = atomicAdd(bt.susp_count, 1);
+    cta_sync();
+    const int slot = s_slot;
+    cta_sync();
+    qp.run_setup_only(bt, b, slot, warp);
+  }
+}
 #endif  // MPCQP_KERNEL_BODIES
 
 }  // namespace mpcqp
