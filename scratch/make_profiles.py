@@ -31,7 +31,7 @@ details_from_csv(open(g + "B1024_details.csv").read(), "profiles/r01_final_B1024
                  "# ncu --set full, scratch/prof_case.py 1024 4 (final code of round 1), third solve of the batch: launch 0 = hard queue (one CTA + 3 PCR assistant warps per SM, 224 threads), launch 1 = the other instances, two 128-thread CTAs per SM, launch 2 = instances migrated after 300 iterations (none left: history flags them)")
 v = raw_selected(open(g + "B1024_raw.csv").read(), "profiles/r01_final_B1024_R4_raw_selected.txt", "# selected raw metrics of the same capture")
 details_from_csv(open(g + "B16384_details.csv").read(), "profiles/r01_final_B16384_R4_details.txt",
-                 "# ncu --set full, scratch/prof_case.py 16384 4 (final code of round 1): the single two-CTAs-per-SM launch of a 16,384-QP batch, hard list first (throughput regime)")
+                 "# ncu --set full, scratch/prof_case.py 16384 4 (final code of round 1), second solve of the batch (history known): launch 0 = mpcqp_setup_kernel (three 128-thread CTAs per SM: Ruiz scaling, rho vector, warm start; leaves every instance parked at iteration 0), launch 1 = the solve launch, two CTAs per SM, resuming all 16,384 instances, hard list first")
 raw_selected(open(g + "B16384_raw.csv").read(), "profiles/r01_final_B16384_R4_raw_selected.txt", "# selected raw metrics of the same capture")
 details_from_csv(open(g + "sweep_details.csv").read(), "profiles/r01_final_sweep_wide_details.txt",
                  "# ncu --set full, scratch/prof_sweep.py (final code of round 1): wide CTA kernel (run-time obstacle count <= 32, rows in shared memory) on the (5 m/s, 20 m/s^2) slice of the first 4,096 sweep instances")
