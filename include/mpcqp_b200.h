@@ -84,7 +84,8 @@ double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e);
 int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
 /* Which solve kernel the last batch ran: 2 = CTA kernel (one 4-warp CTA per QP, parallel-cyclic-reduction solve,
  * horizon 30, num_obs <= 8), 1 = one-warp-per-QP register-resident kernel (same shapes), 0 = generic one-warp
- * shared-memory kernel (any horizon/num_obs that fits).  force_generic(1) pins the generic kernel, (2) the
+ * shared-memory kernel (any horizon/num_obs that fits), 4 = dense generic kernel for problems WITHOUT the mpcPlanner stage
+ * structure (mpcqp_setup / mpcqp_solve only; polyTrajSolver's minimum-snap QPs).  force_generic(1) pins the generic kernel, (2) the
  * one-warp register kernel, (3) the CTA kernel without its assistant warps (launches that give a CTA an SM to itself
  * normally carry three more warps that hold the PCR matrices of levels 1..3 in registers), (0) restores the default
  * dispatch (used by the tests to cover all of them). */
@@ -184,8 +185,11 @@ int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_t C, int32_
 /* ---- (3) OSQP-shaped single problem (explicit CSC) -------------------------------------------------- *
  * mpcqp_setup replaces osqp_setup (osqp.h:58): data is copied, the caller's arrays may die afterwards.
  * P is upper-triangular CSC (n x n), A is CSC (m x n), indices int64 like OSQP's c_int (glob_opts.h:80).
- * The problem must have the mpcPlanner stage structure (diagonal P; dynamics / box / obstacle row blocks as
- * mpcPlanner.cpp:989-1071 lays them out); anything else returns MPCQP_ERR_STRUCTURE. */
+ * A problem with the mpcPlanner stage structure (diagonal P; dynamics / box / obstacle row blocks as
+ * mpcPlanner.cpp:989-1071 lays them out) runs on the stage-structured kernels.  Anything else — the reference's second
+ * consumer of this boundary is polyTrajSolver (polyTrajSolver.cpp:14-37, 162-239, 848-900: block-diagonal minimum-snap
+ * Hessian, continuity equalities, corridor boxes) — runs on the dense generic kernel (csrc/mpcqp_dense.cuh, one CTA per
+ * QP, same OSQP iterate sequence) when n + m <= 4096, and returns MPCQP_ERR_STRUCTURE beyond that.  There is no CPU path. */
 int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int64_t m, const int64_t* P_colptr,
                 const int64_t* P_rowidx, const double* P_val, const double* q, const int64_t* A_colptr,
                 const int64_t* A_rowidx, const double* A_val, const double* l, const double* u,
@@ -202,6 +206,19 @@ typedef struct {                                                             /* 
 int mpcqp_get_info(const mpcqp_problem* pr, mpcqp_info* info);
 int mpcqp_get_solution(const mpcqp_problem* pr, double* x, double* y);       /* work->solution->x / ->y */
 int mpcqp_cleanup(mpcqp_problem* pr);                                        /* osqp_cleanup */
+
+/* ---- (3b) batch of unstructured QPs sharing one CSC pattern ------------------------------------------ *
+ * What polyTrajSolver does with three OsqpEigen::Solver objects (x, y, z: same P and A, own bounds;
+ * polyTrajSolver.cpp:162-239, solved one after the other at :848-900) as ONE launch of the dense generic kernel, one CTA
+ * per QP at a time; also the entry point for scoring many candidate paths at once.  Values are [B][nnz] / [B][n] / [B][m]
+ * row-major; warm_x, warm_y, y, iter, rho_updates, obj, pri_res, dua_res may be NULL.  Host arrays in and out; synchronous.
+ * Same validation and error codes as mpcqp_setup (n + m <= 4096, else MPCQP_ERR_STRUCTURE). */
+int mpcqp_solve_qp_batch_host(mpcqp_engine* e, const mpcqp_settings* s, int32_t B, int64_t n, int64_t m,
+                              const int64_t* P_colptr, const int64_t* P_rowidx, const double* P_val, const double* q,
+                              const int64_t* A_colptr, const int64_t* A_rowidx, const double* A_val, const double* l,
+                              const double* u, const double* warm_x, const double* warm_y, double* x, double* y,
+                              int32_t* status, int32_t* iter, int32_t* rho_updates, double* obj, double* pri_res,
+                              double* dua_res);
 
 #ifdef __cplusplus
 }

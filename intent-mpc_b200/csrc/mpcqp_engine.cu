@@ -17,6 +17,7 @@
 #include "../../include/mpcqp_b200.h"
 #include "mpcqp_core.cuh"
 #include "mpcqp_kernels.cuh"
+#include "mpcqp_dense.cuh"
 
 namespace mpcqp {
 
@@ -150,7 +151,13 @@ struct DevBuf {
   template <class T> T* as() const { return (T*)p; }
 };
 
+struct DenseDev {   // device buffers of one call of the generic (unstructured) path
+  DevBuf Pc, Pi, Px, Ac, Ai, Ax, q, l, u, wx, wy, x, y, ii, dd, ws;
+  void release() { DevBuf* b[] = { &Pc, &Pi, &Px, &Ac, &Ai, &Ax, &q, &l, &u, &wx, &wy, &x, &y, &ii, &dd, &ws }; for (DevBuf* v : b) v->release(); }
+};
+
 struct mpcqp_engine {
+  DenseDev dense;
   int device = 0, num_sms = 0, max_smem_optin = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;          // main stream; side stream for the second solve launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
@@ -216,6 +223,7 @@ extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
   DevBuf* bufs[] = { &e->pd, &e->slack, &e->q, &e->x0s, &e->g, &e->low, &e->ws, &e->counter, &e->hard, &e->order, &e->hist, &e->in_x0, &e->in_xref, &e->in_c,
                      &e->in_semi, &e->in_yaw, &e->in_lin, &e->in_warm, &e->out_x, &e->out_y, &e->out_i, &e->out_d };
   for (DevBuf* b : bufs) b->release();
+  e->dense.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs) cudaEventDestroy(e->evs);
@@ -903,7 +911,18 @@ struct mpcqp_problem {
   bool has_wx = false, has_wy = false, solved = false;
   mpcqp_info info;
   DevBuf d_pd, d_slack, d_q, d_x0, d_g, d_low, d_wx, d_wy, d_x, d_y, d_i, d_d;
+  // generic (unstructured) path, csrc/mpcqp_dense.cuh: dense copies of the user's P (mirrored), A, A' and the bounds
+  bool dense = false;
+  std::vector<int64_t> dPc, dPi, dAc, dAi;
+  std::vector<double> dPx, dAx, dl, du;
+  DenseDev dd;
 };
+
+namespace mpcqp_dense {
+int grid_size(int B, int n, int m, int device);
+int launch(const Batch& bt, int grid, const Settings& st, cudaStream_t stream);
+}
+static_assert(sizeof(mpcqp_dense::Settings) == sizeof(Settings), "the dense path reads mpcqp::Settings by layout");
 
 namespace {
 const double kBoundInf = 1e20;     // OSQP_INFTY is 1e30 (constants.h:78); IEEE inf is what the reference passes
@@ -999,6 +1018,78 @@ int parse_structure(int64_t n, int64_t m, const int64_t* Pp, const int64_t* Pi, 
 }
 }  // namespace
 
+namespace {
+// Generic path.  validate_data of osqp_setup: l <= u, P upper triangular, indices in range, monotone column pointers.
+int validate_csc(mpcqp_engine* e, int64_t n, int64_t m, const int64_t* Pc, const int64_t* Pi, const int64_t* Ac, const int64_t* Ai) {
+  if (n + m > 4096) { e->err = "unstructured problem with n + m > 4096: the dense generic kernel does not take it"; return MPCQP_ERR_STRUCTURE; }
+  if (Pc[0] != 0 || Ac[0] != 0) { e->err = "column pointers do not start at 0"; return MPCQP_ERR_DATA; }
+  for (int64_t j = 0; j < n; ++j) {
+    if (Pc[j + 1] < Pc[j] || Ac[j + 1] < Ac[j]) { e->err = "column pointers are not monotone"; return MPCQP_ERR_DATA; }
+    for (int64_t t = Pc[j]; t < Pc[j + 1]; ++t) if (Pi[t] < 0 || Pi[t] > j) { e->err = "P is not upper triangular (entry " + std::to_string(Pi[t]) + "," + std::to_string(j) + ")"; return MPCQP_ERR_DATA; }
+    for (int64_t t = Ac[j]; t < Ac[j + 1]; ++t) if (Ai[t] < 0 || Ai[t] >= m) { e->err = "A row index out of range in column " + std::to_string(j); return MPCQP_ERR_DATA; }
+  }
+  return MPCQP_OK;
+}
+
+// B QPs sharing one CSC pattern, host arrays in, host arrays out: upload (the CSC data and the vectors are all HBM ever
+// sees of the inputs), ONE launch of mpcqp_dense_solve_kernel (persistent, one CTA per QP at a time), download.
+int run_dense(mpcqp_engine* e, DenseDev& d, const Settings& st, int B, int n, int m, const int64_t* Pc, const int64_t* Pi, const double* Px,
+              const double* q, const int64_t* Ac, const int64_t* Ai, const double* Ax, const double* l, const double* u,
+              const double* wx, const double* wy, double* x, double* y, int32_t* info_i, double* info_d) {
+  const size_t one = sizeof(double), nnzP = (size_t)Pc[n], nnzA = (size_t)Ac[n], mm = (size_t)(m > 0 ? m : 1);
+  CK(cudaSetDevice(e->device));
+  const int grid = mpcqp_dense::grid_size(B, n, m, e->device);
+  if (grid < 1) { e->err = "generic path: the kernel does not fit this device (shared memory / registers)"; cudaGetLastError(); return MPCQP_ERR_CUDA; }
+  const size_t wsd = mpcqp_dense::ws_doubles(n, m);
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t r = b.need(bytes ? bytes : 8); if (r != cudaSuccess || !bytes) return r;
+    return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
+  };
+  CK(up(d.Pc, Pc, (size_t)(n + 1) * 8)); CK(up(d.Pi, Pi, nnzP * 8)); CK(up(d.Px, Px, (size_t)B * nnzP * one));
+  CK(up(d.Ac, Ac, (size_t)(n + 1) * 8)); CK(up(d.Ai, Ai, nnzA * 8)); CK(up(d.Ax, Ax, (size_t)B * nnzA * one));
+  CK(up(d.q, q, (size_t)B * n * one)); CK(up(d.l, l, (size_t)B * m * one)); CK(up(d.u, u, (size_t)B * m * one));
+  if (wx) CK(up(d.wx, wx, (size_t)B * n * one));
+  if (wy && m > 0) CK(up(d.wy, wy, (size_t)B * m * one));
+  CK(d.x.need((size_t)B * n * one)); CK(d.y.need((size_t)B * mm * one)); CK(d.ii.need((size_t)B * 3 * sizeof(int32_t))); CK(d.dd.need((size_t)B * 3 * one));
+  CK(d.ws.need((size_t)grid * wsd * one));
+  mpcqp_dense::Batch bt; memset(&bt, 0, sizeof bt);
+  bt.B = B; bt.n = n; bt.m = m; bt.nnzP = (long long)nnzP; bt.nnzA = (long long)nnzA;
+  bt.Pc = d.Pc.as<int64_t>(); bt.Pi = d.Pi.as<int64_t>(); bt.Ac = d.Ac.as<int64_t>(); bt.Ai = d.Ai.as<int64_t>();
+  bt.Px = d.Px.as<double>(); bt.Ax = d.Ax.as<double>(); bt.q = d.q.as<double>(); bt.l = d.l.as<double>(); bt.u = d.u.as<double>();
+  bt.warm_x = wx ? d.wx.as<double>() : nullptr; bt.warm_y = (wy && m > 0) ? d.wy.as<double>() : nullptr;
+  bt.ws = d.ws.as<double>(); bt.ws_stride = (long long)wsd;
+  bt.x = d.x.as<double>(); bt.y = (y && m > 0) ? d.y.as<double>() : nullptr; bt.info_i = d.ii.as<int32_t>(); bt.info_d = d.dd.as<double>();
+  mpcqp_dense::Settings ds; memcpy(&ds, &st, sizeof ds);
+  e->last_launches = 0;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  CK(cudaEventRecord(e->evs, e->stream));
+  const int rc = mpcqp_dense::launch(bt, grid, ds, e->stream);
+  if (rc) { e->err = std::string("mpcqp_dense_solve_kernel: ") + cudaGetErrorString((cudaError_t)rc); return MPCQP_ERR_CUDA; }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  e->last_launches = 1; e->last_fast = 4;
+  CK(cudaMemcpyAsync(x, d.x.p, (size_t)B * n * one, cudaMemcpyDeviceToHost, e->stream));
+  if (y && m > 0) CK(cudaMemcpyAsync(y, d.y.p, (size_t)B * m * one, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(info_i, d.ii.p, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(info_d, d.dd.p, (size_t)B * 3 * one, cudaMemcpyDeviceToHost, e->stream));
+  return mpcqp_engine_sync(e);
+}
+
+int setup_dense(mpcqp_engine* e, mpcqp_problem* pr, int64_t n, int64_t m, const int64_t* Pc, const int64_t* Pi, const double* Px,
+                const double* q, const int64_t* Ac, const int64_t* Ai, const double* Ax, const double* l, const double* u) {
+  int rc = validate_csc(e, n, m, Pc, Pi, Ac, Ai); if (rc) return rc;
+  for (int64_t i = 0; i < m; ++i) if (l[i] > u[i]) { e->err = "lower bound > upper bound at row " + std::to_string(i); return MPCQP_ERR_DATA; }
+  pr->dense = true;
+  pr->sh = Shape(); pr->sh.n = (int)n; pr->sh.m = (int)m;
+  pr->dPc.assign(Pc, Pc + n + 1); pr->dPi.assign(Pi, Pi + Pc[n]); pr->dPx.assign(Px, Px + Pc[n]);
+  pr->dAc.assign(Ac, Ac + n + 1); pr->dAi.assign(Ai, Ai + Ac[n]); pr->dAx.assign(Ax, Ax + Ac[n]);
+  pr->q.assign(q, q + n); pr->dl.assign(l, l + m); pr->du.assign(u, u + m);
+  pr->sol_x.assign((size_t)n, 0.0); pr->sol_y.assign((size_t)(m > 0 ? m : 1), 0.0);
+  memset(&pr->info, 0, sizeof pr->info);
+  pr->info.status_val = MPCQP_UNSOLVED;
+  return MPCQP_OK;
+}
+}  // namespace
+
 extern "C" int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int64_t m, const int64_t* P_colptr,
                            const int64_t* P_rowidx, const double* P_val, const double* q, const int64_t* A_colptr,
                            const int64_t* A_rowidx, const double* A_val, const double* l, const double* u,
@@ -1014,6 +1105,13 @@ extern "C" int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int6
   if (rc) { delete pr; return rc; }
   pr->user = *s;
   rc = parse_structure(n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, A_val, &pr->sh, &pr->pd, &pr->slack, &pr->g, &e->err);
+  if (rc == MPCQP_ERR_STRUCTURE) {            // not an mpcPlanner QP (e.g. polyTrajSolver.cpp:162-222): generic kernel
+    rc = setup_dense(e, pr, n, m, P_colptr, P_rowidx, P_val, q, A_colptr, A_rowidx, A_val, l, u);
+    if (rc) { mpcqp_cleanup(pr); return rc; }
+    pr->info.setup_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *out = pr;
+    return MPCQP_OK;
+  }
   if (rc) { delete pr; return rc; }
   const int NS = pr->sh.NS, N = NS - 1, R = pr->sh.R;
   pr->x0.assign(8, 0.0); pr->low.assign((size_t)N * (R > 0 ? R : 1), 0.0);
@@ -1066,6 +1164,7 @@ extern "C" int mpcqp_update_lin_cost(mpcqp_problem* pr, const double* q_new) {
   mpcqp_engine* e = pr->e;
   if (!q_new) { e->err = "null q"; return MPCQP_ERR_ARG; }
   pr->q.assign(q_new, q_new + pr->sh.n);
+  if (pr->dense) return MPCQP_OK;              // uploaded by the next solve
   CK(cudaSetDevice(e->device));
   CK(cudaMemcpyAsync(pr->d_q.p, pr->q.data(), pr->q.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1076,6 +1175,11 @@ extern "C" int mpcqp_update_bounds(mpcqp_problem* pr, const double* l_new, const
   if (!pr) return MPCQP_ERR_NOT_INIT;
   mpcqp_engine* e = pr->e;
   if (!l_new || !u_new) { e->err = "null bounds"; return MPCQP_ERR_ARG; }
+  if (pr->dense) {
+    for (int i = 0; i < pr->sh.m; ++i) if (l_new[i] > u_new[i]) { e->err = "lower bound > upper bound at row " + std::to_string(i); return MPCQP_ERR_DATA; }
+    pr->dl.assign(l_new, l_new + pr->sh.m); pr->du.assign(u_new, u_new + pr->sh.m);
+    return MPCQP_OK;
+  }
   Shape sh = pr->sh; std::vector<double> x0(8), low(pr->low.size());
   int rc = parse_bounds(sh, l_new, u_new, x0.data(), sh.blo, sh.bhi, low.data(), &e->err);
   if (rc) return rc;
@@ -1099,6 +1203,17 @@ extern "C" int mpcqp_solve(mpcqp_problem* pr) {
   const double* wx = nullptr; const double* wy = nullptr;
   if (ws && pr->has_wx) wx = pr->warm_x.data(); else if (ws && pr->solved) wx = pr->sol_x.data();
   if (ws && pr->has_wy) wy = pr->warm_y.data(); else if (ws && pr->solved && !pr->has_wx) wy = pr->sol_y.data();
+  if (pr->dense) {
+    int32_t hi[3]; double hd[3];
+    int rc = run_dense(e, pr->dd, pr->st, 1, n, m, pr->dPc.data(), pr->dPi.data(), pr->dPx.data(), pr->q.data(), pr->dAc.data(), pr->dAi.data(),
+                       pr->dAx.data(), pr->dl.data(), pr->du.data(), wx, wy, pr->sol_x.data(), pr->sol_y.data(), hi, hd);
+    if (rc) return rc;
+    pr->info.status_val = hi[0]; pr->info.iter = hi[1]; pr->info.rho_updates = hi[2];
+    pr->info.obj_val = hd[0]; pr->info.pri_res = hd[1]; pr->info.dua_res = hd[2];
+    pr->info.solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    pr->solved = true; pr->has_wx = pr->has_wy = false;
+    return MPCQP_OK;
+  }
   if (wx) { CK(pr->d_wx.need((size_t)n * sizeof(double))); CK(cudaMemcpyAsync(pr->d_wx.p, wx, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream)); }
   if (wy && m > 0) { CK(pr->d_wy.need((size_t)m * sizeof(double))); CK(cudaMemcpyAsync(pr->d_wy.p, wy, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, e->stream)); }
   Batch bt; memset(&bt, 0, sizeof bt);
@@ -1140,11 +1255,34 @@ extern "C" int mpcqp_get_solution(const mpcqp_problem* pr, double* x, double* y)
   return MPCQP_OK;
 }
 
+// B unstructured QPs sharing one CSC pattern in one launch (include/mpcqp_b200.h section 3b).
+extern "C" int mpcqp_solve_qp_batch_host(mpcqp_engine* e, const mpcqp_settings* s, int32_t B, int64_t n, int64_t m,
+                                         const int64_t* P_colptr, const int64_t* P_rowidx, const double* P_val, const double* q,
+                                         const int64_t* A_colptr, const int64_t* A_rowidx, const double* A_val, const double* l,
+                                         const double* u, const double* warm_x, const double* warm_y, double* x, double* y,
+                                         int32_t* status, int32_t* iter, int32_t* rho_updates, double* obj, double* pri_res, double* dua_res) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (B <= 0 || n <= 0 || m < 0 || !P_colptr || !q || !A_colptr || !x || !status || (m > 0 && (!l || !u))) { e->err = "null array or non-positive size"; return MPCQP_ERR_DATA; }
+  Settings st;
+  int rc = check_settings(e, s, &st); if (rc) return rc;
+  rc = validate_csc(e, n, m, P_colptr, P_rowidx, A_colptr, A_rowidx); if (rc) return rc;
+  for (int64_t i = 0; i < (int64_t)B * m; ++i) if (l[i] > u[i]) { e->err = "lower bound > upper bound at row " + std::to_string(i % m) + " of problem " + std::to_string(i / m); return MPCQP_ERR_DATA; }
+  std::vector<int32_t> ii((size_t)B * 3); std::vector<double> dd((size_t)B * 3);
+  rc = run_dense(e, e->dense, st, B, (int)n, (int)m, P_colptr, P_rowidx, P_val, q, A_colptr, A_rowidx, A_val, l, u, warm_x, warm_y, x, y, ii.data(), dd.data());
+  if (rc) return rc;
+  for (int b = 0; b < B; ++b) {
+    status[b] = ii[3 * b]; if (iter) iter[b] = ii[3 * b + 1]; if (rho_updates) rho_updates[b] = ii[3 * b + 2];
+    if (obj) obj[b] = dd[3 * b]; if (pri_res) pri_res[b] = dd[3 * b + 1]; if (dua_res) dua_res[b] = dd[3 * b + 2];
+  }
+  return MPCQP_OK;
+}
+
 extern "C" int mpcqp_cleanup(mpcqp_problem* pr) {
   if (!pr) return MPCQP_ERR_NOT_INIT;
   cudaSetDevice(pr->e->device);
   DevBuf* bufs[] = { &pr->d_pd, &pr->d_slack, &pr->d_q, &pr->d_x0, &pr->d_g, &pr->d_low, &pr->d_wx, &pr->d_wy, &pr->d_x, &pr->d_y, &pr->d_i, &pr->d_d };
   for (DevBuf* b : bufs) b->release();
+  pr->dd.release();
   delete pr;
   return MPCQP_OK;
 }

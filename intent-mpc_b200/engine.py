@@ -136,9 +136,9 @@ class Engine:
 
     @property
     def last_path(self) -> str:
-        """'cta' (4-warp CTA per QP, PCR solve), 'fast' (one warp per QP, register-resident) or 'generic'
-        (one warp per QP, shared-memory kernel for any shape)."""
-        return {2: "cta", 1: "fast"}.get(int(self.lib.mpcqp_engine_last_path(self.h)), "generic")
+        """'cta' (4-warp CTA per QP, PCR solve), 'fast' (one warp per QP, register-resident), 'generic'
+        (one warp per QP, shared-memory kernel for any stage-structured shape) or 'dense' (unstructured QP, one CTA)."""
+        return {2: "cta", 1: "fast", 4: "dense"}.get(int(self.lib.mpcqp_engine_last_path(self.h)), "generic")
 
     def force_generic(self, on=True):
         """True / 1 / 'generic': generic kernel; 2 / 'fast': one-warp register kernel; 3 / 'cta_plain': CTA kernel without
@@ -248,3 +248,80 @@ class Engine:
         self._check(self.lib.mpcqp_gather_rows_device(self.h, C.c_int64(B), C.c_int32(width), C.c_void_p(idx_ptr), C.c_void_p(src_ptr),
                                                       C.c_void_p(dst_ptr)))
 
+
+
+def solve_qp_batch(eng: Engine, qb, warm_y=None, settings: Settings | None = None, want_y: bool = True) -> dict:
+    """mpcqp_solve_qp_batch_host: B unstructured QPs sharing one CSC pattern (attributes of `qb`: n, m, P_colptr, P_rowidx,
+    P_val [B, nnzP], q [B, n], A_colptr, A_rowidx, A_val [B, nnzA], l, u [B, m], warm_x [B, n] or None) in one launch of the
+    dense generic kernel — polyTrajSolver's x / y / z problems, or a set of candidate paths."""
+    s = settings if settings is not None else default_settings()
+    B, n, m = int(qb.q.shape[0]), int(qb.n), int(qb.m)
+    I = C.POINTER(C.c_int64)
+    pat = [np.ascontiguousarray(v, dtype=np.int64) for v in (qb.P_colptr, qb.P_rowidx, qb.A_colptr, qb.A_rowidx)]
+    d = [np.ascontiguousarray(v, dtype=np.float64) for v in (qb.P_val, qb.q, qb.A_val, qb.l, qb.u)]
+    wx = None if getattr(qb, "warm_x", None) is None else np.ascontiguousarray(qb.warm_x, dtype=np.float64)
+    wy = None if warm_y is None else np.ascontiguousarray(warm_y, dtype=np.float64)
+    out = dict(x=np.zeros((B, n)), y=np.zeros((B, m)) if want_y else None, status=np.zeros(B, np.int32),
+               iter=np.zeros(B, np.int32), rho_updates=np.zeros(B, np.int32), obj=np.zeros(B), pri_res=np.zeros(B),
+               dua_res=np.zeros(B))
+    eng._check(eng.lib.mpcqp_solve_qp_batch_host(
+        eng.h, C.byref(s), C.c_int32(B), C.c_int64(n), C.c_int64(m), pat[0].ctypes.data_as(I), pat[1].ctypes.data_as(I),
+        _dp(d[0]), _dp(d[1]), pat[2].ctypes.data_as(I), pat[3].ctypes.data_as(I), _dp(d[2]), _dp(d[3]), _dp(d[4]),
+        _dp(wx), _dp(wy), _dp(out["x"]), _dp(out["y"]), _ip(out["status"]), _ip(out["iter"]), _ip(out["rho_updates"]),
+        _dp(out["obj"]), _dp(out["pri_res"]), _dp(out["dua_res"])))
+    return out
+
+
+class Problem:
+    """OSQP-shaped single problem (mpcqp_setup ... mpcqp_cleanup, include/mpcqp_b200.h section 3): what
+    `OsqpEigen::Solver` drives for one QP.  mpcPlanner-structured problems run on the stage kernels, anything else
+    (polyTrajSolver.cpp:162-239) on the dense generic kernel; `engine.last_path` tells which."""
+
+    def __init__(self, eng: Engine, n, m, P_colptr, P_rowidx, P_val, q, A_colptr, A_rowidx, A_val, l, u,
+                 settings: Settings | None = None):
+        self.eng, self.lib, self.n, self.m = eng, eng.lib, int(n), int(m)
+        self.h = C.c_void_p()
+        s = settings if settings is not None else default_settings()
+        I = C.POINTER(C.c_int64)
+        a = [np.ascontiguousarray(v, dtype=np.int64) for v in (P_colptr, P_rowidx, A_colptr, A_rowidx)]
+        d = [np.ascontiguousarray(v, dtype=np.float64) for v in (P_val, q, A_val, l, u)]
+        rc = self.lib.mpcqp_setup(eng.h, C.byref(self.h), C.c_int64(self.n), C.c_int64(self.m), a[0].ctypes.data_as(I),
+                                  a[1].ctypes.data_as(I), _dp(d[0]), _dp(d[1]), a[2].ctypes.data_as(I),
+                                  a[3].ctypes.data_as(I), _dp(d[2]), _dp(d[3]), _dp(d[4]), C.byref(s))
+        if rc != 0:
+            self.h = None
+        eng._check(rc)
+
+    def warm_start(self, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if y is None:
+            self.eng._check(self.lib.mpcqp_warm_start_x(self.h, _dp(x)))
+        else:
+            self.eng._check(self.lib.mpcqp_warm_start(self.h, _dp(x), _dp(np.ascontiguousarray(y, dtype=np.float64))))
+
+    def update_bounds(self, l, u):
+        self.eng._check(self.lib.mpcqp_update_bounds(self.h, _dp(np.ascontiguousarray(l, dtype=np.float64)),
+                                                     _dp(np.ascontiguousarray(u, dtype=np.float64))))
+
+    def update_lin_cost(self, q):
+        self.eng._check(self.lib.mpcqp_update_lin_cost(self.h, _dp(np.ascontiguousarray(q, dtype=np.float64))))
+
+    def solve(self) -> dict:
+        self.eng._check(self.lib.mpcqp_solve(self.h))
+        info = Info()
+        self.eng._check(self.lib.mpcqp_get_info(self.h, C.byref(info)))
+        x = np.zeros(self.n); y = np.zeros(max(self.m, 1))
+        self.eng._check(self.lib.mpcqp_get_solution(self.h, _dp(x), _dp(y)))
+        return dict(x=x, y=y[:self.m], status=int(info.status_val), iter=int(info.iter), rho_updates=int(info.rho_updates),
+                    obj=info.obj_val, pri_res=info.pri_res, dua_res=info.dua_res, solve_time=info.solve_time)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpcqp_cleanup(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -12,8 +12,10 @@
 //
 // Class and method names, argument meaning, return conventions (bool / ErrorExitFlag / Status) follow
 // third_party/OsqpEigen/{Solver,Data,Settings,Constants}.hpp.  Differences, all forced by the engine:
-//   * every solve runs on the GPU; there is no CPU path.  A problem that does not have the mpcPlanner stage structure
-//     makes initSolver() return false (mpcqp_setup -> MPCQP_ERR_STRUCTURE);
+//   * every solve runs on the GPU; there is no CPU path.  A problem with the mpcPlanner stage structure runs on the
+//     stage-structured kernels, any other (polyTrajSolver.cpp:162-239: setUpProblem / updateProblem with updateBounds)
+//     on the dense generic kernel; only an unstructured problem with n + m > 4096 makes initSolver() return false
+//     (mpcqp_setup -> MPCQP_ERR_STRUCTURE);
 //   * adaptive_rho_interval defaults to 25 and time_limit to 0 (the two determinism pins); setting a time
 //     limit is accepted and ignored with a message on debugStream(), as mpcPlanner sets one (mpcPlanner.cpp:442-444);
 //   * q, l, u are copied when set (the reference keeps pointers until initSolver, Data.hpp:92-122).

@@ -4,6 +4,7 @@
 //   host_test planner <steps> <out.bin>        mpc_node-style receding-horizon loop (mpc_node.cpp:209-236) through the
 //                                              mpcPlanner mirror; dumps the last control step's batch for an oracle check
 //   host_test nogpu                            the facade and the planner must fail loudly without a CUDA device
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,15 +66,19 @@ static int run_facade(const char* in, const char* out) {
   fclose(g);
   solver.clearSolver();
   if (solver.isInitialized()) return 10;
-  // an unstructured problem is refused, not solved on the CPU
+  // an unstructured problem (polyTrajSolver-style use of the facade) runs on the dense generic kernel
   OsqpEigen::Solver bad;
   bad.data()->setNumberOfVariables(2); bad.data()->setNumberOfConstraints(1);
   OsqpEigen::SparseMatrix P2(2, 2), A2(1, 2);
   P2.setFromTriplets({0, 1}, {0, 1}, {1.0, 1.0}); A2.setFromTriplets({0, 0}, {0, 1}, {1.0, 1.0});
   OsqpEigen::Vector q2(2), l2(1), u2(1); q2[0] = q2[1] = 1.0; l2[0] = 0.0; u2[0] = 1.0;
   bad.data()->setHessianMatrix(P2); bad.data()->setGradient(q2); bad.data()->setLinearConstraintsMatrix(A2); bad.data()->setLowerBound(l2); bad.data()->setUpperBound(u2);
-  if (bad.initSolver()) return 11;
-  if (bad.lastEngineError() != MPCQP_ERR_STRUCTURE) return 12;
+  // min 1/2 (a^2 + b^2) + a + b  s.t. 0 <= a + b <= 1  ->  a = b = 0 (the unconstrained minimum (-1,-1) is cut off)
+  if (!bad.initSolver()) return 11;
+  if (bad.solveProblem() != OsqpEigen::ErrorExitFlag::NoError) return 12;
+  if (bad.getStatus() != OsqpEigen::Status::Solved) return 13;
+  const OsqpEigen::Vector& xb = bad.getSolution();
+  if (fabs(xb[0]) > 5e-3 || fabs(xb[1]) > 5e-3) return 14;
   return 0;
 }
 

@@ -10,7 +10,8 @@ from oracle import mpc_assembly as MA
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libemul.so")
-SRC = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_core.cuh")]
+SRC = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_core.cuh"),
+       os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_dense.cuh")]
 
 DEFAULT_D = dict(rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4, eps_dual_inf=1e-4,
                  adaptive_rho_tolerance=5.0)
@@ -73,4 +74,33 @@ def solve(mb, want_y=True, linsys=0, **settings):
                          out["rho_updates"].ctypes.data_as(I), dp(out["obj"]), dp(out["pri_res"]), dp(out["dua_res"]))
     if rc != 0:
         raise RuntimeError(f"emul_solve_batch(linsys={linsys}) -> {rc}")
+    return out
+
+
+def solve_dense(qb, warm_y=None, **settings):
+    """The generic-path kernel source (mpcqp_dense.cuh) on the host, one QpBatch problem at a time."""
+    build()
+    lib = C.CDLL(SO)
+    sd = dict(DEFAULT_D); si = dict(DEFAULT_I)
+    for k, v in settings.items():
+        (sd if k in sd else si)[k] = v
+    sdv = np.array([sd[k] for k in DEFAULT_D], dtype=np.float64)
+    siv = np.array([si[k] for k in DEFAULT_I], dtype=np.int32)
+    B, n, m = qb.q.shape[0], qb.n, qb.m
+    out = dict(x=np.zeros((B, n)), y=np.zeros((B, m)), status=np.zeros(B, np.int32), iter=np.zeros(B, np.int32),
+               rho_updates=np.zeros(B, np.int32), obj=np.zeros(B), pri_res=np.zeros(B), dua_res=np.zeros(B))
+    D = C.POINTER(C.c_double); I = C.POINTER(C.c_int); LL = C.POINTER(C.c_longlong)
+    def dp(a): return a.ctypes.data_as(D) if a is not None else None
+    pat = [np.ascontiguousarray(v, dtype=np.int64) for v in (qb.P_colptr, qb.P_rowidx, qb.A_colptr, qb.A_rowidx)]
+    for b in range(B):
+        ii = np.zeros(3, np.int32); dd = np.zeros(3)
+        wx = np.ascontiguousarray(qb.warm_x[b]) if qb.warm_x is not None else None
+        wy = np.ascontiguousarray(warm_y[b]) if warm_y is not None else None
+        lib.emul_dense_solve(C.c_int(n), C.c_int(m), pat[0].ctypes.data_as(LL), pat[1].ctypes.data_as(LL),
+                             dp(np.ascontiguousarray(qb.P_val[b])), pat[2].ctypes.data_as(LL), pat[3].ctypes.data_as(LL),
+                             dp(np.ascontiguousarray(qb.A_val[b])), dp(np.ascontiguousarray(qb.q[b])),
+                             dp(np.ascontiguousarray(qb.l[b])), dp(np.ascontiguousarray(qb.u[b])), dp(wx), dp(wy), dp(sdv),
+                             siv.ctypes.data_as(I), dp(out["x"][b]), dp(out["y"][b]), ii.ctypes.data_as(I), dp(dd))
+        out["status"][b], out["iter"][b], out["rho_updates"][b] = ii
+        out["obj"][b], out["pri_res"][b], out["dua_res"][b] = dd
     return out

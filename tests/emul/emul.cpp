@@ -42,3 +42,29 @@ extern "C" int emul_solve_batch(int linsys, int NS, int R, int B, double a_pv, d
     default: return -2;
   }
 }
+
+// ---- generic (unstructured) path: intent-mpc_b200/csrc/mpcqp_dense.cuh with one "thread" -------------------------------
+#include "../../intent-mpc_b200/csrc/mpcqp_dense.cuh"
+
+extern "C" int emul_dense_solve(int n, int m, const long long* Pc, const long long* Pi, const double* Px, const long long* Ac,
+                                const long long* Ai, const double* Ax, const double* q, const double* l,
+                                const double* u, const double* warm_x, const double* warm_y, const double* settings_d,
+                                const int* settings_i, double* x, double* y, int* info_i, double* info_d) {
+  namespace dq = mpcqp_dense;
+  dq::Settings st;
+  st.rho = settings_d[0]; st.sigma = settings_d[1]; st.alpha = settings_d[2]; st.eps_abs = settings_d[3];
+  st.eps_rel = settings_d[4]; st.eps_prim_inf = settings_d[5]; st.eps_dual_inf = settings_d[6];
+  st.adaptive_rho_tolerance = settings_d[7];
+  st.max_iter = settings_i[0]; st.scaling = settings_i[1]; st.adaptive_rho = settings_i[2];
+  st.adaptive_rho_interval = settings_i[3]; st.check_termination = settings_i[4]; st.warm_start = settings_i[5];
+  std::vector<double> ws(dq::ws_doubles(n, m)), sm(dq::smem_doubles(n, m));
+  int32_t ii[3];
+  dq::Problem pb;
+  pb.n = n; pb.m = m; pb.Pc = (const int64_t*)Pc; pb.Pi = (const int64_t*)Pi; pb.Px = Px; pb.Ac = (const int64_t*)Ac; pb.Ai = (const int64_t*)Ai; pb.Ax = Ax;
+  pb.q0 = q; pb.l0 = l; pb.u0 = u;
+  pb.warm_x = warm_x; pb.warm_y = warm_y; pb.ws = ws.data(); pb.x = x; pb.y = y; pb.info_i = ii; pb.info_d = info_d;
+  dq::Solver sv;
+  sv.run(pb, st, sm.data(), 0, 1);
+  info_i[0] = ii[0]; info_i[1] = ii[1]; info_i[2] = ii[2];
+  return 0;
+}
