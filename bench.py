@@ -41,10 +41,12 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
     ap.add_argument("--num-obs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="static", choices=["static", "sweep", "receding"],
+    ap.add_argument("--workload", default="static", choices=["static", "sweep", "receding", "polytraj"],
                     help="static: configs[1], the bench line the driver reads (default).  sweep: configs[4], --instances Monte-Carlo "
                          "instances sharded by index over the ranks (strong scaling), one JSON line of the same shape.  receding: "
                          "configs[2], 10,923 scenarios x 6 intent candidates per rank, --steps warm-started control steps")
+    ap.add_argument("--paths", type=int, default=1000, help="--workload polytraj: candidate paths per step (3 QPs each: x, y, z)")
+    ap.add_argument("--segments", type=int, default=8, help="--workload polytraj: path segments K (n = 8K coefficients per axis)")
     ap.add_argument("--instances", type=int, default=1000000, help="--workload sweep: total instances over all ranks")
     ap.add_argument("--chunk", type=int, default=32768, help="--workload sweep: instances per engine call")
     ap.add_argument("--device-loop", action="store_true", help="--workload receding: enumeration, gather, scoring and choice on the device too "
@@ -526,11 +528,63 @@ def run_receding(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_polytraj(args, rank, world, local_rank):
+    """SURVEY.md section 8(f) row 3 — the boundary's second consumer: `--paths` candidate paths of `--segments` segments, i.e.
+    3 x paths minimum-snap QPs of polyTrajSolver's shape (oracle/polytraj_assembly.py), through the batched generic entry
+    point (mpcqp_solve_qp_batch_host: host buffers in and out, one launch of the dense kernel).  Not the driver's bench line.
+    `value`: kernel time (CUDA events of the engine, inputs resident); `e2e`: wall clock of the host call.  One GPU."""
+    from oracle import polytraj_assembly as PA
+    qb = PA.path_batch(args.paths, K=args.segments, seed0=100)
+    B = int(qb.q.shape[0])
+    work = f"polyTrajSolver QPs: {args.paths} paths x 3 axes, K={args.segments} segments, n={qb.n}, m={qb.m} (minimum snap, degree 7, C4 continuity)"
+    if args.impl == "reference":
+        from oracle import bindings as OB
+        orc = OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
+        cores = os.cpu_count() or 1
+        for _ in range(args.warmup):
+            orc.solve_batch(qb, want_y=False, nthreads=cores)
+        ts = [orc.solve_batch(qb, want_y=False, nthreads=cores)["wall"] for _ in range(args.steps)]
+        ms = 1e3 * float(np.mean(ts))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": work, "pins": "adaptive_rho_interval=25,time_limit=0"},
+                          "cpu_baseline": {"value": B / (ms * 1e-3), "unit": UNIT, "cores": cores, "kind": orc.kind, "sample": "the whole batch per step, one QP per thread, setup on the clock"}}), flush=True)
+        return
+    from intent_mpc_b200 import engine
+    eng = engine.Engine(local_rank)
+    for _ in range(max(args.warmup, 1)):
+        r = engine.solve_qp_batch(eng, qb, want_y=False)
+    kms = []; wms = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); r = engine.solve_qp_batch(eng, qb, want_y=False); wms.append(1e3 * (time.perf_counter() - t0)); kms.append(eng.last_kernel_ms)
+    line = {"metric": METRIC, "value": B / (np.mean(kms) * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(kms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": work, "pins": "adaptive_rho_interval=25,time_limit=0", "kernel_path": eng.last_path,
+                       "iterations_total": int(r["iter"].sum()), "iterations_max": int(r["iter"].max()), "status_hist": _hist(r["status"])},
+            "e2e": {"value": B / (np.mean(wms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(wms)),
+                    "note": "pageable host arrays through mpcqp_solve_qp_batch_host, host<->device copies inside"},
+            "gpu_launches": int(eng.last_launches) * args.steps}
+    if not args.no_cpu_baseline:
+        from oracle import bindings as OB
+        orc = OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
+        cores = os.cpu_count() or 1
+        orc.solve_batch(qb, want_y=False, nthreads=cores)
+        c = orc.solve_batch(qb, want_y=False, nthreads=cores)
+        d = np.abs(c["x"]).max(axis=1)
+        line["cpu_baseline"] = {"value": B / c["wall"], "unit": UNIT, "cores": cores, "kind": orc.kind, "sample": "the same batch once, one QP per thread"}
+        line["parity"] = {"checked": B, "status_equal": bool((r["status"] == c["status"]).all()), "iter_equal": bool((r["iter"] == c["iter"]).all()),
+                          "x_rel_err_max": float((np.abs(r["x"] - c["x"]).max(axis=1) / d).max())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "polytraj":
+        if rank == 0:
+            run_polytraj(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload == "sweep":
         run_sweep(args, rank, world, local_rank)

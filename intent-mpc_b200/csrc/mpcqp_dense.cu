@@ -6,7 +6,7 @@
 namespace mpcqp_dense {
 
 // Persistent: one CTA per QP at a time, QPs taken round-robin (b = blockIdx.x, += gridDim.x).  The dense matrices live in
-// the CTA's private global workspace (L2-resident: 3 (n+m)^2 + n^2 + 2nm doubles, 3.1 MB at n = 200, m = 150);
+// the CTA's private global workspace (2 (n+m)^2 + n^2 + 2nm doubles: 2.8 MB at n = 200, m = 150, 0.3 MB at n = 64, m = 48; L2-resident while grid x that stays below the 126 MB);
 // right-hand sides, the pivot column and the reduction scratch in shared memory.  HBM sees the CSC inputs and x, y once.
 __global__ void __launch_bounds__(512) mpcqp_dense_solve_kernel(const __grid_constant__ Batch bt, const __grid_constant__ Settings st) {
   extern __shared__ double dq_smem[];
@@ -19,9 +19,12 @@ __global__ void __launch_bounds__(512) mpcqp_dense_solve_kernel(const __grid_con
 }
 
 int block_threads(int n, int m) {
-  int threads = ((n + m + 31) / 32) * 32;
-  if (threads < 128) threads = 128;
+  // row threads (n + m rounded up to a warp) x kMaxParts k-slices, at most 512 (126 registers per thread)
+  const int nr = ((n + m + 31) / 32) * 32;
+  int parts = 512 / nr; if (parts > kMaxParts) parts = kMaxParts; if (parts < 1) parts = 1;
+  int threads = nr * parts;
   if (threads > 512) threads = 512;
+  if (threads < 128) threads = 128;
   return threads;
 }
 

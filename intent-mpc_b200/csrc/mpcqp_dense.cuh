@@ -65,12 +65,13 @@ struct Batch {      // B QPs sharing one CSC pattern (polyTrajSolver's x / y / z
   int32_t* info_i; double* info_d;            // [B][3] each
 };
 
-// workspace: dense P (mirrored), A, A', the KKT factor and its two inverse-triangle copies, vectors
+// workspace: dense P (mirrored), A, A', the KKT factor (later L^-1) and L^-T, vectors
 inline size_t ws_doubles(int n, int m) {
   const size_t N = (size_t)n + m;
-  return 3 * N * N + (size_t)n * n + 2 * (size_t)n * m + 8 * N + 14 * (size_t)n + 18 * (size_t)m + 64;
+  return 2 * N * N + (size_t)n * n + 2 * (size_t)n * m + 8 * N + 14 * (size_t)n + 18 * (size_t)m + 64;
 }
-inline size_t smem_doubles(int n, int m) { return 3 * ((size_t)n + m) + 40; }
+constexpr int kMaxParts = 1;   // k-slices per row (groups of row threads); > 1 measured slower on B200 at 64 registers / thread
+inline size_t smem_doubles(int n, int m) { return (3 + kMaxParts) * ((size_t)n + m) + 40; }
 
 struct Solver {
   int tid, nt, n, m, N;
@@ -79,7 +80,8 @@ struct Solver {
   double *L, *M1, *M2, *dinv, *tmpN;                    // factor, L^-1 (row i contiguous over threads), L^-T, 1/D
   double *D, *Dinv, *E, *Einv, *rho, *rho_inv, *ctype;
   double *x, *z, *y, *xp, *zp, *xt, *Axv, *Pxv, *Aty, *dy, *dx, *Atdy, *Pdx, *Adx, *tmpn, *tmpm;
-  double *s_rhs, *s_t, *s_col, *s_red;           // shared memory
+  double *s_rhs, *s_t, *s_col, *s_red, *s_part;  // shared memory
+  int RT, parts, rt, my_part;                    // row threads per group, groups, this thread's row lane and group
   double c, cinv;
   double pri_res, dua_res, obj;
   int status, rho_updates;
@@ -119,14 +121,17 @@ struct Solver {
   DQ_FN void carve(const Problem& pb, double* smem) {
     n = pb.n; m = pb.m; N = n + m;
     double* w = pb.ws; const size_t NN = (size_t)N * N;
-    L = w; w += NN; M1 = w; w += NN; M2 = w; w += NN;
+    L = w; M1 = w; w += NN; M2 = w; w += NN;      // M1 (L^-1 for the first mat-vec) takes L's place once L^-1 is formed
     P = w; w += (size_t)n * n; A = w; w += (size_t)n * m; At = w; w += (size_t)n * m; q = w; w += n; l = w; w += m; u = w; w += m;
     dinv = w; w += N; xt = w; w += N; tmpN = w; w += N;
     D = w; w += n; Dinv = w; w += n; x = w; w += n; xp = w; w += n; Pxv = w; w += n; Aty = w; w += n; dx = w; w += n; Atdy = w; w += n;
     Pdx = w; w += n; tmpn = w; w += n;
     E = w; w += m; Einv = w; w += m; rho = w; w += m; rho_inv = w; w += m; ctype = w; w += m; z = w; w += m; zp = w; w += m; y = w; w += m;
     Axv = w; w += m; dy = w; w += m; Adx = w; w += m; tmpm = w; w += m;
-    s_rhs = smem; s_t = smem + N; s_col = smem + 2 * (size_t)N; s_red = smem + 3 * (size_t)N;
+    s_rhs = smem; s_t = smem + N; s_col = smem + 2 * (size_t)N; s_red = smem + 3 * (size_t)N; s_part = s_red + 40;
+    const int NR = ((N + 31) / 32) * 32;
+    RT = nt < NR ? nt : NR; parts = nt / RT; if (parts > kMaxParts) parts = kMaxParts;
+    rt = tid % RT; my_part = tid / RT;
   }
 
   // ---- the caller's CSC -> dense scratch copies (P mirrored to full, A both ways), q, l, u ------------------------------------
@@ -169,16 +174,16 @@ struct Solver {
         tmpm[i] = 1.0 / sqrt(limit_scaling(a));
       }
       DQ_SYNC();
-      for (size_t idx = tid; idx < (size_t)n * n; idx += nt) {
-        const int i = (int)(idx % n), j = (int)(idx / n);
+      for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx % n, j = idx / n;
         P[idx] = (P[idx] * tmpn[i < j ? i : j]) * tmpn[i < j ? j : i];     // upper-triangle entry: row factor, then column factor
       }
-      for (size_t idx = tid; idx < (size_t)m * n; idx += nt) {
-        const int i = (int)(idx % m), j = (int)(idx / m);
+      for (int idx = tid; idx < m * n; idx += nt) {
+        const int i = idx % m, j = idx / m;
         A[idx] = (A[idx] * tmpm[i]) * tmpn[j];
       }
-      for (size_t idx = tid; idx < (size_t)m * n; idx += nt) {
-        const int j = (int)(idx % n), i = (int)(idx / n);
+      for (int idx = tid; idx < m * n; idx += nt) {
+        const int j = idx % n, i = idx / n;
         At[idx] = (At[idx] * tmpm[i]) * tmpn[j];
       }
       DQ_FOR(j, n) { q[j] *= tmpn[j]; D[j] *= tmpn[j]; }
@@ -194,7 +199,7 @@ struct Solver {
       nq = limit_scaling(blk_max(nq));
       if (nq > c_temp) c_temp = nq;
       c_temp = 1.0 / limit_scaling(c_temp);
-      for (size_t idx = tid; idx < (size_t)n * n; idx += nt) P[idx] *= c_temp;
+      for (int idx = tid; idx < n * n; idx += nt) P[idx] *= c_temp;
       DQ_FOR(j, n) q[j] *= c_temp;
       c *= c_temp;
     }
@@ -215,63 +220,102 @@ struct Solver {
     }
   }
 
-  // ---- KKT (kkt.h:15-18), dense lower triangle, L D L' in place, then L^-1 ---------------------------------------------------
+  // ---- KKT (kkt.h:15-18), dense lower triangle stored ROW-major (L[j + N*i] = K(i,j), i >= j: the threads of a warp sit on
+  //      neighbouring columns), L D L' in place, then L^-1 ------------------------------------------------------------------
   DQ_FN void factor() {
     DQ_SYNC();
-    for (size_t idx = tid; idx < (size_t)N * N; idx += nt) {
-      const int i = (int)(idx % N), j = (int)(idx / N);
+    for (int idx = tid; idx < N * N; idx += nt) {
+      const int j = idx % N, i = idx / N;
       double v = 0.0;
       if (i >= j) {
         if (i < n) v = P[i + (size_t)n * j] + (i == j ? s.sigma : 0.0);
-        else if (j < n) v = A[(i - n) + (size_t)m * j];
+        else if (j < n) v = At[j + (size_t)n * (i - n)];
         else if (i == j) v = -rho_inv[i - n];
       }
       L[idx] = v;
     }
+    // right-looking: step k subtracts c_i c_j / d_k from K(i,j), i >= j > k (c = the unscaled pivot column, staged in shared
+    // memory).  Thread <-> column j; the threads of a warp walk the rows i in lockstep (coalesced), starting at the warp's
+    // first diagonal; a column whose multiplier is zero (the KKT matrix is sparse until fill-in) is skipped.
     for (int k = 0; k < N; ++k) {
       DQ_SYNC();
       const int w = N - k - 1;
-      DQ_FOR(ii, w) s_col[ii] = L[(k + 1 + ii) + (size_t)N * k];
+      DQ_FOR(ii, w) s_col[ii] = L[k + (size_t)N * (k + 1 + ii)];
       const double dk = L[k + (size_t)N * k];
       DQ_SYNC();
-      for (int jj = 0; jj < w; ++jj) {
+      for (int jj = tid; jj < w; jj += nt) {
         const double cj = s_col[jj];
         if (cj == 0.0) continue;
         const double f = cj / dk;
-        double* col = L + (size_t)N * (k + 1 + jj) + (k + 1);
-        for (int ii = jj + tid; ii < w; ii += nt) col[ii] -= s_col[ii] * f;
+        double* colj = L + (k + 1 + jj) + (size_t)N * (k + 1);
+#ifdef MPCQP_HOST_EMUL
+        const int i0 = jj;
+#else
+        const int i0 = jj & ~31;
+#endif
+        for (int ii = i0; ii < w; ii += 8) {       // eight loads in flight per thread: the update is latency-bound otherwise
+          double v[8];
+#pragma unroll
+          for (int t8 = 0; t8 < 8; ++t8) { const int r = ii + t8; v[t8] = (r < w) ? colj[(size_t)N * r] : 0.0; }
+#pragma unroll
+          for (int t8 = 0; t8 < 8; ++t8) { const int r = ii + t8; if (r >= jj && r < w) colj[(size_t)N * r] = v[t8] - s_col[r] * f; }
+        }
       }
     }
     DQ_SYNC();
     DQ_FOR(k, N) dinv[k] = 1.0 / L[k + (size_t)N * k];
     DQ_SYNC();
-    for (size_t idx = tid; idx < (size_t)N * N; idx += nt) {
-      const int i = (int)(idx % N), j = (int)(idx / N);
+    for (int idx = tid; idx < N * N; idx += nt) {
+      const int j = idx % N, i = idx / N;
       if (i > j) L[idx] *= dinv[j];
     }
     DQ_SYNC();
-    // column c of L^-1 by forward substitution, one thread per column; M2[c + N*i] = (L^-1)[i][c]
+    // column c of L^-1 by forward substitution, one thread per column; M2[c + N*i] = (L^-1)[i][c]; row i of L is contiguous
     DQ_FOR(cc, N) {
       for (int i = 0; i < N; ++i) {
         double a = (i == cc) ? 1.0 : 0.0;
-        if (i > cc) for (int k = cc; k < i; ++k) a -= L[i + (size_t)N * k] * M2[cc + (size_t)N * k];
+        if (i > cc) { const double* Li = L + (size_t)N * i; for (int k = cc; k < i; ++k) a -= Li[k] * M2[cc + (size_t)N * k]; }
         M2[cc + (size_t)N * i] = a;
       }
     }
     DQ_SYNC();
-    for (size_t idx = tid; idx < (size_t)N * N; idx += nt) {
-      const int i = (int)(idx % N), k = (int)(idx / N);
+    for (int idx = tid; idx < N * N; idx += nt) {  // L is dead from here on: M1 overwrites it
+      const int i = idx % N, k = idx / N;
       M1[idx] = M2[k + (size_t)N * i];           // M1[i + N*k] = (L^-1)[i][k]
     }
     DQ_SYNC();
   }
 
+  // Row mat-vec helper: sum over k in [lo, hi) of M[i + N*k] * v[k] with eight independent partial sums (the loads are
+  // what a thread waits for: L2 latency, not bandwidth, bounds these loops at one CTA per SM).
+  DQ_FN double row_dot(const double* Mi, size_t ld, const double* v, int lo, int hi) {
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int k = lo;
+    for (; k + 8 <= hi; k += 8) {
+#pragma unroll
+      for (int t8 = 0; t8 < 8; ++t8) a[t8] += Mi[ld * (k + t8)] * v[k + t8];
+    }
+    for (; k < hi; ++k) a[0] += Mi[ld * k] * v[k];
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+  // The CTA's threads form `parts` groups of RT row threads (carve): each group takes a contiguous slice of every row's k
+  // range, the slices' sums meet in shared memory (s_part) and are added in a fixed order (deterministic).
   // b (shared) -> out (global): out = L^-T D^-1 L^-1 b; b is preserved
   DQ_FN void tri_solve(const double* b, double* out) {
     DQ_SYNC();
-    DQ_FOR(i, N) { double a = 0; for (int k = 0; k <= i; ++k) a += M1[i + (size_t)N * k] * b[k]; s_t[i] = a * dinv[i]; }
+    if (my_part < parts) for (int i = rt; i < N; i += RT) {
+      const int len = i + 1, lo = (int)((long long)len * my_part / parts), hi = (int)((long long)len * (my_part + 1) / parts);
+      s_part[(size_t)my_part * N + i] = row_dot(M1 + i, (size_t)N, b, lo, hi);
+    }
     DQ_SYNC();
-    DQ_FOR(i, N) { double a = 0; for (int k = i; k < N; ++k) a += M2[i + (size_t)N * k] * s_t[k]; out[i] = a; }
+    DQ_FOR(i, N) { double a = s_part[i]; for (int p = 1; p < parts; ++p) a += s_part[(size_t)p * N + i]; s_t[i] = a * dinv[i]; }
+    DQ_SYNC();
+    if (my_part < parts) for (int i = rt; i < N; i += RT) {
+      const int len = N - i, lo = i + (int)((long long)len * my_part / parts), hi = i + (int)((long long)len * (my_part + 1) / parts);
+      s_part[(size_t)my_part * N + i] = row_dot(M2 + i, (size_t)N, s_t, lo, hi);
+    }
+    DQ_SYNC();
+    DQ_FOR(i, N) { double a = s_part[i]; for (int p = 1; p < parts; ++p) a += s_part[(size_t)p * N + i]; out[i] = a; }
     DQ_SYNC();
   }
   // s_rhs (shared) -> xt, with one step of iterative refinement against the KKT matrix in its original form (P, A, rho):
@@ -280,16 +324,20 @@ struct Solver {
   DQ_FN void kkt_solve() {
     tri_solve(s_rhs, xt);
     if (!kRefine) return;
-    DQ_FOR(j, n) {
-      double a = s.sigma * xt[j];
-      for (int i = 0; i < n; ++i) a += P[j + (size_t)n * i] * xt[i];
-      for (int i = 0; i < m; ++i) a += At[j + (size_t)n * i] * xt[n + i];
-      s_col[j] = s_rhs[j] - a;
+    if (my_part < parts) for (int r = rt; r < N; r += RT) {     // K xt, row r, slice my_part of the n columns (+ of the m rows of A')
+      const int lo = (int)((long long)n * my_part / parts), hi = (int)((long long)n * (my_part + 1) / parts);
+      double a;
+      if (r < n) {
+        const int lo2 = (int)((long long)m * my_part / parts), hi2 = (int)((long long)m * (my_part + 1) / parts);
+        a = row_dot(P + r, (size_t)n, xt, lo, hi) + row_dot(At + r, (size_t)n, xt + n, lo2, hi2);
+      } else a = row_dot(A + (r - n), (size_t)m, xt, lo, hi);
+      s_part[(size_t)my_part * N + r] = a;
     }
-    DQ_FOR(i, m) {
-      double a = -rho_inv[i] * xt[n + i];
-      for (int j = 0; j < n; ++j) a += A[i + (size_t)m * j] * xt[j];
-      s_col[n + i] = s_rhs[n + i] - a;
+    DQ_SYNC();
+    DQ_FOR(r, N) {
+      double a = s_part[r]; for (int p = 1; p < parts; ++p) a += s_part[(size_t)p * N + r];
+      a += (r < n) ? s.sigma * xt[r] : -rho_inv[r - n] * xt[r];
+      s_col[r] = s_rhs[r] - a;
     }
     tri_solve(s_col, tmpN);
     DQ_FOR(i, N) xt[i] += tmpN[i];
