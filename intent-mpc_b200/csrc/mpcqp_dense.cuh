@@ -18,6 +18,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifdef MPCQP_HOST_EMUL
 #define DQ_FN inline
@@ -27,6 +28,12 @@
 #define DQ_SYNC() __syncthreads()
 #endif
 #define DQ_FOR(i, cnt) for (int i = tid; i < (cnt); i += nt)
+// -DMPCQP_DENSE_PHASES: development build that prints clock64 totals per phase of one QP (scratch/dense_phases.py)
+#if defined(MPCQP_DENSE_PHASES) && !defined(MPCQP_HOST_EMUL)
+#define DQ_T(slot) do { DQ_SYNC(); const long long t_now = clock64(); ph[slot] += t_now - t_last; t_last = t_now; } while (0)
+#else
+#define DQ_T(slot) ((void)0)
+#endif
 
 namespace mpcqp_dense {
 
@@ -85,6 +92,9 @@ struct Solver {
   double c, cinv;
   double pri_res, dua_res, obj;
   int status, rho_updates;
+#if defined(MPCQP_DENSE_PHASES) && !defined(MPCQP_HOST_EMUL)
+  long long ph[12], t_last;
+#endif
 
   // ---- CTA-wide reductions; every thread gets the result --------------------------------------------------------------
   DQ_FN double blk_max(double v) {
@@ -220,6 +230,18 @@ struct Solver {
     }
   }
 
+  // Row mat-vec helper: sum over k in [lo, hi) of M[i + N*k] * v[k] with eight independent partial sums (the loads are
+  // what a thread waits for: L2 latency, not bandwidth, bounds these loops at one CTA per SM).
+  DQ_FN double row_dot(const double* Mi, size_t ld, const double* v, int lo, int hi) {
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int k = lo;
+    for (; k + 8 <= hi; k += 8) {
+#pragma unroll
+      for (int t8 = 0; t8 < 8; ++t8) a[t8] += Mi[ld * (k + t8)] * v[k + t8];
+    }
+    for (; k < hi; ++k) a[0] += Mi[ld * k] * v[k];
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
   // ---- KKT (kkt.h:15-18), dense lower triangle stored ROW-major (L[j + N*i] = K(i,j), i >= j: the threads of a warp sit on
   //      neighbouring columns), L D L' in place, then L^-1 ------------------------------------------------------------------
   DQ_FN void factor() {
@@ -234,6 +256,7 @@ struct Solver {
       }
       L[idx] = v;
     }
+    DQ_T(8);
     // right-looking: step k subtracts c_i c_j / d_k from K(i,j), i >= j > k (c = the unscaled pivot column, staged in shared
     // memory).  Thread <-> column j; the threads of a warp walk the rows i in lockstep (coalesced), starting at the warp's
     // first diagonal; a column whose multiplier is zero (the KKT matrix is sparse until fill-in) is skipped.
@@ -253,15 +276,16 @@ struct Solver {
 #else
         const int i0 = jj & ~31;
 #endif
-        for (int ii = i0; ii < w; ii += 8) {       // eight loads in flight per thread: the update is latency-bound otherwise
-          double v[8];
+        for (int ii = i0; ii < w; ii += 16) {      // sixteen loads in flight per thread: the update is latency-bound otherwise
+          double v[16];
 #pragma unroll
-          for (int t8 = 0; t8 < 8; ++t8) { const int r = ii + t8; v[t8] = (r < w) ? colj[(size_t)N * r] : 0.0; }
+          for (int t8 = 0; t8 < 16; ++t8) { const int r = ii + t8; v[t8] = (r < w) ? colj[(size_t)N * r] : 0.0; }
 #pragma unroll
-          for (int t8 = 0; t8 < 8; ++t8) { const int r = ii + t8; if (r >= jj && r < w) colj[(size_t)N * r] = v[t8] - s_col[r] * f; }
+          for (int t8 = 0; t8 < 16; ++t8) { const int r = ii + t8; if (r >= jj && r < w) colj[(size_t)N * r] = v[t8] - s_col[r] * f; }
         }
       }
     }
+    DQ_T(2);
     DQ_SYNC();
     DQ_FOR(k, N) dinv[k] = 1.0 / L[k + (size_t)N * k];
     DQ_SYNC();
@@ -274,7 +298,7 @@ struct Solver {
     DQ_FOR(cc, N) {
       for (int i = 0; i < N; ++i) {
         double a = (i == cc) ? 1.0 : 0.0;
-        if (i > cc) { const double* Li = L + (size_t)N * i; for (int k = cc; k < i; ++k) a -= Li[k] * M2[cc + (size_t)N * k]; }
+        if (i > cc) a -= row_dot(M2 + cc, (size_t)N, L + (size_t)N * i, cc, i);     // eight partial sums: the chain is the critical path
         M2[cc + (size_t)N * i] = a;
       }
     }
@@ -284,20 +308,9 @@ struct Solver {
       M1[idx] = M2[k + (size_t)N * i];           // M1[i + N*k] = (L^-1)[i][k]
     }
     DQ_SYNC();
+    DQ_T(3);
   }
 
-  // Row mat-vec helper: sum over k in [lo, hi) of M[i + N*k] * v[k] with eight independent partial sums (the loads are
-  // what a thread waits for: L2 latency, not bandwidth, bounds these loops at one CTA per SM).
-  DQ_FN double row_dot(const double* Mi, size_t ld, const double* v, int lo, int hi) {
-    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int k = lo;
-    for (; k + 8 <= hi; k += 8) {
-#pragma unroll
-      for (int t8 = 0; t8 < 8; ++t8) a[t8] += Mi[ld * (k + t8)] * v[k + t8];
-    }
-    for (; k < hi; ++k) a[0] += Mi[ld * k] * v[k];
-    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-  }
   // The CTA's threads form `parts` groups of RT row threads (carve): each group takes a contiguous slice of every row's k
   // range, the slices' sums meet in shared memory (s_part) and are added in a fixed order (deterministic).
   // b (shared) -> out (global): out = L^-T D^-1 L^-1 b; b is preserved
@@ -322,7 +335,9 @@ struct Solver {
   // r = b - K s, s += K^-1 r.  The minimum-snap Hessians are ill-conditioned (entries 1 .. 1e5 per segment block); the
   // refined solve is at the accuracy of OSQP's own factorisation or better.  s_rhs is preserved.
   DQ_FN void kkt_solve() {
+    DQ_T(6);
     tri_solve(s_rhs, xt);
+    DQ_T(4);
     if (!kRefine) return;
     if (my_part < parts) for (int r = rt; r < N; r += RT) {     // K xt, row r, slice my_part of the n columns (+ of the m rows of A')
       const int lo = (int)((long long)n * my_part / parts), hi = (int)((long long)n * (my_part + 1) / parts);
@@ -339,9 +354,11 @@ struct Solver {
       a += (r < n) ? s.sigma * xt[r] : -rho_inv[r - n] * xt[r];
       s_col[r] = s_rhs[r] - a;
     }
+    DQ_T(5);
     tri_solve(s_col, tmpN);
     DQ_FOR(i, N) xt[i] += tmpN[i];
     DQ_SYNC();
+    DQ_T(4);
   }
 
   // ---- auxil.h:67-112, one ADMM iteration ------------------------------------------------------------------------------
@@ -476,10 +493,16 @@ struct Solver {
   DQ_FN void run(const Problem& pb, const Settings& st, double* smem, int tid_, int nt_) {
     tid = tid_; nt = nt_; s = st;
     carve(pb, smem);
+#if defined(MPCQP_DENSE_PHASES) && !defined(MPCQP_HOST_EMUL)
+    for (int t = 0; t < 12; ++t) ph[t] = 0;
+    t_last = clock64();
+#endif
     densify(pb);
+    DQ_T(0);
     if (s.scaling) scale_data();
     else { c = cinv = 1.0; DQ_FOR(j, n) D[j] = Dinv[j] = 1.0; DQ_FOR(i, m) E[i] = Einv[i] = 1.0; }
     DQ_SYNC();
+    DQ_T(1);
     set_rho_vec();
     factor();
     // iterates: cold start or osqp_warm_start (x <- D^-1 x, y <- c E^-1 y, z <- A x)
@@ -494,7 +517,9 @@ struct Solver {
       iterate();
       last = iter;
       can_check = s.check_termination && (iter % s.check_termination == 0);
+      DQ_T(6);
       if (can_check) { update_info(); if (check_termination(false)) { done = true; break; } }
+      DQ_T(7);
       if (s.adaptive_rho && s.adaptive_rho_interval && (iter % s.adaptive_rho_interval == 0)) {
         if (!can_check) update_info();
         adapt_rho();
@@ -513,6 +538,10 @@ struct Solver {
     const bool ok = has_solution();
     DQ_FOR(j, n) pb.x[j] = ok ? (s.scaling ? D[j] * x[j] : x[j]) : kOsqpNan;
     if (pb.y) DQ_FOR(i, m) pb.y[i] = ok ? (s.scaling ? E[i] * y[i] * cinv : y[i]) : kOsqpNan;
+#if defined(MPCQP_DENSE_PHASES) && !defined(MPCQP_HOST_EMUL)
+    if (tid == 0 && blockIdx.x == 0) printf("phases N %d iters %d: densify %lld scale %lld kkt-fill %lld ldl %lld inverse %lld tri_solve %lld residual %lld iterate-rest %lld check %lld\n",
+                                            N, last, ph[0], ph[1], ph[8], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+#endif
     if (tid == 0) {
       pb.info_i[0] = status; pb.info_i[1] = last; pb.info_i[2] = rho_updates;
       pb.info_d[0] = obj; pb.info_d[1] = pri_res; pb.info_d[2] = dua_res;

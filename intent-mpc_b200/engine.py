@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpcqp_b200.so")
+LIB_PATH = os.environ.get("MPCQP_B200_LIB", os.path.join(HERE, "libmpcqp_b200.so"))   # development builds only
 
 STATUS_NAMES = {1: "solved", 2: "solved inaccurate", 3: "primal infeasible inaccurate",
                 4: "dual infeasible inaccurate", -2: "maximum iterations reached", -3: "primal infeasible",
