@@ -79,6 +79,19 @@ static int run_facade(const char* in, const char* out) {
   if (bad.getStatus() != OsqpEigen::Status::Solved) return 13;
   const OsqpEigen::Vector& xb = bad.getSolution();
   if (fabs(xb[0]) > 5e-3 || fabs(xb[1]) > 5e-3) return 14;
+  // polyTrajSolver::updateProblem (polyTrajSolver.cpp:225-239): new bounds on the same solver object, solved again;
+  // 0.5 <= a + b <= 1  ->  a = b = 0.25
+  OsqpEigen::Vector l3(1), u3(1); l3[0] = 0.5; u3[0] = 1.0;
+  if (!bad.updateBounds(l3, u3)) return 15;
+  if (!bad.solve()) return 16;
+  const OsqpEigen::Vector& xc = bad.getSolution();
+  if (fabs(xc[0] - 0.25) > 5e-3 || fabs(xc[1] - 0.25) > 5e-3) return 17;
+  // polyTrajSolver::setUpProblem (:180-191) on a used solver: clearSolver + clear*Matrix + set* + initSolver again
+  bad.clearSolver(); bad.data()->clearHessianMatrix(); bad.data()->clearLinearConstraintsMatrix();
+  bad.data()->setNumberOfVariables(2); bad.data()->setNumberOfConstraints(1);
+  if (!bad.data()->setHessianMatrix(P2) || !bad.data()->setGradient(q2) || !bad.data()->setLinearConstraintsMatrix(A2) ||
+      !bad.data()->setLowerBound(l2) || !bad.data()->setUpperBound(u2) || !bad.initSolver() || !bad.solve()) return 18;
+  if (fabs(bad.getSolution()[0]) > 5e-3) return 19;
   return 0;
 }
 
