@@ -235,6 +235,13 @@ struct Solver {
   DQ_FN double row_dot(const double* Mi, size_t ld, const double* v, int lo, int hi) {
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int k = lo;
+    for (; k + 16 <= hi; k += 16) {      // sixteen matrix loads in flight (one L2 round trip per group is what a warp waits for)
+      double mv[16];
+#pragma unroll
+      for (int t8 = 0; t8 < 16; ++t8) mv[t8] = Mi[ld * (k + t8)];
+#pragma unroll
+      for (int t8 = 0; t8 < 16; ++t8) a[t8 & 7] += mv[t8] * v[k + t8];
+    }
     for (; k + 8 <= hi; k += 8) {
 #pragma unroll
       for (int t8 = 0; t8 < 8; ++t8) a[t8] += Mi[ld * (k + t8)] * v[k + t8];
