@@ -530,10 +530,10 @@ def run_receding(args, rank, world, local_rank):
 
 def run_polytraj(args, rank, world, local_rank):
     """SURVEY.md section 8(f) row 3 — the boundary's second consumer: `--paths` candidate paths of `--segments` segments, i.e.
-    3 x paths minimum-snap QPs of polyTrajSolver's shape (oracle/polytraj_assembly.py), through the batched generic entry
+    3 x paths minimum-snap QPs of polyTrajSolver's shape (intent-mpc_b200/polytraj_workload.py), through the batched generic entry
     point (mpcqp_solve_qp_batch_host: host buffers in and out, one launch of the dense kernel).  Not the driver's bench line.
     `value`: kernel time (CUDA events of the engine, inputs resident); `e2e`: wall clock of the host call.  One GPU."""
-    from oracle import polytraj_assembly as PA
+    from intent_mpc_b200 import polytraj_workload as PA
     qb = PA.path_batch(args.paths, K=args.segments, seed0=100)
     B = int(qb.q.shape[0])
     work = f"polyTrajSolver QPs: {args.paths} paths x 3 axes, K={args.segments} segments, n={qb.n}, m={qb.m} (minimum snap, degree 7, C4 continuity)"

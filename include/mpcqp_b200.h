@@ -11,7 +11,7 @@
  *   (1) engine lifecycle, one engine per GPU / host thread;
  *   (2) the batched entry point: B independent mpcPlanner control-step QPs are ASSEMBLED ON THE DEVICE from
  *       the planner's own inputs (current state, reference window, per-stage obstacle ellipsoids,
- *       linearisation point, warm start) and solved, one warp per QP;
+ *       linearisation point, warm start) and solved, one CTA per QP (csrc/mpcqp_core.cuh);
  *   (3) an OSQP-shaped single-problem set (setup / warm_start / solve / info / solution / cleanup) taking
  *       explicit CSC matrices, which is what the OsqpEigen::Solver-shaped C++ facade
  *       (intent-mpc_b200/host/OsqpEigenB200.hpp) calls.
@@ -33,7 +33,7 @@ enum mpcqp_error {
   MPCQP_ERR_ARG = -2,           /* null pointer / bad size */
   MPCQP_ERR_DATA = -3,          /* OSQP_DATA_VALIDATION_ERROR analogue (osqp constants.h:41-49): l > u, bad dims */
   MPCQP_ERR_SETTINGS = -4,      /* OSQP_SETTINGS_VALIDATION_ERROR analogue, or a setting the engine does not implement */
-  MPCQP_ERR_STRUCTURE = -5,     /* CSC problem is not the mpcPlanner stage structure (no generic kernel yet) */
+  MPCQP_ERR_STRUCTURE = -5,     /* CSC problem has no mpcPlanner stage structure AND is too large for the dense generic kernel (n + m > 4096) */
   MPCQP_ERR_NOT_INIT = -7       /* OSQP_WORKSPACE_NOT_INIT_ERROR analogue */
 };
 

@@ -28,7 +28,7 @@
 #define DQ_SYNC() __syncthreads()
 #endif
 #define DQ_FOR(i, cnt) for (int i = tid; i < (cnt); i += nt)
-// -DMPCQP_DENSE_PHASES: development build that prints clock64 totals per phase of one QP (scratch/dense_phases.py)
+// -DMPCQP_DENSE_PHASES: development build that prints clock64 totals per phase of one QP (tools/)
 #if defined(MPCQP_DENSE_PHASES) && !defined(MPCQP_HOST_EMUL)
 #define DQ_T(slot) do { DQ_SYNC(); const long long t_now = clock64(); ph[slot] += t_now - t_last; t_last = t_now; } while (0)
 #else

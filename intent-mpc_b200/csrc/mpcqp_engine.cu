@@ -136,8 +136,15 @@ static SolveKernel pick_setup_kernel(int R) {
 // ------------------------------------------------------------------------------------------------
 using namespace mpcqp;
 
+struct DevBuf;
+// Every DevBuf constructed while an engine is being built registers itself here, so that mpcqp_engine_destroy releases
+// all of them without a hand-kept list (new members cannot be forgotten).
+static thread_local std::vector<DevBuf*>* g_devbuf_registry = nullptr;
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
+  DevBuf() { if (g_devbuf_registry) g_devbuf_registry->push_back(this); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
   cudaError_t need(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
@@ -150,19 +157,25 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return (T*)p; }
 };
+struct DevBufScope {   // first member of the engine: opens the registry before the DevBuf members are constructed
+  std::vector<DevBuf*> all;
+  DevBufScope() { g_devbuf_registry = &all; }
+};
+struct DevBufScopeEnd { DevBufScopeEnd() { g_devbuf_registry = nullptr; } };   // last member: closes it
 
 struct DenseDev {   // device buffers of one call of the generic (unstructured) path
   DevBuf Pc, Pi, Px, Ac, Ai, Ax, q, l, u, wx, wy, x, y, ii, dd, ws;
-  void release() { DevBuf* b[] = { &Pc, &Pi, &Px, &Ac, &Ai, &Ax, &q, &l, &u, &wx, &wy, &x, &y, &ii, &dd, &ws }; for (DevBuf* v : b) v->release(); }
 };
 
 struct mpcqp_engine {
+  DevBufScope bufs;                                          // must stay the first member (see DevBufScope)
   DenseDev dense;
   int device = 0, num_sms = 0, max_smem_optin = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;          // main stream; side stream for the second solve launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr;   // batch start / end, solve-kernel start
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
+  int live_problems = 0; bool destroy_pending = false;       // mpcqp_problem handles keep their engine alive (see mpcqp_engine_destroy)
   double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int split_setup = 1; int migrate = 1, suspend_at = 300, hist_active = 0;
   const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
@@ -170,6 +183,7 @@ struct mpcqp_engine {
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
+  DevBufScopeEnd bufs_end;                                   // must stay the last member
 };
 
 static float f32(double v) { return (float)v; }
@@ -217,13 +231,14 @@ extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
   return MPCQP_OK;
 }
 
+// Problems created by mpcqp_setup hold a pointer to their engine.  Destroying an engine that still has live problems
+// (an OsqpEigen::Solver that outlives the thread-local engine of its thread, OsqpEigenB200.hpp) only marks it; the last
+// mpcqp_cleanup then releases it.
 extern "C" int mpcqp_engine_destroy(mpcqp_engine* e) {
   if (!e) return MPCQP_ERR_ARG;
+  if (e->live_problems > 0) { e->destroy_pending = true; return MPCQP_OK; }
   cudaSetDevice(e->device);
-  DevBuf* bufs[] = { &e->pd, &e->slack, &e->q, &e->x0s, &e->g, &e->low, &e->ws, &e->counter, &e->hard, &e->order, &e->hist, &e->in_x0, &e->in_xref, &e->in_c,
-                     &e->in_semi, &e->in_yaw, &e->in_lin, &e->in_warm, &e->out_x, &e->out_y, &e->out_i, &e->out_d };
-  for (DevBuf* b : bufs) b->release();
-  e->dense.release();
+  for (DevBuf* b : e->bufs.all) b->release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evs) cudaEventDestroy(e->evs);
@@ -899,11 +914,12 @@ extern "C" int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_
 
 // ------------------------------------------------------------------------------------------------
 // (3) OSQP-shaped single problem with explicit CSC data (what OsqpEigen::Solver hands to osqp_setup,
-// OsqpEigen/Data.tpp:38-39,77; osqp.h:58).  The problem must have the mpcPlanner stage structure
-// (mpcPlanner.cpp:932-1146); it is parsed on the host into the structured form the kernels take and solved
-// by the same kernels as a batch of one.  There is no generic (unstructured) kernel and no host solve.
+// OsqpEigen/Data.tpp:38-39,77; osqp.h:58).  A problem with the mpcPlanner stage structure
+// (mpcPlanner.cpp:932-1146) is parsed on the host into the structured form the stage kernels take and solved by them as a
+// batch of one; anything else goes to the dense generic kernel (csrc/mpcqp_dense.cuh).  There is no host solve.
 // ------------------------------------------------------------------------------------------------
 struct mpcqp_problem {
+  DevBufScope bufs;                                          // must stay the first member (see DevBufScope)
   mpcqp_engine* e = nullptr;
   Shape sh; Settings st; mpcqp_settings user;
   std::vector<double> pd, q, x0, g, low, warm_x, warm_y, sol_x, sol_y;
@@ -916,6 +932,11 @@ struct mpcqp_problem {
   std::vector<int64_t> dPc, dPi, dAc, dAi;
   std::vector<double> dPx, dAx, dl, du;
   DenseDev dd;
+  // the caller's CSC data of a structured problem, kept so that mpcqp_update_bounds can move it to the generic path when the
+  // new bounds leave the planner's pattern (osqp_update_bounds accepts any l <= u)
+  std::vector<int64_t> cPc, cPi, cAc, cAi;
+  std::vector<double> cPx, cAx;
+  DevBufScopeEnd bufs_end;                                   // must stay the last member
 };
 
 namespace mpcqp_dense {
@@ -1020,15 +1041,20 @@ int parse_structure(int64_t n, int64_t m, const int64_t* Pp, const int64_t* Pi, 
 
 namespace {
 // Generic path.  validate_data of osqp_setup: l <= u, P upper triangular, indices in range, monotone column pointers.
-int validate_csc(mpcqp_engine* e, int64_t n, int64_t m, const int64_t* Pc, const int64_t* Pi, const int64_t* Ac, const int64_t* Ai) {
-  if (n + m > 4096) { e->err = "unstructured problem with n + m > 4096: the dense generic kernel does not take it"; return MPCQP_ERR_STRUCTURE; }
+int validate_csc_pattern(mpcqp_engine* e, int64_t n, int64_t m, const int64_t* Pc, const int64_t* Pi, const int64_t* Ac, const int64_t* Ai) {
   if (Pc[0] != 0 || Ac[0] != 0) { e->err = "column pointers do not start at 0"; return MPCQP_ERR_DATA; }
+  for (int64_t j = 0; j < n; ++j) if (Pc[j + 1] < Pc[j] || Ac[j + 1] < Ac[j]) { e->err = "column pointers are not monotone"; return MPCQP_ERR_DATA; }
+  if ((Pc[n] > 0 && !Pi) || (Ac[n] > 0 && !Ai)) { e->err = "null row-index array"; return MPCQP_ERR_DATA; }
   for (int64_t j = 0; j < n; ++j) {
     if (Pc[j + 1] < Pc[j] || Ac[j + 1] < Ac[j]) { e->err = "column pointers are not monotone"; return MPCQP_ERR_DATA; }
     for (int64_t t = Pc[j]; t < Pc[j + 1]; ++t) if (Pi[t] < 0 || Pi[t] > j) { e->err = "P is not upper triangular (entry " + std::to_string(Pi[t]) + "," + std::to_string(j) + ")"; return MPCQP_ERR_DATA; }
     for (int64_t t = Ac[j]; t < Ac[j + 1]; ++t) if (Ai[t] < 0 || Ai[t] >= m) { e->err = "A row index out of range in column " + std::to_string(j); return MPCQP_ERR_DATA; }
   }
   return MPCQP_OK;
+}
+int validate_csc(mpcqp_engine* e, int64_t n, int64_t m, const int64_t* Pc, const int64_t* Pi, const int64_t* Ac, const int64_t* Ai) {
+  if (n + m > 4096) { e->err = "unstructured problem with n + m > 4096: the dense generic kernel does not take it"; return MPCQP_ERR_STRUCTURE; }
+  return validate_csc_pattern(e, n, m, Pc, Pi, Ac, Ai);
 }
 
 // B QPs sharing one CSC pattern, host arrays in, host arrays out: upload (the CSC data and the vectors are all HBM ever
@@ -1100,23 +1126,31 @@ extern "C" int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int6
   if (n <= 0 || m < 0 || !P_colptr || !q || !A_colptr || (m > 0 && (!l || !u))) { e->err = "null array or non-positive size"; return MPCQP_ERR_DATA; }
   const auto t0 = std::chrono::steady_clock::now();
   mpcqp_problem* pr = new mpcqp_problem();
-  pr->e = e;
+  pr->e = e; ++e->live_problems;
   int rc = check_settings(e, s, &pr->st);
-  if (rc) { delete pr; return rc; }
+  if (rc) { mpcqp_cleanup(pr); return rc; }
   pr->user = *s;
+  rc = validate_csc_pattern(e, n, m, P_colptr, P_rowidx, A_colptr, A_rowidx);       // before any column is walked
+  if (rc) { mpcqp_cleanup(pr); return rc; }
   rc = parse_structure(n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, A_val, &pr->sh, &pr->pd, &pr->slack, &pr->g, &e->err);
-  if (rc == MPCQP_ERR_STRUCTURE) {            // not an mpcPlanner QP (e.g. polyTrajSolver.cpp:162-222): generic kernel
+  if (rc == MPCQP_OK) {
+    const int NS = pr->sh.NS, N = NS - 1, R = pr->sh.R;
+    pr->x0.assign(8, 0.0); pr->low.assign((size_t)N * (R > 0 ? R : 1), 0.0);
+    rc = parse_bounds(pr->sh, l, u, pr->x0.data(), pr->sh.blo, pr->sh.bhi, pr->low.data(), &e->err);
+  }
+  if (rc == MPCQP_ERR_STRUCTURE) {            // not an mpcPlanner QP (e.g. polyTrajSolver.cpp:162-222), or the planner's matrices with
+                                              // bounds outside its pattern (non-uniform box, finite obstacle upper bound): generic kernel
     rc = setup_dense(e, pr, n, m, P_colptr, P_rowidx, P_val, q, A_colptr, A_rowidx, A_val, l, u);
     if (rc) { mpcqp_cleanup(pr); return rc; }
     pr->info.setup_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     *out = pr;
     return MPCQP_OK;
   }
-  if (rc) { delete pr; return rc; }
-  const int NS = pr->sh.NS, N = NS - 1, R = pr->sh.R;
-  pr->x0.assign(8, 0.0); pr->low.assign((size_t)N * (R > 0 ? R : 1), 0.0);
-  rc = parse_bounds(pr->sh, l, u, pr->x0.data(), pr->sh.blo, pr->sh.bhi, pr->low.data(), &e->err);
-  if (rc) { delete pr; return rc; }
+  if (rc) { mpcqp_cleanup(pr); return rc; }
+  if (n + m <= 4096) {                        // kept for a later mpcqp_update_bounds that leaves the pattern
+    pr->cPc.assign(P_colptr, P_colptr + n + 1); pr->cPi.assign(P_rowidx, P_rowidx + P_colptr[n]); pr->cPx.assign(P_val, P_val + P_colptr[n]);
+    pr->cAc.assign(A_colptr, A_colptr + n + 1); pr->cAi.assign(A_rowidx, A_rowidx + A_colptr[n]); pr->cAx.assign(A_val, A_val + A_colptr[n]);
+  }
   pr->q.assign(q, q + n);
   pr->sol_x.assign((size_t)n, 0.0); pr->sol_y.assign((size_t)m, 0.0);
   memset(&pr->info, 0, sizeof pr->info);
@@ -1182,6 +1216,16 @@ extern "C" int mpcqp_update_bounds(mpcqp_problem* pr, const double* l_new, const
   }
   Shape sh = pr->sh; std::vector<double> x0(8), low(pr->low.size());
   int rc = parse_bounds(sh, l_new, u_new, x0.data(), sh.blo, sh.bhi, low.data(), &e->err);
+  if (rc == MPCQP_ERR_STRUCTURE && !pr->cPc.empty()) {
+    // bounds outside the planner's pattern: osqp_update_bounds would take them, so the problem moves to the generic path
+    const std::vector<double> q = pr->q, sx = pr->sol_x, sy = pr->sol_y;
+    const mpcqp_info info = pr->info; const Shape keep = pr->sh;
+    rc = setup_dense(e, pr, keep.n, keep.m, pr->cPc.data(), pr->cPi.data(), pr->cPx.data(), q.data(), pr->cAc.data(), pr->cAi.data(),
+                     pr->cAx.data(), l_new, u_new);
+    if (rc) { pr->dense = false; pr->sh = keep; return rc; }
+    pr->sol_x = sx; pr->sol_y = sy; pr->info = info;        // the previous solution / a pending warm start survive (same n, m)
+    return MPCQP_OK;
+  }
   if (rc) return rc;
   pr->sh = sh; pr->x0 = x0; pr->low = low;
   CK(cudaSetDevice(e->device));
@@ -1202,7 +1246,8 @@ extern "C" int mpcqp_solve(mpcqp_problem* pr) {
   const bool ws = pr->st.warm_start != 0;
   const double* wx = nullptr; const double* wy = nullptr;
   if (ws && pr->has_wx) wx = pr->warm_x.data(); else if (ws && pr->solved) wx = pr->sol_x.data();
-  if (ws && pr->has_wy) wy = pr->warm_y.data(); else if (ws && pr->solved && !pr->has_wx) wy = pr->sol_y.data();
+  // osqp_warm_start_x replaces x only: the dual iterate of the previous solve stays (osqp.h:165)
+  if (ws && pr->has_wy) wy = pr->warm_y.data(); else if (ws && pr->solved) wy = pr->sol_y.data();
   if (pr->dense) {
     int32_t hi[3]; double hd[3];
     int rc = run_dense(e, pr->dd, pr->st, 1, n, m, pr->dPc.data(), pr->dPi.data(), pr->dPx.data(), pr->q.data(), pr->dAc.data(), pr->dAi.data(),
@@ -1280,9 +1325,9 @@ extern "C" int mpcqp_solve_qp_batch_host(mpcqp_engine* e, const mpcqp_settings* 
 extern "C" int mpcqp_cleanup(mpcqp_problem* pr) {
   if (!pr) return MPCQP_ERR_NOT_INIT;
   cudaSetDevice(pr->e->device);
-  DevBuf* bufs[] = { &pr->d_pd, &pr->d_slack, &pr->d_q, &pr->d_x0, &pr->d_g, &pr->d_low, &pr->d_wx, &pr->d_wy, &pr->d_x, &pr->d_y, &pr->d_i, &pr->d_d };
-  for (DevBuf* b : bufs) b->release();
-  pr->dd.release();
+  for (DevBuf* b : pr->bufs.all) b->release();
+  mpcqp_engine* e = pr->e;
   delete pr;
+  if (e && --e->live_problems <= 0 && e->destroy_pending) { e->live_problems = 0; mpcqp_engine_destroy(e); }
   return MPCQP_OK;
 }

@@ -30,6 +30,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mpcqp_b200.h"
@@ -217,13 +218,20 @@ class Data {
 };
 
 // One engine per (host thread, device): mpcPlanner creates a fresh Solver every control step
-// (mpcPlanner.cpp:436), which must not pay for stream / event creation each time.
+// (mpcPlanner.cpp:436), which must not pay for stream / event creation each time.  Engines are kept per device for the
+// life of the thread; a Solver that outlives its thread's engines (a static Solver, a polyTrajSolver member destroyed late)
+// stays valid because mpcqp_engine_destroy defers while problems of that engine are alive.
 inline mpcqp_engine* threadEngine(int device = 0) {
-  struct Holder { mpcqp_engine* e = nullptr; int dev = -1; ~Holder() { if (e) mpcqp_engine_destroy(e); } };
+  struct Holder {
+    std::vector<std::pair<int, mpcqp_engine*>> engines;
+    ~Holder() { for (auto& kv : engines) if (kv.second) mpcqp_engine_destroy(kv.second); }
+  };
   static thread_local Holder h;
-  if (h.e && h.dev != device) { mpcqp_engine_destroy(h.e); h.e = nullptr; }
-  if (!h.e) { if (mpcqp_engine_create(device, &h.e) != MPCQP_OK) h.e = nullptr; h.dev = device; }
-  return h.e;
+  for (auto& kv : h.engines) if (kv.first == device) return kv.second;
+  mpcqp_engine* e = nullptr;
+  if (mpcqp_engine_create(device, &e) != MPCQP_OK) return nullptr;
+  h.engines.emplace_back(device, e);
+  return e;
 }
 
 // ---- Solver (OsqpEigen/Solver.hpp:87-249) ------------------------------------------------------------

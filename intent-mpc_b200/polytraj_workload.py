@@ -1,5 +1,5 @@
-"""ORACLE / test infrastructure (not product): numpy restatement of the QP that `polyTrajSolver` hands to
-OsqpEigen — the second in-tree consumer of the solver boundary.
+"""Workload generator (inputs only, no solving): the QP that `polyTrajSolver` hands to OsqpEigen — the second in-tree
+consumer of the solver boundary — assembled with numpy.
 
 Follows trajectory_planner/include/trajectory_planner/polyTrajSolver.cpp: `constructP` (:241-272, per-segment
 minimum-`diffDegree` Hessian on normalised time, full block), `constructQ` (:309-312, zero), `constructA` (:314-575:
@@ -8,11 +8,29 @@ durations, optional corridor rows) and `constructBound` (:578-760: equalities fr
 velocities / accelerations, `softConstraint_` boxes around the mid points, corridor boxes), `avgTimeAllocation`
 (:125-138) and `getConstraintNum` (:156-160).  One QP per axis; x, y, z share P and A and differ in the bounds.
 
-Returns an `oracle.mpc_assembly.QpBatch` (B = 3: the x, y and z problems) so the oracle drivers take it unchanged.
+Returns a `QpBatch` (B = 3: the x, y and z problems) with the field names of the oracle's container, so the oracle
+drivers and `Engine.solve_qp_batch` take it unchanged.
 """
+from dataclasses import dataclass
+
 import numpy as np
 
-from oracle.mpc_assembly import QpBatch
+
+@dataclass
+class QpBatch:
+    """B problems sharing one CSC pattern (what OsqpEigen::Data would hold per problem)."""
+    n: int
+    m: int
+    P_colptr: np.ndarray   # [n+1] int64, upper-triangular P
+    P_rowidx: np.ndarray   # [nnzP]
+    P_val: np.ndarray      # [B, nnzP]
+    q: np.ndarray          # [B, n]
+    A_colptr: np.ndarray   # [n+1]
+    A_rowidx: np.ndarray   # [nnzA]
+    A_val: np.ndarray      # [B, nnzA]
+    l: np.ndarray          # [B, m]
+    u: np.ndarray          # [B, m]
+    warm_x: np.ndarray     # [B, n]
 
 
 def _csc(dense, upper=False):

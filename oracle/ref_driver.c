@@ -113,8 +113,9 @@ typedef struct {
   c_int *status, *iter, *rho_updates, *exitflag;
   /* optional internal dump of instance `dump_idx` (scaled iterates & scaling) */
   c_float *dump; c_int dump_idx;
-  /* work split */
-  c_int begin, end;
+  /* work split: a shared counter, every thread takes the next unsolved problem (a static split would leave the threads
+   * that drew the 4000-iteration instances as the tail) */
+  c_int *next;
 } job_t;
 
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
@@ -160,7 +161,11 @@ static void solve_one(const job_t *J, c_int b) {
   J->wall_time[b] = now_s() - t0;
 }
 
-static void *worker(void *arg) { job_t *J = (job_t *)arg; for (c_int b = J->begin; b < J->end; ++b) solve_one(J, b); return NULL; }
+static void *worker(void *arg) {
+  job_t *J = (job_t *)arg;
+  for (;;) { c_int b = __atomic_fetch_add(J->next, 1, __ATOMIC_RELAXED); if (b >= J->B) break; solve_one(J, b); }
+  return NULL;
+}
 
 /* Solve B problems sharing one CSC pattern, one problem per thread at a time (setup on the clock,
  * as the reference re-creates the solver per QP, mpcPlanner.cpp:436,527).  Returns total wall seconds. */
@@ -177,6 +182,7 @@ double ref_solve_batch(c_int n, c_int m, c_int nnzP, c_int nnzA, c_int B,
   if (nthreads > B) nthreads = (int)(B > 0 ? B : 1);
   job_t *jobs = (job_t *)calloc((size_t)nthreads, sizeof(job_t));
   pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+  c_int next = 0;
   double t0 = now_s();
   for (int t = 0; t < nthreads; ++t) {
     job_t *J = &jobs[t];
@@ -187,7 +193,7 @@ double ref_solve_batch(c_int n, c_int m, c_int nnzP, c_int nnzA, c_int B,
     J->setup_time = setup_time; J->solve_time = solve_time; J->wall_time = wall_time;
     J->status = status; J->iter = iter; J->rho_updates = rho_updates; J->exitflag = exitflag;
     J->dump = dump; J->dump_idx = dump_idx;
-    J->begin = B * t / nthreads; J->end = B * (t + 1) / nthreads;
+    J->next = &next;
     if (nthreads == 1) worker(J); else pthread_create(&th[t], NULL, worker, J);
   }
   if (nthreads > 1) for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);

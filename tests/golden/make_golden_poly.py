@@ -1,5 +1,5 @@
 """Generate tests/golden/polytraj_ref_golden.npz: the REFERENCE's own solver binary (oracle/_ref/libosqp.so) on the
-polyTrajSolver-shaped QPs of oracle/polytraj_assembly.py (cases()), with the determinism pins of SURVEY.md section 8(c)
+polyTrajSolver-shaped QPs of intent-mpc_b200/polytraj_workload.py (cases()), with the determinism pins of SURVEY.md section 8(c)
 (adaptive_rho_interval=25, time_limit=0), plus each case re-solved with shifted bounds (polyTrajSolver::updateProblem,
 polyTrajSolver.cpp:225-239).  Run in the build container: python tests/golden/make_golden_poly.py"""
 import dataclasses
@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import bindings as OB  # noqa: E402
-from oracle import polytraj_assembly as PA  # noqa: E402
+from intent_mpc_b200 import polytraj_workload as PA  # noqa: E402
 
 
 def shifted(qb):

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import polytraj_assembly as PA
+from intent_mpc_b200 import polytraj_workload as PA
 from tests.golden.make_golden_poly import shifted
 from tests.helpers import rel_inf
 
