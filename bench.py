@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--segments", type=int, default=8, help="--workload polytraj: path segments K (n = 8K coefficients per axis)")
     ap.add_argument("--instances", type=int, default=1000000, help="--workload sweep: total instances over all ranks")
     ap.add_argument("--chunk", type=int, default=32768, help="--workload sweep: instances per engine call")
-    ap.add_argument("--device-loop", action="store_true", help="--workload receding: enumeration, gather, scoring and choice on the device too "
+    ap.add_argument("--device-loop", action="store_true", help="--workload receding: evaluate the obstacle predictions on the device too instead of uploading them from the host every step "
                                                                 "(intent-mpc_b200/receding_device.py); e2e is then the wall clock of the whole control steps")
     return ap.parse_args()
 
@@ -328,19 +328,29 @@ def run_b200(args, rank, world, local_rank):
         # plan chosen one step earlier (candidate enumeration / scoring on the host, intent-mpc_b200/receding.py; untimed)
         if rank == 0:
             from intent_mpc_b200 import receding
-            rs = receding.IntentSweep(S=10923, D=4, seed0=5)
-            rs.step(eng.solve_mpc_batch)
-            per = []
-            for _ in range(3):
-                ms_ = [0.0]; its_ = [0]; nq_ = [0]
-                def solve_(mb_):
-                    o_ = eng.solve_mpc_batch(mb_); ms_[0] += eng.last_kernel_ms; its_[0] += int(o_["iter"].sum()); nq_[0] += mb_.B
-                    return o_
-                rs.step(solve_)
-                per.append((nq_[0], ms_[0], its_[0]))
-            extras["receding_horizon"] = {"qps_per_step": per[-1][0], "value": per[-1][0] / (per[-1][1] * 1e-3), "unit": UNIT,
-                                          "ms_per_step": [p_[1] for p_ in per], "iterations_per_step": [p_[2] for p_ in per],
-                                          "note": "configs[2] at full size, control steps 2-4 of a warm-started loop; device kernels of the two solve calls per step"}
+            from intent_mpc_b200.receding_device import DeviceIntentSweep
+            per = {}
+            for mode in ("device", "host"):
+                ds_ = DeviceIntentSweep(eng, receding.IntentSweep(S=10923, D=4, seed0=5), device=local_rank, host_predictions=(mode == "host"))
+                ds_.step(); ds_.step()                   # obstacle-free first step + one step with candidates (warm-up)
+                rows = []
+                for _ in range(3):
+                    m0 = ds_.kernel_ms; b0 = (ds_.h2d_bytes, ds_.d2h_bytes)
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    ds_.step()
+                    torch.cuda.synchronize()
+                    rows.append((1e3 * (time.perf_counter() - t0), ds_.kernel_ms - m0, int(ds_.buf["iter"].sum().item()), ds_.h2d_bytes - b0[0], ds_.d2h_bytes - b0[1]))
+                per[mode] = rows
+                del ds_
+            nq = 6 * 10923
+            extras["receding_horizon"] = {
+                "qps_per_step": nq, "value": nq / (per["device"][-1][1] * 1e-3), "unit": UNIT,
+                "ms_per_step": [r_[1] for r_ in per["device"]], "iterations_per_step": [r_[2] for r_ in per["device"]],
+                "e2e": {"value": nq / (float(np.mean([r_[0] for r_ in per["host"]])) * 1e-3), "unit": UNIT, "ms_per_step": [r_[0] for r_ in per["host"]],
+                        "h2d_bytes_per_step": per["host"][-1][3], "d2h_bytes_per_step": per["host"][-1][4],
+                        "note": "whole control step by the wall clock with HOST predictions: numpy predictions -> H2D, enumeration, gather, two solves, scoring, choice on the device, chosen plan -> D2H"},
+                "e2e_device_resident": {"value": nq / (float(np.mean([r_[0] for r_ in per["device"]])) * 1e-3), "unit": UNIT, "ms_per_step": [r_[0] for r_ in per["device"]]},
+                "note": "configs[2] at full size, control steps 3-5 of a warm-started loop (intent-mpc_b200/receding_device.py); value = device kernels of the two solve calls per step"}
     except Exception as ex:
         extras["error"] = repr(ex)
 
@@ -449,80 +459,54 @@ def run_sweep(args, rank, world, local_rank):
 
 def run_receding(args, rank, world, local_rank):
     """BASELINE.json configs[2]: per rank 10,923 scenarios x 6 intent candidates = 65,538 QPs per control step, --steps
-    control steps of the warm-started receding-horizon loop (intent-mpc_b200/receding.py; enumeration / scoring on the host,
-    untimed).  `value` = QPs per second of device kernel time, summed over the steps; the max over ranks is the job's time."""
+    control steps of the warm-started receding-horizon loop (intent-mpc_b200/receding_device.py: enumeration, gather, two
+    solves, scoring and choice are engine calls on device arrays).  `value` = QPs per second of device kernel time of the solve
+    calls, summed over the steps; `e2e` = the wall clock of the whole control steps — with --device-loop the obstacle
+    predictions are evaluated on the device too (nothing crosses PCIe), without it they come from the host every step and
+    the chosen plan goes back (host buffers inside the timed region).  The max over ranks is the job's time."""
     import torch
     import torch.distributed as dist
     from intent_mpc_b200 import engine, receding
+    from intent_mpc_b200.receding_device import DeviceIntentSweep
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = engine.Engine(local_rank)
     S = 10923
-    rs = receding.IntentSweep(S=S, D=4, seed0=1000 * rank + 5)
-    if args.device_loop:
-        from intent_mpc_b200.receding_device import DeviceIntentSweep
-        ds = DeviceIntentSweep(eng, rs, device=local_rank)
-        ds.step(); ds.step()                            # first (obstacle-free) step and one warm-up step with candidates
-        ds.kernel_ms = 0.0
-        per_step = []; its = 0
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            m0 = ds.kernel_ms
-            ds.step()
-            per_step.append(ds.kernel_ms - m0); its += int(ds.buf["iter"].sum().item())
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        dev = torch.device("cuda", local_rank)
-        t = torch.tensor([ds.kernel_ms, wall_ms], dtype=torch.float64, device=dev)
-        agg = torch.tensor([float(6 * S * args.steps), float(its)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            line = {"metric": METRIC, "value": float(agg[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2,
-                    "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                    "config": {"workload": f"configs[2], device-resident loop: {S} scenarios x 6 intent candidates = {6 * S} QPs per control step per GPU, {args.steps} "
-                                           "warm-started receding-horizon steps; enumeration, gather, solves, scoring and choice are engine calls on device arrays",
-                               "pins": "adaptive_rho_interval=25,time_limit=0", "iterations_total": int(agg[1]),
-                               "ms_per_step_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
-                               "progress_m_rank0": float(ds.pos[:, 0].mean().item())},
-                    "e2e": {"value": float(agg[0]) / (float(t[1]) * 1e-3), "unit": UNIT, "ms": float(t[1]), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                            "note": "wall clock of the whole control steps (predictions, enumeration, gather, two solves, scoring, choice, state update), nothing crosses PCIe"}}
-            print(json.dumps(line), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    rs.step(eng.solve_mpc_batch)                        # first control step: obstacle-free QPs (mpcPlanner.cpp:598-602)
-    ms = [0.0]; its = [0]; nq = [0]; wall = [0.0]; hist = {}
-    def solve_(mb_):
-        t0 = time.perf_counter()
-        o_ = eng.solve_mpc_batch(mb_)
-        wall[0] += time.perf_counter() - t0
-        ms[0] += eng.last_kernel_ms; its[0] += int(o_["iter"].sum()); nq[0] += mb_.B
-        for k_, v_ in _hist(o_["status"]).items():
-            hist[k_] = hist.get(k_, 0) + v_
-        return o_
-    per_step = []
+    ds = DeviceIntentSweep(eng, receding.IntentSweep(S=S, D=4, seed0=1000 * rank + 5), device=local_rank, host_predictions=not args.device_loop)
+    ds.step(); ds.step()                            # first (obstacle-free) step and one warm-up step with candidates
+    ds.kernel_ms = 0.0; ds.h2d_bytes = ds.d2h_bytes = 0
+    per_step = []; its = 0; hist = {}
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        m0 = ms[0]
-        rs.step(solve_)
-        per_step.append(ms[0] - m0)
+        m0 = ds.kernel_ms
+        ds.step()
+        per_step.append(ds.kernel_ms - m0); its += int(ds.buf["iter"].sum().item())
+        for k_, v_ in _hist(ds.buf["status"].cpu().numpy()).items():
+            hist[k_] = hist.get(k_, 0) + v_
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     dev = torch.device("cuda", local_rank)
-    t = torch.tensor([ms[0], wall[0] * 1e3], dtype=torch.float64, device=dev)
-    agg = torch.tensor([float(nq[0]), float(its[0])], dtype=torch.float64, device=dev)
+    t = torch.tensor([ds.kernel_ms, wall_ms], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(6 * S * args.steps), float(its)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     if rank == 0:
-        line = {"metric": METRIC, "value": float(agg[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 1,
+        where = "on the device (nothing crosses PCIe)" if args.device_loop else "on the host, uploaded every step; the chosen plan is downloaded every step"
+        line = {"metric": METRIC, "value": float(agg[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2,
                 "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"configs[2]: {S} scenarios x 6 intent candidates = {6 * S} QPs per control step per GPU, {args.steps} warm-started "
-                                       "receding-horizon steps (4 dynamic obstacles with 4 intent predictions each; candidates 4, 5 carry the closest obstacle twice)",
+                "config": {"workload": f"configs[2]: {S} scenarios x 6 intent candidates = {6 * S} QPs per control step per GPU, {args.steps} "
+                                       "warm-started receding-horizon steps (4 dynamic obstacles with 4 intent predictions each; candidates 4, 5 carry the closest "
+                                       f"obstacle twice); enumeration, gather, solves, scoring and choice are engine calls on device arrays; predictions {where}",
                            "pins": "adaptive_rho_interval=25,time_limit=0", "iterations_total": int(agg[1]), "status_hist_rank0": hist,
                            "ms_per_step_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
-                           "progress_m_rank0": float((rs.pos[:, 0]).mean())},
+                           "progress_m_rank0": float(ds.pos[:, 0].mean().item())},
                 "e2e": {"value": float(agg[0]) / (float(t[1]) * 1e-3), "unit": UNIT, "ms": float(t[1]),
-                        "note": "the solve calls with host numpy buffers (copies inside); candidate enumeration and scoring on the host are untimed"}}
+                        "h2d_bytes_per_step": int(ds.h2d_bytes // max(args.steps, 1)), "d2h_bytes_per_step": int(ds.d2h_bytes // max(args.steps, 1)),
+                        "note": "wall clock of the whole control steps (predictions, enumeration, gather, two solves, scoring, choice, state update)"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

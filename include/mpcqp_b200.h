@@ -156,8 +156,9 @@ int mpcqp_solve_mpc_batch_device(mpcqp_engine* e, const mpcqp_mpc_params* p, con
  *   prev_plan [B][n] / NULL the plan each candidate is compared with (currentStatesSol_; the warm start array); NULL on
  *                           the first control step (consistency score 0, :783-785)
  *   xref, obs_c, obs_semi   as given to the solve; the first n_dynamic rows of a stage are dynamic obstacles (full-size
- *                           xy diagonal + dynamicSafetyDist_), the rest static (half-size diagonal + staticSafetyDist_);
- *                           stage N is scored against the obstacle positions of stage N-1 (the last the solve holds)
+ *                           xy diagonal + dynamicSafetyDist_), the rest static (half-size diagonal + staticSafetyDist_)
+ *   obs_c_last, obs_semi_last [B][R][3]  the same for stage N: getSafetyScore walks every state 0..N (mpcPlanner.cpp:818-826)
+ *                           while the QP only has obstacle rows for stages 0..N-1; required when num_obs > 0
  *   score     [B][3]        (consistency, detour, safety)
  * select: scenario s has C candidates, rows cand[s][c] of `score` / `x_all`, with weights weight[s][c] (the intent
  * probabilities in the order evaluateTraj indexes them).  best[s] = argmax_c weight * (avg_c/c_c + avg_d/d_c + s_c/avg_s),
@@ -167,17 +168,19 @@ int mpcqp_solve_mpc_batch_device(mpcqp_engine* e, const mpcqp_mpc_params* p, con
  * dynamic_predictor/utils.h:15-20), prob [S][D][4], prev_plan [S][n] or NULL on the first step (then pos [S][3] is used).
  * The six hypotheses of a scenario, sorted by descending weight, become rows of two solve batches: scen_a [4S] / obs_c_a,
  * obs_semi_a [4S][N][D][3] (one intent for the closest obstacle) and scen_b [2S] / obs_c_b, obs_semi_b [2S][N][D+1][3] (two
- * intents: the closest obstacle twice); cand [S][6] = row of sorted candidate c in the concatenation (batch a, then b),
+ * intents: the closest obstacle twice); obs_c_last_a, obs_semi_last_a [4S][D][3] and obs_c_last_b, obs_semi_last_b
+ * [2S][D+1][3] (all four or none; need NP >= horizon) receive the predictions of stage N for the scoring; cand [S][6] = row of sorted candidate c in the concatenation (batch a, then b),
  * weight [S][6] as evaluateTraj indexes it.  mpcqp_gather_rows_device replicates scenario-level arrays (x0, xref, lin_pt,
  * warm_x) per row: dst[b] = src[idx[b]]. */
 int mpcqp_intent_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t S, int32_t D, int32_t NP,
                                    const double* pred_pos, const double* pred_size, const double* prob, const double* prev_plan,
                                    const double* pos, int32_t* scen_a, int32_t* scen_b, double* obs_c_a, double* obs_semi_a,
-                                   double* obs_c_b, double* obs_semi_b, double* weight, int32_t* cand);
+                                   double* obs_c_b, double* obs_semi_b, double* obs_c_last_a, double* obs_semi_last_a,
+                                   double* obs_c_last_b, double* obs_semi_last_b, double* weight, int32_t* cand);
 int mpcqp_gather_rows_device(mpcqp_engine* e, int64_t B, int32_t width, const int32_t* idx, const double* src, double* dst);
 int mpcqp_score_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t B, int32_t num_obs, int32_t n_dynamic,
                                   const double* x, const double* prev_plan, const double* xref, const double* obs_c,
-                                  const double* obs_semi, double* score);
+                                  const double* obs_semi, const double* obs_c_last, const double* obs_semi_last, double* score);
 int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_t C, int32_t n, const int32_t* cand,
                                    const double* weight, const double* score, const double* x_all, int32_t* best,
                                    double* weighted, double* plan);

@@ -679,51 +679,63 @@ extern "C" int mpcqp_fp64_fma_peak(mpcqp_engine* e, double* tflops) {
 // solves of makePlanWithPred (mpcPlanner.cpp:609-644), their scoring and the choice of the plan need no host round trip.
 // ------------------------------------------------------------------------------------------------
 namespace mpcqp {
-// one warp per candidate, lane = stage (strided for longer horizons)
+// one warp per candidate, lane = stage (in chunks of 32 for longer horizons).  The per-stage terms are computed in parallel
+// and then added by lane 0 in stage order, which is the reference's own summation order (mpcPlanner.cpp:789-795, 804-810,
+// 817-848): the scores differ from the reference's only by the rounding of tanh (CUDA's vs glibc's).
+__device__ __forceinline__ double ordered_warp_sum(double acc, double term, int count) {
+  for (int k = 0; k < count; ++k) acc += __shfl_sync(0xffffffffu, term, k);
+  return acc;
+}
 __global__ void __launch_bounds__(128) mpc_score_kernel(int B, int NS, int R, int n_dynamic, int n, double dyn_safety, double stat_safety,
                                                          const double* __restrict__ x, const double* __restrict__ prev,
                                                          const double* __restrict__ xref, const double* __restrict__ obs_c,
-                                                         const double* __restrict__ obs_semi, double* __restrict__ score) {
+                                                         const double* __restrict__ obs_semi, const double* __restrict__ obs_c_last,
+                                                         const double* __restrict__ obs_semi_last, double* __restrict__ score) {
   const int lane = threadIdx.x & 31;
   const int N = NS - 1;
   const double k05 = 0.54930614433405484570;             // atanh(0.5), mpcPlanner.cpp:830,840
   for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += (long long)gridDim.x * (blockDim.x >> 5)) {
     const double* xb = x + b * n;
     double cons = 0.0, det = 0.0, saf = 0.0;
-    for (int k = lane; k < NS; k += 32) {
-      const double px = xb[8 * k], py = xb[8 * k + 1], pz = xb[8 * k + 2];
-      if (prev && k < 10) {                                // numConsistencyStep = 10 (mpcPlanner.cpp:781)
-        const double* pv = prev + b * n + 8 * k;
-        const double dx = pv[0] - px, dy = pv[1] - py, dz = pv[2] - pz;
-        cons += sqrt(dx * dx + dy * dy + dz * dz);
-      }
-      {
-        const double* rf = xref + (b * NS + k) * 3;
-        const double dx = rf[0] - px, dy = rf[1] - py, dz = rf[2] - pz;
-        det += sqrt(dx * dx + dy * dy + dz * dz);
-      }
-      if (R > 0) {
-        // obstacle rows exist for stages 0..N-1; stage N is scored against the last prediction held
-        const int ko = k < N ? k : N - 1;
-        double dist = 0.0, tw = 0.0;
-        for (int o = 0; o < R; ++o) {
-          const long long u = ((b * N + ko) * R + o) * 3;
-          const bool dynamic = o < n_dynamic;
-          const double sd = dynamic ? dyn_safety : stat_safety;
-          // dynamic: maxSize = |full size (x, y)|; static: |half size (x, y)|   (mpcPlanner.cpp:828,838); semi = size/2 + safety
-          const double hx = obs_semi[u] - sd, hy = obs_semi[u + 1] - sd;
-          const double ms = (dynamic ? 2.0 : 1.0) * sqrt(hx * hx + hy * hy);
-          const double ex = px - obs_c[u], ey = py - obs_c[u + 1];
-          const double d = sqrt(ex * ex + ey * ey);
-          const double w = 1.0 - tanh(k05 / (sd + ms) * d);
-          dist += d * w; tw += w;
+    for (int k0 = 0; k0 < NS; k0 += 32) {
+      const int k = k0 + lane, cnt = NS - k0 < 32 ? NS - k0 : 32;
+      double tc = 0.0, td = 0.0, tsf = 0.0;
+      if (k < NS) {
+        const double px = xb[8 * k], py = xb[8 * k + 1], pz = xb[8 * k + 2];
+        if (prev && k < 10) {                              // numConsistencyStep = 10 (mpcPlanner.cpp:781)
+          const double* pv = prev + b * n + 8 * k;
+          const double dx = pv[0] - px, dy = pv[1] - py, dz = pv[2] - pz;
+          tc = sqrt(dx * dx + dy * dy + dz * dz);
         }
-        saf += dist / tw;
+        {
+          const double* rf = xref + (b * NS + k) * 3;
+          const double dx = rf[0] - px, dy = rf[1] - py, dz = rf[2] - pz;
+          td = sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        if (R > 0) {
+          // obstaclePos[j][i] for EVERY state i = 0..N (mpcPlanner.cpp:818-826): the solve holds stages 0..N-1, the
+          // prediction of stage N comes in obs_*_last
+          const double* oc = k < N ? obs_c + ((b * N + k) * R) * 3 : obs_c_last + (b * R) * 3;
+          const double* om = k < N ? obs_semi + ((b * N + k) * R) * 3 : obs_semi_last + (b * R) * 3;
+          double dist = 0.0, tw = 0.0;
+          for (int o = 0; o < R; ++o) {
+            const bool dynamic = o < n_dynamic;
+            const double sd = dynamic ? dyn_safety : stat_safety;
+            // dynamic: maxSize = |full size (x, y)|; static: |half size (x, y)|   (mpcPlanner.cpp:828,838); semi = size/2 + safety
+            const double hx = om[3 * o] - sd, hy = om[3 * o + 1] - sd;
+            const double sx = dynamic ? 2.0 * hx : hx, sy = dynamic ? 2.0 * hy : hy;
+            const double ms = sqrt(sx * sx + sy * sy);
+            const double ex = px - oc[3 * o], ey = py - oc[3 * o + 1];
+            const double d = sqrt(ex * ex + ey * ey + 0.0);
+            const double w = 1.0 - tanh(k05 / (sd + ms) * d);
+            dist += d * w; tw += w;
+          }
+          tsf = dist / tw;
+        }
       }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cons += __shfl_xor_sync(0xffffffffu, cons, o); det += __shfl_xor_sync(0xffffffffu, det, o); saf += __shfl_xor_sync(0xffffffffu, saf, o);
+      cons = ordered_warp_sum(cons, tc, cnt < 10 - k0 ? cnt : (10 - k0 > 0 ? 10 - k0 : 0));
+      det = ordered_warp_sum(det, td, cnt);
+      saf = ordered_warp_sum(saf, tsf, cnt);
     }
     if (lane == 0) {
       const int steps = NS < 10 ? NS : 10;
@@ -742,13 +754,14 @@ __global__ void mpc_select_kernel(int S, int C, int n, const int* __restrict__ c
     double avg[3] = {0.0, 0.0, 0.0};
     for (int c = 0; c < C; ++c) { const double* sc = score + (long long)cand[s * C + c] * 3; avg[0] += sc[0]; avg[1] += sc[1]; avg[2] += sc[2]; }
     avg[0] /= C; avg[1] /= C; avg[2] /= C;
-    int bi = 0; double bv = -INFINITY;
+    // weightedScore.maxCoeff(&bestTrajIdx) (mpcPlanner.cpp:883), Eigen 3.3's visitor: start from element 0, replace on a
+    // strict `>`; a NaN elsewhere never wins, a NaN in element 0 is never replaced
+    int bi = 0; double bv = 0.0;
     for (int c = 0; c < C; ++c) {
       const double* sc = score + (long long)cand[s * C + c] * 3;
-      double w = weight[s * C + c] * (avg[0] / sc[0] + avg[1] / sc[1] + sc[2] / avg[2]);
-      if (w != w) w = -INFINITY;                           // NaN never wins maxCoeff's comparison chain
+      const double w = weight[s * C + c] * (1.0 * (avg[0] / sc[0]) + 1.0 * (avg[1] / sc[1]) + 1.0 * (sc[2] / avg[2]));
       if (weighted) weighted[s * C + c] = w;
-      if (w > bv) { bv = w; bi = c; }
+      if (c == 0) bv = w; else if (w > bv) { bv = w; bi = c; }
     }
     best[s] = bi;
   }
@@ -785,11 +798,19 @@ __global__ void mpc_intent_enumerate_kernel(int S, int D, int NP, int n, const d
       s0[0] = pl[0]; s0[1] = pl[1]; s0[2] = pl[2];
       ta = atan2(pl[8 + 1] - pl[1], pl[8] - pl[0]);
     } else { s0[0] = pos[s * 3]; s0[1] = pos[s * 3 + 1]; s0[2] = pos[s * 3 + 2]; }
+    const int nterm = ((n + 5) / 13) / 3;                 // currentStatesSol_.size() / 3 (mpcPlanner.cpp:689)
     for (int j = 0; j < D; ++j) {
       const double* o = pp + ((((long long)s * D + j) * 4 + FORWARD) * NP) * 3;
       const double dx = s0[0] - o[0], dy = s0[1] - o[1], dz = s0[2] - o[2];
-      double w = sqrt(dx * dx + dy * dy + dz * dz);
-      if (prev_plan) w *= 3.0 - cos(ta - atan2(o[1] - s0[1], o[0] - s0[0]));
+      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      double w = d;
+      if (prev_plan) {
+        // the reference adds exp(-t) * d * (3 - cos(.)) for t = 0 .. size/3 - 1 with the SAME state every term and stops
+        // once the sum passes the best so far (mpcPlanner.cpp:689-702); same order of additions here
+        const double c3 = 3.0 - cos(ta - atan2(o[1] - s0[1], o[0] - s0[0]));
+        w = 0.0;
+        for (int t = 0; t < nterm; ++t) { w += exp(-(double)t) * d * c3; if (w > best) break; }
+      }
       if (w < best) { best = w; ob = j; }
     }
     const double* pr = prob + ((long long)s * D + ob) * 4;
@@ -820,21 +841,27 @@ __global__ void mpc_intent_enumerate_kernel(int S, int D, int NP, int n, const d
   }
 }
 // the obstacle rows of every candidate: centre = predicted position, semi-axes = predicted size / 2 + dynamicSafetyDist_
+// (updateObstacleParam, mpcPlanner.cpp:1160-1172) for the N stages the QP constrains, plus — in the *_last arrays — the
+// prediction of stage N, which only getSafetyScore reads (mpcPlanner.cpp:818-826)
 __global__ void mpc_intent_fill_kernel(int S, int D, int NP, int N, double safety, const double* __restrict__ pp, const double* __restrict__ ps,
                                        const int* __restrict__ row_ob, const int* __restrict__ row_it, const int* __restrict__ scen_a,
                                        const int* __restrict__ scen_b, double* __restrict__ ca, double* __restrict__ sa,
-                                       double* __restrict__ cb, double* __restrict__ sb) {
-  const long long na = (long long)4 * S * N * D, nb = (long long)2 * S * N * (D + 1);
+                                       double* __restrict__ cb, double* __restrict__ sb, double* __restrict__ la, double* __restrict__ lsa,
+                                       double* __restrict__ lb, double* __restrict__ lsb) {
+  const int NK = la ? N + 1 : N;                          // stage N goes to the *_last arrays
+  const long long na = (long long)4 * S * NK * D, nb = (long long)2 * S * NK * (D + 1);
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < na + nb; t += (long long)gridDim.x * blockDim.x) {
     const bool two = t >= na;
     const long long u = two ? t - na : t;
     const int R = two ? D + 1 : D;
-    const int o = (int)(u % R); const long long bk = u / R; const int k = (int)(bk % N); const int b = (int)(bk / N);
+    const int o = (int)(u % R); const long long bk = u / R; const int k = (int)(bk % NK); const int b = (int)(bk / NK);
     const int row = two ? 4 * S + b : b;
     const int s = two ? scen_b[b] : scen_a[b];
     const int j = row_ob[(long long)row * (D + 1) + o], it = row_it[(long long)row * (D + 1) + o];
     const long long src = ((((long long)s * D + j) * 4 + it) * NP + k) * 3;
-    double* c = (two ? cb : ca) + u * 3; double* m = (two ? sb : sa) + u * 3;
+    double* c; double* m;
+    if (k < N) { const long long v = (((long long)b * N + k) * R + o) * 3; c = (two ? cb : ca) + v; m = (two ? sb : sa) + v; }
+    else { const long long v = ((long long)b * R + o) * 3; c = (two ? lb : la) + v; m = (two ? lsb : lsa) + v; }
     c[0] = pp[src]; c[1] = pp[src + 1]; c[2] = pp[src + 2];
     m[0] = ps[src] / 2 + safety; m[1] = ps[src + 1] / 2 + safety; m[2] = ps[src + 2] / 2 + safety;
   }
@@ -850,8 +877,13 @@ __global__ void mpc_gather_rows_kernel(long long B, int w, const int* __restrict
 extern "C" int mpcqp_intent_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t S, int32_t D, int32_t NP,
                                               const double* pred_pos, const double* pred_size, const double* prob, const double* prev_plan,
                                               const double* pos, int32_t* scen_a, int32_t* scen_b, double* obs_c_a, double* obs_semi_a,
-                                              double* obs_c_b, double* obs_semi_b, double* weight, int32_t* cand) {
+                                              double* obs_c_b, double* obs_semi_b, double* obs_c_last_a, double* obs_semi_last_a,
+                                              double* obs_c_last_b, double* obs_semi_last_b, double* weight, int32_t* cand) {
   if (!e) return MPCQP_ERR_ARG;
+  const bool want_last = obs_c_last_a || obs_semi_last_a || obs_c_last_b || obs_semi_last_b;
+  if (want_last && (!obs_c_last_a || !obs_semi_last_a || !obs_c_last_b || !obs_semi_last_b || !p || NP < p->horizon)) {
+    e->err = "the stage-N obstacle arrays need all four pointers and predictions of at least `horizon` steps"; return MPCQP_ERR_ARG;
+  }
   if (!p || S <= 0 || D <= 0 || D > 31 || NP < p->horizon - 1 || !pred_pos || !pred_size || !prob || (!prev_plan && !pos) || !scen_a || !scen_b ||
       !obs_c_a || !obs_semi_a || !obs_c_b || !obs_semi_b || !weight || !cand) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
   CK(cudaSetDevice(e->device));
@@ -861,11 +893,13 @@ extern "C" int mpcqp_intent_candidates_device(mpcqp_engine* e, const mpcqp_mpc_p
   mpc_intent_enumerate_kernel<<<(unsigned)((S + 127) / 128), 128, 0, e->stream>>>(S, D, NP, n, pred_pos, prob, prev_plan, pos, row_ob, row_it,
                                                                                     scen_a, scen_b, weight, cand);
   CK(cudaGetLastError());
-  const long long total = (long long)4 * S * N * D + (long long)2 * S * N * (D + 1);
+  const int NK = want_last ? N + 1 : N;
+  const long long total = (long long)4 * S * NK * D + (long long)2 * S * NK * (D + 1);
   long long blocks = (total + 255) / 256; const long long cap = (long long)e->num_sms * 16;
   if (blocks > cap) blocks = cap;
   mpc_intent_fill_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(S, D, NP, N, p->dynamic_safety_dist, pred_pos, pred_size, row_ob, row_it,
-                                                                   scen_a, scen_b, obs_c_a, obs_semi_a, obs_c_b, obs_semi_b);
+                                                                   scen_a, scen_b, obs_c_a, obs_semi_a, obs_c_b, obs_semi_b,
+                                                                   obs_c_last_a, obs_semi_last_a, obs_c_last_b, obs_semi_last_b);
   CK(cudaGetLastError());
   return MPCQP_OK;
 }
@@ -883,15 +917,19 @@ extern "C" int mpcqp_gather_rows_device(mpcqp_engine* e, int64_t B, int32_t widt
 
 extern "C" int mpcqp_score_candidates_device(mpcqp_engine* e, const mpcqp_mpc_params* p, int32_t B, int32_t R, int32_t n_dynamic,
                                              const double* x, const double* prev_plan, const double* xref, const double* obs_c,
-                                             const double* obs_semi, double* score) {
+                                             const double* obs_semi, const double* obs_c_last, const double* obs_semi_last, double* score) {
   if (!e) return MPCQP_ERR_ARG;
   if (!p || B <= 0 || R < 0 || n_dynamic < 0 || n_dynamic > R || !x || !xref || !score || (R > 0 && (!obs_c || !obs_semi))) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
+  if (R > 0 && (!obs_c_last || !obs_semi_last)) {
+    e->err = "getSafetyScore reads the obstacle prediction of stage N as well (mpcPlanner.cpp:818-826): obs_c_last / obs_semi_last are required";
+    return MPCQP_ERR_ARG;
+  }
   CK(cudaSetDevice(e->device));
   const int NS = p->horizon, n = 8 * NS + 5 * (NS - 1);
   long long blocks = ((long long)B + 3) / 4; const long long cap = (long long)e->num_sms * 16;
   if (blocks > cap) blocks = cap;
   mpc_score_kernel<<<(unsigned)blocks, 128, 0, e->stream>>>(B, NS, R, n_dynamic, n, p->dynamic_safety_dist, p->static_safety_dist, x, prev_plan,
-                                                              xref, obs_c, obs_semi, score);
+                                                              xref, obs_c, obs_semi, obs_c_last, obs_semi_last, score);
   CK(cudaGetLastError());
   return MPCQP_OK;
 }

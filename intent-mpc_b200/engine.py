@@ -222,11 +222,13 @@ class Engine:
 
     # ---- candidate scoring / selection on the device (getTrajectoryScore, evaluateTraj) --------------------------
     def score_candidates_ptr(self, params, B: int, R: int, n_dynamic: int, ptrs: dict):
-        """ptrs: device addresses for x, prev_plan (0 = first control step), xref, obs_c, obs_semi, score.  Asynchronous."""
+        """ptrs: device addresses for x, prev_plan (0 = first control step), xref, obs_c, obs_semi, obs_c_last, obs_semi_last
+        (stage N, [B][R][3]), score.  Asynchronous."""
         p = params_to_c(params)
         g = lambda k: C.c_void_p(ptrs.get(k) or None)
         self._check(self.lib.mpcqp_score_candidates_device(self.h, C.byref(p), C.c_int32(B), C.c_int32(R), C.c_int32(n_dynamic),
-                                                           g("x"), g("prev_plan"), g("xref"), g("obs_c"), g("obs_semi"), g("score")))
+                                                           g("x"), g("prev_plan"), g("xref"), g("obs_c"), g("obs_semi"), g("obs_c_last"),
+                                                           g("obs_semi_last"), g("score")))
 
     def select_candidates_ptr(self, S: int, Cn: int, n: int, ptrs: dict):
         """ptrs: device addresses for cand [S][C] int32, weight [S][C], score, x_all, best [S] int32, weighted (optional),
@@ -237,12 +239,14 @@ class Engine:
 
     def intent_candidates_ptr(self, params, S: int, D: int, NP: int, ptrs: dict):
         """ptrs: device addresses for pred_pos, pred_size, prob, prev_plan (0 on the first step), pos, scen_a, scen_b, obs_c_a,
-        obs_semi_a, obs_c_b, obs_semi_b, weight, cand.  Asynchronous on the engine stream."""
+        obs_semi_a, obs_c_b, obs_semi_b, obs_c_last_a, obs_semi_last_a, obs_c_last_b, obs_semi_last_b (stage N for the scoring;
+        all four or none), weight, cand.  Asynchronous on the engine stream."""
         p = params_to_c(params)
         g = lambda k: C.c_void_p(ptrs.get(k) or None)
         self._check(self.lib.mpcqp_intent_candidates_device(self.h, C.byref(p), C.c_int32(S), C.c_int32(D), C.c_int32(NP), g("pred_pos"),
                                                             g("pred_size"), g("prob"), g("prev_plan"), g("pos"), g("scen_a"), g("scen_b"),
-                                                            g("obs_c_a"), g("obs_semi_a"), g("obs_c_b"), g("obs_semi_b"), g("weight"), g("cand")))
+                                                            g("obs_c_a"), g("obs_semi_a"), g("obs_c_b"), g("obs_semi_b"), g("obs_c_last_a"),
+                                                            g("obs_semi_last_a"), g("obs_c_last_b"), g("obs_semi_last_b"), g("weight"), g("cand")))
 
     def gather_rows_ptr(self, B: int, width: int, idx_ptr: int, src_ptr: int, dst_ptr: int):
         self._check(self.lib.mpcqp_gather_rows_device(self.h, C.c_int64(B), C.c_int32(width), C.c_void_p(idx_ptr), C.c_void_p(src_ptr),

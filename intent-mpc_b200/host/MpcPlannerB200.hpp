@@ -77,6 +77,7 @@ class mpcPlanner {
     std::vector<Vec3> xRef; getReferenceTraj(xRef);
     std::vector<std::vector<double>> st, ct;
     const bool ok = solveTraj(so, dp, ds, st, ct, xRef);
+    candidateStatus_ = lastStatus_; candidateIter_ = lastIter_;
     if (ok) { currentStatesSol_ = st; currentControlsSol_ = ct; firstTime_ = false; ref_ = xRef; }
     return ok;
   }
@@ -93,6 +94,7 @@ class mpcPlanner {
       // the candidates of one control step as batches of equal obstacle count
       std::vector<std::vector<std::vector<double>>> st(combPos.size()), ct(combPos.size());
       std::vector<char> solved(combPos.size(), 0);
+      std::vector<int> cst(combPos.size(), MPCQP_UNSOLVED), cit(combPos.size(), 0);
       std::vector<size_t> counts;
       for (auto& c : combPos) if (std::find(counts.begin(), counts.end(), c.size()) == counts.end()) counts.push_back(c.size());
       for (size_t cnt : counts) {
@@ -101,8 +103,13 @@ class mpcPlanner {
         std::vector<const std::vector<ObTraj>*> pp, ss;
         for (int i : idx) { pp.push_back(&combPos[(size_t)i]); ss.push_back(&combSize[(size_t)i]); }
         std::vector<std::vector<std::vector<double>>> bst, bct;
-        if (solveBatch(so, pp, ss, xRef, bst, bct)) for (size_t a = 0; a < idx.size(); ++a) { st[(size_t)idx[a]] = bst[a]; ct[(size_t)idx[a]] = bct[a]; solved[(size_t)idx[a]] = 1; }
+        if (solveBatch(so, pp, ss, xRef, bst, bct)) for (size_t a = 0; a < idx.size(); ++a) {
+          st[(size_t)idx[a]] = bst[a]; ct[(size_t)idx[a]] = bct[a]; solved[(size_t)idx[a]] = 1;
+          cst[(size_t)idx[a]] = lastStatus_[a]; cit[(size_t)idx[a]] = lastIter_[a];
+        }
       }
+      candidateStatus_.clear(); candidateIter_.clear();
+      for (size_t i = 0; i < combPos.size(); ++i) if (solved[i]) { candidateStatus_.push_back(cst[i]); candidateIter_.push_back(cit[i]); }
       std::vector<std::vector<std::vector<double>>> cs, cc; std::vector<Vec3> score; std::vector<int> intentType;
       for (size_t i = 0; i < combPos.size(); ++i) if (solved[i]) {
         cs.push_back(st[i]); cc.push_back(ct[i]);
@@ -119,6 +126,7 @@ class mpcPlanner {
       candidateStates_.clear(); candidateControls_.clear(); trajWeightedScore_.clear(); trajScore_.clear();
       std::vector<std::vector<double>> st, ct;
       valid = solveTraj(so, dp, ds, st, ct, xRef);
+      candidateStatus_ = lastStatus_; candidateIter_ = lastIter_;
       if (valid) { currentStatesSol_ = st; currentControlsSol_ = ct; firstTime_ = false; ref_ = xRef; }
     }
     return valid;
@@ -147,8 +155,12 @@ class mpcPlanner {
   double getTs() const { return p_.ts; }
   double getHorizon() const { return p_.horizon; }
   double getLastQpSolveTime() const { return lastQpSolveTime_; }       // device + transfer time of the last batched solve, seconds
-  const std::vector<int>& lastStatus() const { return lastStatus_; }   // OSQP status per candidate of the last solve (the reference never looks)
-  const std::vector<int>& lastIterations() const { return lastIter_; }
+  const std::vector<int>& lastStatus() const { return candidateStatus_; }   // OSQP status per QP of the last plan call, in candidate order (the reference never looks)
+  const std::vector<int>& lastIterations() const { return candidateIter_; }
+  const std::vector<Vec3>& trajScore() const { return trajScore_; }       // (consistency, detour, safety) per candidate
+  const std::vector<std::vector<std::vector<double>>>& candidateStates() const { return candidateStates_; }
+  const std::vector<std::vector<std::vector<double>>>& candidateControls() const { return candidateControls_; }
+  int closestObstacle() const { return obIdx_; }
   const std::vector<double>& trajWeightedScore() const { return trajWeightedScore_; }
   int bestCandidate() const { return bestIdx_; }
   const std::vector<std::vector<double>>& currentStates() const { return currentStatesSol_; }
@@ -236,11 +248,12 @@ class mpcPlanner {
     ca /= (double)score.size(); da /= (double)score.size(); sa /= (double)score.size();
     const auto& pr = obIntentProb_[(size_t)obIdx];
     const double w[6] = {pr[STOP], pr[LEFT], pr[RIGHT], pr[FORWARD], std::max(pr[LEFT], pr[FORWARD]), std::max(pr[RIGHT], pr[FORWARD])};
-    int best = 0; double bs = -INFINITY;
+    // weightedScore.maxCoeff(&bestTrajIdx): Eigen 3.3's visitor starts from element 0 and replaces on a strict `>`
+    int best = 0; double bs = 0.0;
     for (size_t i = 0; i < score.size(); ++i) {
-      const double v = w[intentType[i]] * (ca / score[i][0] + da / score[i][1] + score[i][2] / sa);
+      const double v = w[intentType[i]] * (1.0 * (ca / score[i][0]) + 1.0 * (da / score[i][1]) + 1.0 * (score[i][2] / sa));
       trajWeightedScore_.push_back(v);
-      if (v > bs) { bs = v; best = (int)i; }
+      if (i == 0) bs = v; else if (v > bs) { bs = v; best = (int)i; }
     }
     return best;
   }
@@ -320,7 +333,7 @@ class mpcPlanner {
   std::vector<std::vector<double>> currentStatesSol_, currentControlsSol_;
   std::vector<std::vector<std::vector<double>>> candidateStates_, candidateControls_;
   std::vector<double> trajWeightedScore_;
-  std::vector<int> lastStatus_, lastIter_;
+  std::vector<int> lastStatus_, lastIter_, candidateStatus_, candidateIter_;
 };
 
 }  // namespace trajPlannerB200

@@ -1,12 +1,14 @@
-"""Device-resident control step for BASELINE.json configs[2]: the same loop as `receding.IntentSweep.step`, with every
+"""Device-resident control step for BASELINE.json configs[2]: S scenarios advance together, with every
 array of a step on the GPU and `makePlanWithPred` (mpcPlanner.cpp:571-661) chained from the engine's own calls —
 enumeration (`mpcqp_intent_candidates_device`), replication of the scenario-level inputs (`mpcqp_gather_rows_device`), the
 two solves (`mpcqp_solve_mpc_batch_device`), scoring (`mpcqp_score_candidates_device`) and choice
 (`mpcqp_select_candidates_device`).  torch only holds the buffers and evaluates the closed-form obstacle predictions and
-the reference window (elementwise arithmetic); no QP data crosses PCIe between steps.
+the reference window (elementwise arithmetic); no QP data crosses PCIe between steps.  With `host_predictions=True` the
+predictions are evaluated on the host (numpy, `IntentSweep.predictions`) and uploaded every step and the chosen plan is
+downloaded — the end-to-end form with host buffers that bench.py times for configs[2].
 
-The scenario state starts from a host `IntentSweep` (same seeds, same obstacles), so the two drivers can be compared
-step by step (tests/test_receding.py)."""
+The scenario state starts from a host `IntentSweep` (scenario generator: seeds, obstacles).  The tests compare every piece of a
+step with the literal restatement of the reference planner in oracle/mpc_planner.py (tests/test_planner_parity.py)."""
 from __future__ import annotations
 
 import numpy as np
@@ -17,8 +19,10 @@ from .receding import IntentSweep, FORWARD, LEFT, RIGHT, STOP
 
 
 class DeviceIntentSweep:
-    def __init__(self, eng: E.Engine, host: IntentSweep, device: int = 0):
+    def __init__(self, eng: E.Engine, host: IntentSweep, device: int = 0, host_predictions: bool = False):
         self.eng, self.p, self.S, self.D = eng, host.p, host.S, host.D
+        self.host, self.host_predictions = host, host_predictions
+        self.h2d_bytes = 0; self.d2h_bytes = 0
         self.dev = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(eng.stream, device=self.dev)
         self.st = E.default_settings()
@@ -35,6 +39,9 @@ class DeviceIntentSweep:
             scen_a=torch.empty(4 * S, **i32), scen_b=torch.empty(2 * S, **i32), weight=torch.empty((S, 6), **f64), cand=torch.empty((S, 6), **i32),
             obs_c_a=torch.empty((4 * S, N, D, 3), **f64), obs_semi_a=torch.empty((4 * S, N, D, 3), **f64), obs_yaw_a=torch.zeros((4 * S, N, D), **f64),
             obs_c_b=torch.empty((2 * S, N, D + 1, 3), **f64), obs_semi_b=torch.empty((2 * S, N, D + 1, 3), **f64), obs_yaw_b=torch.zeros((2 * S, N, D + 1), **f64),
+            # stage N of every candidate's obstacle rows: only the safety score reads it (mpcPlanner.cpp:818-826)
+            obs_c_last_a=torch.empty((4 * S, D, 3), **f64), obs_semi_last_a=torch.empty((4 * S, D, 3), **f64),
+            obs_c_last_b=torch.empty((2 * S, D + 1, 3), **f64), obs_semi_last_b=torch.empty((2 * S, D + 1, 3), **f64),
             x0=torch.empty((6 * S, 6), **f64), xref=torch.empty((6 * S, N + 1, 3), **f64), lin=torch.empty((6 * S, N, 3), **f64),
             warm=torch.empty((6 * S, n), **f64), x=torch.empty((6 * S, n), **f64), status=torch.empty(6 * S, **i32), iter=torch.empty(6 * S, **i32),
             rho_updates=torch.empty(6 * S, **i32), obj=torch.empty(6 * S, **f64), pri_res=torch.empty(6 * S, **f64), dua_res=torch.empty(6 * S, **f64),
@@ -50,6 +57,10 @@ class DeviceIntentSweep:
         return self.centre + torch.stack([x, y, z], dim=-1)
 
     def predictions(self):
+        if self.host_predictions:                          # numpy on the host, uploaded (the e2e form)
+            pp, ps = self.host.predictions(self.step_idx)
+            self.h2d_bytes += pp.nbytes + ps.nbytes
+            return torch.from_numpy(pp).to(self.dev, non_blocking=False), torch.from_numpy(ps).to(self.dev, non_blocking=False)
         T = 31
         t0 = self.step_idx * self.p.ts
         pos = self._trefoil(t0); vel = (self._trefoil(t0 + 1e-3) - pos) / 1e-3
@@ -97,7 +108,8 @@ class DeviceIntentSweep:
             else:
                 pp, ps = self.predictions()
                 lin = self.plan[:, : 8 * (N + 1)].reshape(S, N + 1, 8)[:, :N, 0:3].contiguous()
-                ptrs = {k: b[k].data_ptr() for k in ("scen_a", "scen_b", "obs_c_a", "obs_semi_a", "obs_c_b", "obs_semi_b", "weight", "cand")}
+                ptrs = {k: b[k].data_ptr() for k in ("scen_a", "scen_b", "obs_c_a", "obs_semi_a", "obs_c_b", "obs_semi_b", "obs_c_last_a",
+                                                     "obs_semi_last_a", "obs_c_last_b", "obs_semi_last_b", "weight", "cand")}
                 ptrs.update(pred_pos=pp.data_ptr(), pred_size=ps.data_ptr(), prob=self.prob.data_ptr(), pos=self.pos.data_ptr(), prev_plan=self.plan.data_ptr())
                 eng.intent_candidates_ptr(p, S, D, pp.shape[3], ptrs)
                 for src, name, w in ((x0, "x0", 6), (xref, "xref", 3 * (N + 1)), (lin, "lin", 3 * N), (self.plan, "warm", n)):
@@ -105,9 +117,11 @@ class DeviceIntentSweep:
                     eng.gather_rows_ptr(2 * S, w, b["scen_b"].data_ptr(), src.data_ptr(), b[name][4 * S:].data_ptr())
                 self._solve(4 * S, D, 0, (b["obs_c_a"], b["obs_semi_a"], b["obs_yaw_a"]))
                 self._solve(2 * S, D + 1, 4 * S, (b["obs_c_b"], b["obs_semi_b"], b["obs_yaw_b"]))
-                for B_, R_, off, oc, osz in ((4 * S, D, 0, b["obs_c_a"], b["obs_semi_a"]), (2 * S, D + 1, 4 * S, b["obs_c_b"], b["obs_semi_b"])):
+                for B_, R_, off, sfx in ((4 * S, D, 0, "a"), (2 * S, D + 1, 4 * S, "b")):
                     eng.score_candidates_ptr(p, B_, R_, R_, {"x": b["x"][off:].data_ptr(), "prev_plan": b["warm"][off:].data_ptr(), "xref": b["xref"][off:].data_ptr(),
-                                                            "obs_c": oc.data_ptr(), "obs_semi": osz.data_ptr(), "score": b["score"][off:].data_ptr()})
+                                                            "obs_c": b["obs_c_" + sfx].data_ptr(), "obs_semi": b["obs_semi_" + sfx].data_ptr(),
+                                                            "obs_c_last": b["obs_c_last_" + sfx].data_ptr(), "obs_semi_last": b["obs_semi_last_" + sfx].data_ptr(),
+                                                            "score": b["score"][off:].data_ptr()})
                 eng.select_candidates_ptr(S, 6, n, {"cand": b["cand"].data_ptr(), "weight": b["weight"].data_ptr(), "score": b["score"].data_ptr(),
                                                     "x_all": b["x"].data_ptr(), "best": b["best"].data_ptr(), "weighted": b["weighted"].data_ptr(),
                                                     "plan": b["plan"].data_ptr()})
@@ -116,5 +130,27 @@ class DeviceIntentSweep:
             st = self.plan[:, : 8 * (N + 1)].reshape(S, N + 1, 8)
             self.pos = st[:, 1, 0:3].contiguous(); self.vel = st[:, 1, 3:6].contiguous()   # perfect tracking (mpc_node.cpp:223-224)
             self.step_idx += 1
+            if self.host_predictions:                      # what a host-side caller reads back every step: the accepted plan
+                self.plan_host = self.plan.cpu(); self.d2h_bytes += self.plan.numel() * 8
         self.stream.synchronize()
+        self.had_candidates = best is not None
         return best
+
+    def batches_host(self):
+        """The solve batches of the LAST step as host `MpcBatch`es with their outputs (for oracle checks): one obstacle-free
+        batch after the first step, else [4S rows with D obstacle rows per stage, 2S rows with D + 1]."""
+        from .workloads import MpcBatch
+        p, S, D, b = self.p, self.S, self.D, self.buf
+        N = p.N
+        h = lambda t: t.detach().cpu().numpy()
+        outs = lambda lo, hi: {k: h(b[k][lo:hi]) for k in ("x", "status", "iter", "rho_updates", "obj", "pri_res", "dua_res")}
+        if not getattr(self, "had_candidates", False):
+            z = np.zeros((S, N, 0, 3))
+            mb = MpcBatch(p, h(b["x0"][:S]), h(b["xref"][:S]), z, z.copy(), np.zeros((S, N, 0)), np.zeros((N, 0), dtype=np.int32), h(b["lin"][:S]), h(b["warm"][:S]))
+            return [(mb, outs(0, S))]
+        res = []
+        for lo, hi, R, sfx in ((0, 4 * S, D, "a"), (4 * S, 6 * S, D + 1, "b")):
+            mb = MpcBatch(p, h(b["x0"][lo:hi]), h(b["xref"][lo:hi]), h(b["obs_c_" + sfx]), h(b["obs_semi_" + sfx]), h(b["obs_yaw_" + sfx]),
+                          np.ones((N, R), dtype=np.int32), h(b["lin"][lo:hi]), h(b["warm"][lo:hi]))
+            res.append((mb, outs(lo, hi)))
+        return res

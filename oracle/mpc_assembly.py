@@ -155,6 +155,61 @@ def ellipsoid_linearisation(c, oxyz, osize, yaw):
     return fxx, fyy, fzz, low
 
 
+_PATTERN_CACHE = {}
+
+
+def _constraint_pattern(N, num_obs, nhs, is_dyn, Adf, Bdf):
+    """Entry list of castMPCToQPConstraintMatrix in the reference's insertion order (MP.cpp:989-1071) and its CSC sort."""
+    key = (N, num_obs, nhs, is_dyn.tobytes(), Adf.tobytes(), Bdf.tobytes())
+    hit = _PATTERN_CACHE.get(key)
+    if hit is not None:
+        return hit
+    nx, nu = NUM_STATES, NUM_CONTROLS
+    n = nx * (N + 1) + nu * N
+    rows, cols, kind, aux = [], [], [], []      # kind: 0 const value, 1 obstacle gradient (aux=(k,j,c)), 2 half-space
+    def add(r, c, v): rows.append(r); cols.append(c); kind.append(0); aux.append(v)
+    for i in range(nx * (N + 1)):
+        add(i, i, -1.0)
+    for i in range(N):
+        for j in range(nx):
+            for k in range(nx):
+                if Adf[j, k] != 0: add(nx * (i + 1) + j, nx * i + k, Adf[j, k])
+    for i in range(N):
+        for j in range(nx):
+            for k in range(nu):
+                if Bdf[j, k] != 0: add(nx * (i + 1) + j, nu * i + k + nx * (N + 1), Bdf[j, k])
+    for i in range(n):
+        add(i + (N + 1) * nx, i, 1.0)
+    base_hs = 2 * nx * (N + 1) + nu * N
+    if nhs:
+        for i in range(N):
+            for which, comp in [(0, 0), (0, 1), (1, 0), (1, 1)]:
+                rr = base_hs + nhs * i + which
+                rows.append(rr); cols.append(nx * i + comp); kind.append(2); aux.append((which, comp))
+    base_ob = base_hs + nhs * N
+    for i in range(N):
+        for j in range(num_obs):
+            r = base_ob + i * num_obs + j
+            for c in range(3):
+                rows.append(r); cols.append(nx * i + c); kind.append(1); aux.append((i, j, c))
+            sc = 3 if is_dyn[i, j] else 4
+            add(r, nx * (N + 1) + nu * i + sc, -1.0)
+    rows = np.array(rows, dtype=np.int64); cols = np.array(cols, dtype=np.int64)
+    order = np.lexsort((rows, cols))
+    A_rowidx = rows[order]
+    A_colptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(A_colptr, cols + 1, 1)
+    A_colptr = np.cumsum(A_colptr)
+    kind = np.array(kind)
+    const_pos = np.nonzero(kind == 0)[0]; const_val = np.array([aux[e] for e in const_pos], dtype=np.float64)
+    grad_pos = np.nonzero(kind == 1)[0]; grad_idx = np.array([aux[e] for e in grad_pos], dtype=np.int64).reshape(-1, 3)
+    hs_pos = np.nonzero(kind == 2)[0]; hs_idx = np.array([aux[e] for e in hs_pos], dtype=np.int64).reshape(-1, 2)
+    out = (A_colptr, A_rowidx, order, const_pos, const_val, grad_pos, grad_idx, hs_pos, hs_idx, len(rows))
+    if len(_PATTERN_CACHE) < 64:
+        _PATTERN_CACHE[key] = out
+    return out
+
+
 @dataclasses.dataclass
 class QpBatch:
     """B problems sharing one CSC pattern (what OsqpEigen::Data would hold per problem)."""
@@ -207,57 +262,22 @@ def assemble_batch(p: MpcParams, x0, xref, oxyz, osize, yaw, is_dyn, lin_pt, war
     xr = np.zeros((B, N + 1, nx)); xr[:, :, 0:3] = xref
     q[:, : nx * (N + 1)] = (-(xr) * Q[None, None, :]).reshape(B, -1)
 
-    # ---- A pattern (MP.cpp:989-1071) as COO, then sorted into CSC
-    rows, cols, kind, aux = [], [], [], []      # kind: 0 const value, 1 obstacle gradient (aux=(k,j,c)), 2 half-space
-    def add(r, c, v): rows.append(r); cols.append(c); kind.append(0); aux.append(v)
-    for i in range(nx * (N + 1)):
-        add(i, i, -1.0)
-    for i in range(N):
-        for j in range(nx):
-            for k in range(nx):
-                if Adf[j, k] != 0: add(nx * (i + 1) + j, nx * i + k, Adf[j, k])
-    for i in range(N):
-        for j in range(nx):
-            for k in range(nu):
-                if Bdf[j, k] != 0: add(nx * (i + 1) + j, nu * i + k + nx * (N + 1), Bdf[j, k])
-    for i in range(n):
-        add(i + (N + 1) * nx, i, 1.0)
-    base_hs = 2 * nx * (N + 1) + nu * N
-    hs_entries = []
-    if nhs:
-        for i in range(N):
-            for r, (which, comp) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
-                rr = base_hs + nhs * i + which
-                rows.append(rr); cols.append(nx * i + comp); kind.append(2); aux.append((which, comp))
-    base_ob = base_hs + nhs * N
-    for i in range(N):
-        for j in range(num_obs):
-            r = base_ob + i * num_obs + j
-            for c in range(3):
-                rows.append(r); cols.append(nx * i + c); kind.append(1); aux.append((i, j, c))
-            sc = 3 if is_dyn[i, j] else 4
-            add(r, nx * (N + 1) + nu * i + sc, -1.0)
-    rows = np.array(rows, dtype=np.int64); cols = np.array(cols, dtype=np.int64)
-    order = np.lexsort((rows, cols))
-    A_rowidx = rows[order]
-    A_colptr = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(A_colptr, cols + 1, 1)
-    A_colptr = np.cumsum(A_colptr)
+    # ---- A pattern (MP.cpp:989-1071) as COO, then sorted into CSC (cached per shape: the pattern depends only on the
+    # horizon, the obstacle count, the half-space count and the slack column of every obstacle row)
+    A_colptr, A_rowidx, order, const_pos, const_val, grad_pos, grad_idx, hs_pos, hs_idx, n_entries = \
+        _constraint_pattern(N, num_obs, nhs, np.ascontiguousarray(is_dyn, dtype=np.int32), Adf, Bdf)
 
     # ---- values
     fxx, fyy, fzz, low = ellipsoid_linearisation(np.asarray(lin_pt)[:, :, None, :], oxyz, osize, yaw) \
         if num_obs else (None, None, None, np.zeros((B, N, 0)))
-    grads = (fxx, fyy, fzz)
-    vals = np.zeros((B, len(rows)))
-    for e, (kd, ax) in enumerate(zip(kind, aux)):
-        if kd == 0:
-            vals[:, e] = ax
-        elif kd == 1:
-            i, j, c = ax
-            vals[:, e] = grads[c][:, i, j]
-        else:
-            which, comp = ax
-            vals[:, e] = half_space[which][:, comp]
+    vals = np.zeros((B, n_entries))
+    vals[:, const_pos] = const_val[None, :]
+    if num_obs:
+        grads = np.stack([fxx, fyy, fzz], axis=1)                    # [B, 3, N, numObs]
+        vals[:, grad_pos] = grads[:, grad_idx[:, 2], grad_idx[:, 0], grad_idx[:, 1]]
+    if nhs:
+        hsv = np.stack([np.asarray(half_space[0]), np.asarray(half_space[1])], axis=1)   # [B, 2, 3]
+        vals[:, hs_pos] = hsv[:, hs_idx[:, 0], hs_idx[:, 1]]
     A_val = vals[:, order]
 
     # ---- l, u (MP.cpp:1074-1146)
