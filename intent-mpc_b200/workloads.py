@@ -154,12 +154,12 @@ def snapshot(params: MpcParams | None = None) -> MpcBatch:
     return MpcBatch(p, x0, xref, obs_c, obs_semi, obs_yaw, obs_dyn, lin_pt, warm_x)
 
 
-def stress_batch(B: int, seed0: int = 0, num_obs: int = 2) -> MpcBatch:
+def stress_batch(B: int, seed0: int = 0, num_obs: int = 2, horizon: int = 60) -> MpcBatch:
     """BASELINE.json configs[3]: doubled horizon, tight bounds and infeasible instances (SURVEY.md §8d
     "Config 4"): horizon 60, maxVel = maxAcc = 1.5, z in [1.9, 2.1].  Instance b cycles through four kinds:
     0 nominal inside the bounds, 1 start above the z box (oracle: status -2 after 4000 iterations),
     2 initial speed above maxVel (same), 3 an obstacle whose ellipsoid contains the start (slack saturation)."""
-    p = MpcParams(horizon=60, max_vel=1.5, max_acc=1.5, z_min=1.9, z_max=2.1)
+    p = MpcParams(horizon=horizon, max_vel=1.5, max_acc=1.5, z_min=1.9, z_max=2.1)
     mb = static_batch(B, num_obs=num_obs, params=p, seed0=seed0 + 100000)
     N = p.N
     for b in range(B):

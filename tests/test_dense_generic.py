@@ -176,3 +176,44 @@ def test_dense_batch_of_candidate_paths_against_oracle_and_repeatable():
     assert np.abs((r["obj"][ok] - want["obj"][ok]) / want["obj"][ok]).max() < TOL
     assert rel_inf(r["x"][~ok], want["x"][~ok]).max(initial=0.0) < TOL_STALLED
     assert (r["x"] == r2["x"]).all() and (r["iter"] == r2["iter"]).all()
+
+
+# ---- mpcPlanner QPs with the field-of-view half-space rows (mpcPlanner.cpp:265-297, 1027-1038, 1102-1111) ---------------------
+FOV_GOLD = os.path.join(os.path.dirname(__file__), "golden", "fov_ref_golden.npz")
+
+
+def _check_fov(got, g, tol=TOL):
+    assert (np.asarray(got["status"]) == g["fov_status"]).all(), (got["status"], g["fov_status"])
+    assert (np.asarray(got["iter"]) == g["fov_iter"]).all(), (got["iter"], g["fov_iter"])
+    assert (np.asarray(got["rho_updates"]) == g["fov_rho_updates"]).all()
+    assert rel_inf(got["x"], g["fov_x"]).max() < tol
+    assert np.abs((np.asarray(got["obj"]) - g["fov_obj"]) / g["fov_obj"]).max() < tol
+
+
+def test_oracle_port_matches_reference_golden_with_fov_rows():
+    from oracle import bindings as OB
+    from tests.golden import fov_cases as FC
+    _check_fov(OB.PortOsqp().solve_batch(FC.case(), want_y=True, nthreads=4), np.load(FOV_GOLD))
+
+
+@pytest.mark.gpu
+def test_planner_qp_with_fov_half_space_rows_runs_on_the_generic_path():
+    """The 3-argument updateCurrStates adds two half-space rows per stage; such a QP has no slack column on those rows, so it
+    is not the structure the stage kernels take: mpcqp_setup routes it to the dense generic kernel (n + m = 1126 + 58)."""
+    from intent_mpc_b200 import engine as E
+    from tests.golden import fov_cases as FC
+    eng = E.Engine(0)
+    try:
+        qb = FC.case()
+        got = dict(status=[], iter=[], rho_updates=[], obj=[], x=[])
+        for b in range(qb.q.shape[0]):
+            pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[b], qb.q[b], qb.A_colptr, qb.A_rowidx, qb.A_val[b], qb.l[b], qb.u[b])
+            pr.warm_start(qb.warm_x[b], np.zeros(qb.m))
+            r = pr.solve()
+            assert eng.last_path == "dense"
+            for k in got:
+                got[k].append(r[k])
+            pr.close()
+        _check_fov({k: np.asarray(v) for k, v in got.items()}, np.load(FOV_GOLD))
+    finally:
+        eng.close()
