@@ -60,6 +60,9 @@ struct Shape {              // batch-uniform problem shape, passed by value
   int n, m;
   double a_pv, b_pa, b_va;  // dynamics coefficients as the reference inserts them (float-rounded, MP.cpp:1003,1014)
   double blo[NV], bhi[NV];  // box bounds on (x_k, u_k), stage-uniform (MP.cpp:904-921)
+  double obs_hi;            // upper bound of every obstacle row: IEEE +inf as the reference writes it (MP.cpp:1139), or the finite
+                            // "infinity" of a caller of the CSC entry points (OSQP_INFTY = 1e30): OSQP's primal-infeasibility
+                            // certificate multiplies this bound by a zero multiplier — NaN with inf, 0 with 1e30
 };
 
 struct Settings {           // third_party/osqp/types.h:139-176 (subset that affects the iterates)
@@ -329,7 +332,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   MQ_HD void row_bounds(int k, int i, double& lo, double& hi) const {
     if (i < 8) { double v = (k == 0) ? -x0p[i] : 0.0; lo = v; hi = v; }
     else if (i < NBR) { lo = box_lo(i - 8); hi = box_hi(i - 8); }
-    else { lo = LO_(i - NBR, k); hi = INFINITY; }
+    else { lo = LO_(i - NBR, k); hi = sh.obs_hi; }
   }
   // rho class on SCALED bounds (auxil.h: set_rho_vec): -1 loose, 1 equality, 0 inequality
   MQ_HD int row_type(double e, double lo, double hi) const {
@@ -2376,7 +2379,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         if (o < R && hasu) {
           const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4], xs = XR[osl[q] * NS + k];
           row(og3[3 * q] * x0v + og3[3 * q + 1] * x1v + og3[3 * q + 2] * x2v - xs, zo[q], eo_[q]);
-          cert(orh[q] * (uo[q] - ouo_[q]), eo_[q], olo[q], INFINITY);
+          cert(orh[q] * (uo[q] - ouo_[q]), eo_[q], olo[q], sh.obs_hi);
         }
       }
       if constexpr (kWide) {
@@ -2386,7 +2389,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             const double e_ = WSE_(NBR + o, k), uv = UO[o * NS + k], rv = ORH[o * NS + k];
             row(OG3[(3 * o) * NS + k] * x0v + OG3[(3 * o + 1) * NS + k] * x1v + OG3[(3 * o + 2) * NS + k] * x2v - (((slmask >> o) & 1u) ? xs_ : xd),
                 ZO[o * NS + k], e_);
-            cert(rv * (uv - OU_(NBR + o, k)), e_, OLO[o * NS + k], INFINITY);
+            cert(rv * (uv - OU_(NBR + o, k)), e_, OLO[o * NS + k], sh.obs_hi);
           }
         }
       }
@@ -2513,11 +2516,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 #pragma unroll
           for (int t = 0; t < 2; ++t) rescale(rhd[t], ud[t], WSE_(di(t), k), bnd[t], bnd[t]);
 #pragma unroll
-          for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R && hasu) rescale(orh[q], uo[q], WSE_(NBR + o, k), olo[q], INFINITY); }
+          for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R && hasu) rescale(orh[q], uo[q], WSE_(NBR + o, k), olo[q], sh.obs_hi); }
           if constexpr (kWide) {
             if (hasu) for (int o = warp; o < R; o += 4) {
               double rv = ORH[o * NS + k], uv = UO[o * NS + k];
-              rescale(rv, uv, WSE_(NBR + o, k), OLO[o * NS + k], INFINITY);
+              rescale(rv, uv, WSE_(NBR + o, k), OLO[o * NS + k], sh.obs_hi);
               ORH[o * NS + k] = rv; UO[o * NS + k] = uv;
             }
           }

@@ -299,6 +299,7 @@ static int shape_from_params(mpcqp_engine* e, const mpcqp_mpc_params* p, int R, 
   if (!p || p->horizon < 3 || R < 0) { e->err = "bad mpc params (horizon >= 3, num_obs >= 0)"; return MPCQP_ERR_ARG; }
   const int NS = p->horizon, N = NS - 1;
   sh->NS = NS; sh->R = R; sh->n = 8 * NS + 5 * N; sh->m = 16 * NS + 5 * N + R * N;
+  sh->obs_hi = INFINITY;                                    // upperBound = +inf on the obstacle rows (MP.cpp:1139)
   // Ad/Bd entries pass through `float value` (MP.cpp:1003,1014)
   sh->a_pv = (double)f32(p->ts); sh->b_pa = (double)f32(1.0 / 2 * (p->ts * p->ts)); sh->b_va = (double)f32(p->ts);
   const double sks = 1.0 - (1 - p->static_slack) * (1 - p->static_slack);
@@ -987,7 +988,7 @@ namespace {
 const double kBoundInf = 1e20;     // OSQP_INFTY is 1e30 (constants.h:78); IEEE inf is what the reference passes
 
 // l / u of the stage structure -> x0, stage-uniform box, obstacle lower bounds.  Returns 0 or an error code.
-int parse_bounds(const Shape& sh, const double* l, const double* u, double* x0, double* blo, double* bhi, double* low, std::string* err) {
+int parse_bounds(const Shape& sh, const double* l, const double* u, double* x0, double* blo, double* bhi, double* low, double* obs_hi, std::string* err) {
   const int NS = sh.NS, N = NS - 1, R = sh.R;
   for (int i = 0; i < sh.m; ++i) if (l[i] > u[i]) { *err = "lower bound > upper bound at row " + std::to_string(i); return MPCQP_ERR_DATA; }
   for (int i = 0; i < 8 * NS; ++i) {
@@ -1007,8 +1008,12 @@ int parse_bounds(const Shape& sh, const double* l, const double* u, double* x0, 
   for (int k = 0; k < N; ++k) for (int o = 0; o < R; ++o) {
     const int i = 16 * NS + 5 * N + k * R + o;
     if (!(u[i] >= kBoundInf)) { *err = "obstacle row " + std::to_string(i) + " has a finite upper bound"; return MPCQP_ERR_STRUCTURE; }
+    // one "infinity" for all of them: IEEE inf (the reference) or a finite stand-in such as OSQP_INFTY (the certificates differ)
+    if (k == 0 && o == 0) *obs_hi = u[i];
+    else if (u[i] != *obs_hi) { *err = "obstacle rows mix different infinite upper bounds"; return MPCQP_ERR_STRUCTURE; }
     low[k * R + o] = l[i];
   }
+  if (N * R == 0) *obs_hi = INFINITY;
   return MPCQP_OK;
 }
 
@@ -1174,7 +1179,7 @@ extern "C" int mpcqp_setup(mpcqp_engine* e, mpcqp_problem** out, int64_t n, int6
   if (rc == MPCQP_OK) {
     const int NS = pr->sh.NS, N = NS - 1, R = pr->sh.R;
     pr->x0.assign(8, 0.0); pr->low.assign((size_t)N * (R > 0 ? R : 1), 0.0);
-    rc = parse_bounds(pr->sh, l, u, pr->x0.data(), pr->sh.blo, pr->sh.bhi, pr->low.data(), &e->err);
+    rc = parse_bounds(pr->sh, l, u, pr->x0.data(), pr->sh.blo, pr->sh.bhi, pr->low.data(), &pr->sh.obs_hi, &e->err);
   }
   if (rc == MPCQP_ERR_STRUCTURE) {            // not an mpcPlanner QP (e.g. polyTrajSolver.cpp:162-222), or the planner's matrices with
                                               // bounds outside its pattern (non-uniform box, finite obstacle upper bound): generic kernel
@@ -1253,7 +1258,7 @@ extern "C" int mpcqp_update_bounds(mpcqp_problem* pr, const double* l_new, const
     return MPCQP_OK;
   }
   Shape sh = pr->sh; std::vector<double> x0(8), low(pr->low.size());
-  int rc = parse_bounds(sh, l_new, u_new, x0.data(), sh.blo, sh.bhi, low.data(), &e->err);
+  int rc = parse_bounds(sh, l_new, u_new, x0.data(), sh.blo, sh.bhi, low.data(), &sh.obs_hi, &e->err);
   if (rc == MPCQP_ERR_STRUCTURE && !pr->cPc.empty()) {
     // bounds outside the planner's pattern: osqp_update_bounds would take them, so the problem moves to the generic path
     const std::vector<double> q = pr->q, sx = pr->sol_x, sy = pr->sol_y;
@@ -1283,9 +1288,14 @@ extern "C" int mpcqp_solve(mpcqp_problem* pr) {
   // solution (OSQP keeps its iterates between solves when settings->warm_start is on), else zeros.
   const bool ws = pr->st.warm_start != 0;
   const double* wx = nullptr; const double* wy = nullptr;
-  if (ws && pr->has_wx) wx = pr->warm_x.data(); else if (ws && pr->solved) wx = pr->sol_x.data();
+  // an infeasible / non-convex outcome leaves no iterate behind: store_solution fills the solution with OSQP_NAN and
+  // cold-starts the workspace (x = z = y = 0), so the next solve of the same object starts from zeros
+  const int64_t ps = pr->info.status_val;
+  const bool prev = pr->solved && !(ps == MPCQP_PRIMAL_INFEASIBLE || ps == MPCQP_PRIMAL_INFEASIBLE_INACCURATE || ps == MPCQP_DUAL_INFEASIBLE ||
+                                    ps == MPCQP_DUAL_INFEASIBLE_INACCURATE || ps == MPCQP_NON_CVX);
+  if (ws && pr->has_wx) wx = pr->warm_x.data(); else if (ws && prev) wx = pr->sol_x.data();
   // osqp_warm_start_x replaces x only: the dual iterate of the previous solve stays (osqp.h:165)
-  if (ws && pr->has_wy) wy = pr->warm_y.data(); else if (ws && pr->solved) wy = pr->sol_y.data();
+  if (ws && pr->has_wy) wy = pr->warm_y.data(); else if (ws && prev) wy = pr->sol_y.data();
   if (pr->dense) {
     int32_t hi[3]; double hd[3];
     int rc = run_dense(e, pr->dd, pr->st, 1, n, m, pr->dPc.data(), pr->dPi.data(), pr->dPx.data(), pr->q.data(), pr->dAc.data(), pr->dAi.data(),

@@ -51,10 +51,13 @@ def structured_inputs(mb):
                 low=np.ascontiguousarray(low), warm_x=np.ascontiguousarray(mb.warm_x))
 
 
-def solve(mb, want_y=True, linsys=0, **settings):
+def solve(mb, want_y=True, linsys=0, finite_inf=None, **settings):
     build()
     lib = C.CDLL(SO)
     s = structured_inputs(mb)
+    obs_hi = float("inf")
+    if finite_inf is not None:                         # the caller writes its infinite bounds as a finite number (OSQP_INFTY)
+        s["blo"] = np.where(np.isinf(s["blo"]), -finite_inf, s["blo"]); s["bhi"] = np.where(np.isinf(s["bhi"]), finite_inf, s["bhi"]); obs_hi = float(finite_inf)
     sd = dict(DEFAULT_D); si = dict(DEFAULT_I)
     for k, v in settings.items():
         (sd if k in sd else si)[k] = v
@@ -67,7 +70,7 @@ def solve(mb, want_y=True, linsys=0, **settings):
     D = C.POINTER(C.c_double); I = C.POINTER(C.c_int)
     def dp(a): return a.ctypes.data_as(D) if a is not None else None
     rc = lib.emul_solve_batch(C.c_int(linsys), C.c_int(s["NS"]), C.c_int(s["R"]), C.c_int(B), C.c_double(s["a_pv"]), C.c_double(s["b_pa"]),
-                         C.c_double(s["b_va"]), dp(s["blo"]), dp(s["bhi"]), dp(sdv), siv.ctypes.data_as(I),
+                         C.c_double(s["b_va"]), dp(s["blo"]), dp(s["bhi"]), C.c_double(obs_hi), dp(sdv), siv.ctypes.data_as(I),
                          dp(np.ascontiguousarray(s["pd"])), s["slack"].ctypes.data_as(C.POINTER(C.c_ubyte)),
                          dp(s["q"]), dp(s["x0"]), dp(s["g"]), dp(s["low"]), dp(s["warm_x"]),
                          dp(out["x"]), dp(out["y"]), out["status"].ctypes.data_as(I), out["iter"].ctypes.data_as(I),

@@ -7,14 +7,14 @@
 #include <cstring>
 
 extern "C" int emul_solve_batch(int linsys, int NS, int R, int B, double a_pv, double b_pa, double b_va, const double* blo,
-                                const double* bhi, const double* settings_d, const int* settings_i,
+                                const double* bhi, double obs_hi, const double* settings_d, const int* settings_i,
                                 const double* pd, const unsigned char* slack, const double* q, const double* x0,
                                 const double* g, const double* low, const double* warm_x, double* x, double* y,
                                 int* status, int* iter, int* rho_updates, double* obj, double* pri_res,
                                 double* dua_res) {
   using namespace mpcqp;
   Shape sh; sh.NS = NS; sh.R = R; sh.n = 8 * NS + 5 * (NS - 1); sh.m = 16 * NS + 5 * (NS - 1) + R * (NS - 1);
-  sh.a_pv = a_pv; sh.b_pa = b_pa; sh.b_va = b_va;
+  sh.a_pv = a_pv; sh.b_pa = b_pa; sh.b_va = b_va; sh.obs_hi = obs_hi;
   for (int j = 0; j < NV; ++j) { sh.blo[j] = blo[j]; sh.bhi[j] = bhi[j]; }
   Settings st;
   st.rho = settings_d[0]; st.sigma = settings_d[1]; st.alpha = settings_d[2]; st.eps_abs = settings_d[3];

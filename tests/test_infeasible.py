@@ -64,6 +64,18 @@ def test_emulated_dense_kernel_matches_reference_golden(name):
     _check(name, EM.solve_dense(qb, **kw), np.load(GOLD))
 
 
+@pytest.mark.parametrize("horizon,linsys", [(30, 0), (30, 1), (60, 0)])
+def test_emulated_stage_kernel_declares_primal_infeasibility_like_osqp(horizon, linsys):
+    """Kernel SOURCE of the stage-structured path (csrc/mpcqp_core.cuh) compiled for the host, with the bounds the
+    mpc_finite_* cases carry (1e30 for every infinite bound): linsys 0 = block LDL' chain, 1 = the CTA path's PCR algebra."""
+    from intent_mpc_b200 import workloads as W
+    from tests.emul import binding as EM
+    name = f"mpc_finite_h{horizon}"
+    B = IC.cases()[name][0].q.shape[0]
+    got = EM.solve(W.stress_batch(B, horizon=horizon), want_y=True, linsys=linsys, finite_inf=1e30)
+    _check(name, got, np.load(GOLD))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SMALL)
 def test_single_problem_abi_reports_infeasibility_like_osqp(name):
