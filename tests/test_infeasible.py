@@ -92,8 +92,9 @@ def test_single_problem_abi_reports_infeasibility_like_osqp(name):
         got["x"] = r["x"][None]; got["y"] = r["y"][None]
         _check(name, got, np.load(GOLD))
         # a second solve of the same object starts cold after an infeasible outcome (store_solution cold-starts) and repeats it
-        r2 = pr.solve()
-        assert r2["status"] == r["status"] and r2["iter"] == r["iter"]
+        if r["status"] in (-3, 3, -4, 4):
+            r2 = pr.solve()
+            assert r2["status"] == r["status"] and r2["iter"] == r["iter"]
         pr.close()
     finally:
         eng.close()
