@@ -185,6 +185,27 @@ int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_t C, int32_
                                    const double* weight, const double* score, const double* x_all, int32_t* best,
                                    double* weighted, double* plan);
 
+/* ---- (2c) predictor rollouts --------------------------------------------------------------------------- *
+ * The step immediately upstream of the planner: dynamicPredictor::predictor::predict (dynamic_predictor/include/
+ * dynamic_predictor/dynamicPredictor.cpp:162-195) = intentProb (:197-281) + predTraj (:283-541: forward / turning / stop
+ * sampling, mean path, box inflated by 2 sqrt(var) z) for num_obstacles obstacles at once; its outputs are exactly the
+ * arguments of updatePredObstacles (mpcPlanner.cpp:343-373) / mpcqp_intent_candidates_device.  Device pointers,
+ * asynchronous on the engine's stream.
+ *   pos_hist, vel_hist [num_obstacles][num_hist][3]   history, index 0 = newest (getDynamicObstaclesHist)
+ *   size               [num_obstacles][3]             current box size (robot size already added, fakeDetector.cpp:540)
+ *   pred_pos, pred_size [num_obstacles][4][prediction_size + 1][3]   intent order FORWARD, LEFT, RIGHT, STOP
+ *   intent_prob        [num_obstacles][4]
+ * The occupancy map the reference consults while sampling (isInflatedOccupied) is taken as free space. */
+typedef struct {
+  int32_t prediction_size;                /* predictor_param.yaml keys, defaults of intent_mpc_demo */
+  double prediction_time_step, min_turning_time, max_turning_time, prediction_z_score;
+  double max_front_prob, front_angle_deg, stop_velocity_threshold, prob_scale_param;
+} mpcqp_predictor_params;
+void mpcqp_default_predictor_params(mpcqp_predictor_params* p);
+int mpcqp_predict_device(mpcqp_engine* e, const mpcqp_predictor_params* pp, int32_t num_obstacles, int32_t num_hist,
+                         const double* pos_hist, const double* vel_hist, const double* size, double* pred_pos,
+                         double* pred_size, double* intent_prob);
+
 /* ---- (3) OSQP-shaped single problem (explicit CSC) -------------------------------------------------- *
  * mpcqp_setup replaces osqp_setup (osqp.h:58): data is copied, the caller's arrays may die afterwards.
  * P is upper-triangular CSC (n x n), A is CSC (m x n), indices int64 like OSQP's c_int (glob_opts.h:80).

@@ -952,6 +952,171 @@ extern "C" int mpcqp_select_candidates_device(mpcqp_engine* e, int32_t S, int32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// (2c) predictor rollouts on the device: dynamicPredictor::predictor's intentProb and predTraj
+// (dynamic_predictor/include/dynamic_predictor/dynamicPredictor.cpp:197-541) for many obstacles at once — the producer of
+// updatePredObstacles' arguments.  One warp per (obstacle, intent).  The sampling loops of modelForward / modelTurning run on
+// accumulating DOUBLE counters exactly as the reference writes them (every lane walks the loop nest, so all lanes see the
+// same counter values and the same sample count; sample s is rolled out by lane s mod 32); the mean and the two-pass
+// variance of genTraj are warp reductions.  The occupancy map is free space (isInflatedOccupied == false): perception is
+// outside SURVEY.md section 8.
+// ------------------------------------------------------------------------------------------------
+namespace mpcqp {
+struct PredConsts { int numPred; double dt, zScore, minTurn, maxTurn, frontAngle, stopVel, pscale, paramf, paraml, paramr, params; };
+constexpr int kPredMax = 64;                    // prediction_size + 1 <= kPredMax
+
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// PASS 0: accumulate sum x, sum y per step; PASS 1: accumulate squared deviations from (mx, my)
+template <int PASS>
+__device__ __forceinline__ void pred_rollout(const PredConsts& c, int intent, const double* pos, double speed, double angleInit, double angVel,
+                                             double endAngle, bool turning, double* ax, double* ay, const double* mx, const double* my) {
+  double angle = angleInit;
+  double x = pos[0], y = pos[1], vx = speed * cos(angle), vy = speed * sin(angle);
+  if (PASS == 0) { ax[0] += x; ay[0] += y; } else { ax[0] += (x - mx[0]) * (x - mx[0]); ay[0] += (y - my[0]) * (y - my[0]); }
+  for (int k = 1; k <= c.numPred; ++k) {
+    x = x + c.dt * vx; y = y + c.dt * vy;                      // model * currState (dynamicPredictor.cpp:372-376, 446-450)
+    if (PASS == 0) { ax[k] += x; ay[k] += y; } else { ax[k] += (x - mx[k]) * (x - mx[k]); ay[k] += (y - my[k]) * (y - my[k]); }
+    if (turning) {                                           // :461-471
+      angle += angVel * c.dt;
+      angle = intent == 1 ? fmin(angle, endAngle) : fmax(angle, endAngle);
+      const double v = sqrt(vx * vx + vy * vy);
+      vx = v * cos(angle); vy = v * sin(angle);
+    }
+  }
+}
+
+template <int PASS>
+__device__ __forceinline__ int pred_samples(const PredConsts& c, int intent, const double* pos, const double* vel, int lane, double* ax, double* ay,
+                                            const double* mx, const double* my) {
+  const double v = sqrt(vel[0] * vel[0] + vel[1] * vel[1]);
+  const double angleInit = atan2(vel[1], vel[0]);
+  const double minVel = v - v, maxVel = v + v;
+  int s = 0;
+  if (intent == 0) {                                         // modelForward, :353-404
+    const double minAngle = angleInit - c.frontAngle, maxAngle = angleInit + c.frontAngle;
+    for (double i = minAngle; i < maxAngle; i += 0.1)
+      for (double j = minVel; j < maxVel; j += 0.1) {
+        if ((s & 31) == lane) pred_rollout<PASS>(c, intent, pos, j, i, 0.0, 0.0, false, ax, ay, mx, my);
+        ++s;
+      }
+  } else {                                                   // modelTurning, :406-491
+    const double kPi = 3.14159265358979323846;
+    double endMin, endMax, minAngVel, maxAngVel;
+    if (intent == 1) { endMin = c.frontAngle + angleInit; endMax = (kPi - c.frontAngle) + angleInit; minAngVel = (kPi / 2) / c.maxTurn; maxAngVel = (kPi / 2) / c.minTurn; }
+    else { endMin = -(kPi - c.frontAngle) + angleInit; endMax = -c.frontAngle + angleInit; minAngVel = (-kPi / 2) / c.minTurn; maxAngVel = (-kPi / 2) / c.maxTurn; }
+    for (double i = minVel; i < maxVel; i += 0.2)
+      for (double j = minAngVel; j < maxAngVel; j += 0.2)
+        for (double endAngle = endMin; endAngle < endMax; endAngle += 0.2) {
+          if ((s & 31) == lane) pred_rollout<PASS>(c, intent, pos, i, angleInit, j, endAngle, true, ax, ay, mx, my);
+          ++s;
+        }
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(128) mpc_predict_kernel(const __grid_constant__ PredConsts c, int NOB, int H, const double* __restrict__ pos_hist,
+                                                           const double* __restrict__ vel_hist, const double* __restrict__ size,
+                                                           double* __restrict__ pred_pos, double* __restrict__ pred_size, double* __restrict__ prob) {
+  const int lane = threadIdx.x & 31;
+  const int T = c.numPred + 1;
+  __shared__ double acc[4][4][kPredMax];                     // per warp: sum x, sum y -> mean x, mean y, then var x, var y
+  double* const sx = acc[threadIdx.x >> 5][0]; double* const sy = acc[threadIdx.x >> 5][1];
+  double* const vx_ = acc[threadIdx.x >> 5][2]; double* const vy_ = acc[threadIdx.x >> 5][3];
+  for (long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); w < (long long)NOB * 4; w += (long long)gridDim.x * 4) {
+    const int ob = (int)(w >> 2), intent = (int)(w & 3);
+    const double* ph = pos_hist + (long long)ob * H * 3; const double* vh = vel_hist + (long long)ob * H * 3;
+    const double pos[3] = {ph[0], ph[1], ph[2]}, vel[3] = {vh[0], vh[1], vh[2]};
+    const double sz[3] = {size[ob * 3], size[ob * 3 + 1], size[ob * 3 + 2]};
+    double* op = pred_pos + ((long long)ob * 4 + intent) * T * 3; double* os = pred_size + ((long long)ob * 4 + intent) * T * 3;
+    const double v = sqrt(vel[0] * vel[0] + vel[1] * vel[1]);
+    if (intent == 0 && lane == 0) {                          // intentProb, :197-226 (+ genTransitionMatrix / Vector, :229-281)
+      double P[4] = {0.25, 0.25, 0.25, 0.25};
+      const double kPi = 3.14159265358979323846;
+      for (int j = 2; j < H; ++j) {
+        const double* prevPos = ph + (H - j - 1) * 3; const double* currPos = ph + (H - j - 2) * 3; const double* older = ph + (H - j) * 3;
+        const double* currVel = vh + (H - j - 2) * 3;
+        const double prevAngle = atan2(prevPos[1] - older[1], prevPos[0] - older[0]);
+        const double currAngle = atan2(currPos[1] - prevPos[1], currPos[0] - prevPos[0]);
+        double theta = currAngle - prevAngle;
+        if (theta > kPi) theta = theta - 2 * kPi; else if (theta <= -kPi) theta = theta + 2 * kPi;
+        const double r = sqrt(currVel[0] * currVel[0] + currVel[1] * currVel[1]);
+        double nP[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < 4; ++i) {
+          double sc[4] = {1.0, 1.0, 1.0, 1.0}; sc[i] = c.pscale;
+          double pf = sc[0] * (exp(-0.5 * (theta / c.paramf) * (theta / c.paramf)) + c.paraml);
+          double pl = sc[1] * (c.paraml * (1 + sin(theta)));
+          double pr = sc[2] * (c.paramr * (1 - sin(theta)));
+          const double ps = (1 - tanh(c.params / sc[3] * r));
+          const double sum = pr + pl + pf;
+          pr = (1 - ps) * pr / sum; pl = (1 - ps) * pl / sum; pf = (1 - ps) * pf / sum;
+          nP[0] += pf * P[i]; nP[1] += pl * P[i]; nP[2] += pr * P[i]; nP[3] += ps * P[i];
+        }
+        P[0] = nP[0]; P[1] = nP[1]; P[2] = nP[2]; P[3] = nP[3];
+      }
+      prob[ob * 4] = P[0]; prob[ob * 4 + 1] = P[1]; prob[ob * 4 + 2] = P[2]; prob[ob * 4 + 3] = P[3];
+    }
+    if (intent == 3 || v <= c.stopVel) {                     // modelStop, :493-505 (genTraj adds 2 sqrt(0) z = 0)
+      if (lane == 0) {
+        double s0 = sz[0], s1 = sz[1];
+        const double g = 2 * fmin(v, c.stopVel) * c.dt;
+        for (int k = 0; k < T; ++k) {
+          op[k * 3] = pos[0]; op[k * 3 + 1] = pos[1]; op[k * 3 + 2] = pos[2];
+          os[k * 3] = s0 + 2 * sqrt(0.0) * c.zScore; os[k * 3 + 1] = s1 + 2 * sqrt(0.0) * c.zScore; os[k * 3 + 2] = sz[2];
+          s0 += g; s1 += g;
+        }
+      }
+      continue;
+    }
+    double ax[kPredMax], ay[kPredMax];
+    for (int k = 0; k < T; ++k) { ax[k] = 0.0; ay[k] = 0.0; }
+    const int cnt = pred_samples<0>(c, intent, pos, vel, lane, ax, ay, nullptr, nullptr);
+    for (int k = 0; k < T; ++k) { const double a = warp_sum_all(ax[k]), b = warp_sum_all(ay[k]); if (lane == 0) { sx[k] = a / cnt; sy[k] = b / cnt; } }
+    __syncwarp();
+    for (int k = 0; k < T; ++k) { ax[k] = 0.0; ay[k] = 0.0; }
+    pred_samples<1>(c, intent, pos, vel, lane, ax, ay, sx, sy);
+    for (int k = 0; k < T; ++k) { const double a = warp_sum_all(ax[k]), b = warp_sum_all(ay[k]); if (lane == 0) { vx_[k] = a / cnt; vy_[k] = b / cnt; } }
+    __syncwarp();
+    for (int k = lane; k < T; k += 32) {                      // genTraj, :507-541
+      op[k * 3] = sx[k]; op[k * 3 + 1] = sy[k]; op[k * 3 + 2] = pos[2];
+      os[k * 3] = sz[0] + 2 * sqrt(vx_[k]) * c.zScore; os[k * 3 + 1] = sz[1] + 2 * sqrt(vy_[k]) * c.zScore; os[k * 3 + 2] = sz[2];
+    }
+    __syncwarp();
+  }
+}
+}  // namespace mpcqp
+
+extern "C" void mpcqp_default_predictor_params(mpcqp_predictor_params* p) {
+  if (!p) return;
+  p->prediction_size = 30; p->prediction_time_step = 0.1; p->min_turning_time = 2.0; p->max_turning_time = 3.0; p->prediction_z_score = 0.674;
+  p->max_front_prob = 0.5; p->front_angle_deg = 25.0; p->stop_velocity_threshold = 0.1; p->prob_scale_param = 5.0;
+}
+
+extern "C" int mpcqp_predict_device(mpcqp_engine* e, const mpcqp_predictor_params* pp, int32_t num_obstacles, int32_t num_hist, const double* pos_hist,
+                                    const double* vel_hist, const double* size, double* pred_pos, double* pred_size, double* intent_prob) {
+  if (!e) return MPCQP_ERR_ARG;
+  if (!pp || num_obstacles <= 0 || num_hist < 1 || !pos_hist || !vel_hist || !size || !pred_pos || !pred_size || !intent_prob) { e->err = "bad arguments"; return MPCQP_ERR_ARG; }
+  if (pp->prediction_size < 1 || pp->prediction_size + 1 > kPredMax || !(pp->prediction_time_step > 0) || !(pp->stop_velocity_threshold > 0) ||
+      !(pp->min_turning_time > 0) || !(pp->max_turning_time > 0) || !(3 * pp->max_front_prob - 1 > 0)) { e->err = "bad predictor parameters"; return MPCQP_ERR_ARG; }
+  CK(cudaSetDevice(e->device));
+  PredConsts c;                                               // initParam, dynamicPredictor.cpp:14-117
+  c.numPred = pp->prediction_size; c.dt = pp->prediction_time_step; c.zScore = pp->prediction_z_score; c.minTurn = pp->min_turning_time;
+  c.maxTurn = pp->max_turning_time; c.stopVel = pp->stop_velocity_threshold; c.pscale = pp->prob_scale_param;
+  c.paraml = (1 - pp->max_front_prob) / (3 * pp->max_front_prob - 1); c.paramr = c.paraml;
+  c.frontAngle = pp->front_angle_deg * M_PI / 180;
+  c.paramf = sqrt(c.frontAngle * c.frontAngle / (-2 * log(c.paraml * (1 + sin(c.frontAngle)) - c.paraml)));
+  c.params = atanh(0.5) / c.stopVel;
+  long long blocks = ((long long)num_obstacles * 4 + 3) / 4; const long long cap = (long long)e->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  mpc_predict_kernel<<<(unsigned)blocks, 128, 0, e->stream>>>(c, num_obstacles, num_hist, pos_hist, vel_hist, size, pred_pos, pred_size, intent_prob);
+  CK(cudaGetLastError());
+  return MPCQP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // (3) OSQP-shaped single problem with explicit CSC data (what OsqpEigen::Solver hands to osqp_setup,
 // OsqpEigen/Data.tpp:38-39,77; osqp.h:58).  A problem with the mpcPlanner stage structure
 // (mpcPlanner.cpp:932-1146) is parsed on the host into the structured form the stage kernels take and solved by them as a

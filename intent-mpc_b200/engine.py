@@ -40,6 +40,23 @@ class MpcParamsC(C.Structure):
                                           "acceleration_weight")]
 
 
+class PredictorParamsC(C.Structure):
+    """mpcqp_predictor_params (predictor_param.yaml keys)."""
+    _fields_ = [("prediction_size", C.c_int32)] + \
+               [(k, C.c_double) for k in ("prediction_time_step", "min_turning_time", "max_turning_time", "prediction_z_score",
+                                          "max_front_prob", "front_angle_deg", "stop_velocity_threshold", "prob_scale_param")]
+
+
+def default_predictor_params(**overrides) -> PredictorParamsC:
+    p = PredictorParamsC()
+    load_library().mpcqp_default_predictor_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"unknown predictor parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
 class Info(C.Structure):
     _fields_ = [("iter", C.c_int64), ("status_val", C.c_int64), ("rho_updates", C.c_int64),
                 ("obj_val", C.c_double), ("pri_res", C.c_double), ("dua_res", C.c_double),
@@ -247,6 +264,13 @@ class Engine:
                                                             g("pred_size"), g("prob"), g("prev_plan"), g("pos"), g("scen_a"), g("scen_b"),
                                                             g("obs_c_a"), g("obs_semi_a"), g("obs_c_b"), g("obs_semi_b"), g("obs_c_last_a"),
                                                             g("obs_semi_last_a"), g("obs_c_last_b"), g("obs_semi_last_b"), g("weight"), g("cand")))
+
+    def predict_ptr(self, pparams: PredictorParamsC, num_obstacles: int, num_hist: int, ptrs: dict):
+        """mpcqp_predict_device: ptrs = device addresses of pos_hist, vel_hist [NOB][H][3] (newest first), size [NOB][3], pred_pos,
+        pred_size [NOB][4][prediction_size + 1][3], intent_prob [NOB][4].  Asynchronous on the engine stream."""
+        g = lambda k: C.c_void_p(ptrs.get(k) or None)
+        self._check(self.lib.mpcqp_predict_device(self.h, C.byref(pparams), C.c_int32(num_obstacles), C.c_int32(num_hist), g("pos_hist"), g("vel_hist"),
+                                                  g("size"), g("pred_pos"), g("pred_size"), g("intent_prob")))
 
     def gather_rows_ptr(self, B: int, width: int, idx_ptr: int, src_ptr: int, dst_ptr: int):
         self._check(self.lib.mpcqp_gather_rows_device(self.h, C.c_int64(B), C.c_int32(width), C.c_void_p(idx_ptr), C.c_void_p(src_ptr),

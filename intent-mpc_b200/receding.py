@@ -52,6 +52,18 @@ class IntentSweep:
         vel = (pos2 - pos) / 1e-3
         return pos.reshape(self.S, self.D, 3), vel.reshape(self.S, self.D, 3)
 
+    def history(self, step, H: int = 10, dt_hist: float = 0.1):
+        """Obstacle histories as the detector hands them to the predictor (fakeDetector::getDynamicObstaclesHist,
+        fakeDetector.cpp:525-553): posHist / velHist [S, D, H, 3], index 0 = newest, velocities (Vx, Vy, 0)."""
+        t = step * self.p.ts - dt_hist * np.arange(H)
+        flat = lambda a: a.reshape(-1)
+        pos = _trefoil(t, flat(self.scale), flat(self.slow), flat(self.off), self.centre.reshape(-1, 3))            # [H, S*D, 3]
+        pos2 = _trefoil(t + 1e-3, flat(self.scale), flat(self.slow), flat(self.off), self.centre.reshape(-1, 3))
+        vel = (pos2 - pos) / 1e-3
+        vel[..., 2] = 0.0
+        sh = (self.S, self.D, H, 3)
+        return np.ascontiguousarray(pos.transpose(1, 0, 2)).reshape(sh), np.ascontiguousarray(vel.transpose(1, 0, 2)).reshape(sh)
+
     def predictions(self, step):
         """predPos [S, D, 4, NS+1? -> NS+0: 31 steps, 3], predSize likewise."""
         T = 31

@@ -19,9 +19,15 @@ from .receding import IntentSweep, FORWARD, LEFT, RIGHT, STOP
 
 
 class DeviceIntentSweep:
-    def __init__(self, eng: E.Engine, host: IntentSweep, device: int = 0, host_predictions: bool = False):
+    def __init__(self, eng: E.Engine, host: IntentSweep, device: int = 0, host_predictions: bool = False, predictor: str = "closed_form",
+                 num_hist: int = 10):
+        """predictor: "closed_form" = the scenario generator's stand-in predictions and fixed intent probabilities;
+        "sampled" = the reference predictor itself on the device (mpcqp_predict_device, dynamicPredictor.cpp:197-541) from
+        the obstacles' histories — then only the histories come from the host when host_predictions is set."""
+        assert predictor in ("closed_form", "sampled")
         self.eng, self.p, self.S, self.D = eng, host.p, host.S, host.D
-        self.host, self.host_predictions = host, host_predictions
+        self.host, self.host_predictions, self.predictor, self.num_hist = host, host_predictions, predictor, num_hist
+        self.pparams = E.default_predictor_params()
         self.h2d_bytes = 0; self.d2h_bytes = 0
         self.dev = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(eng.stream, device=self.dev)
@@ -56,7 +62,28 @@ class DeviceIntentSweep:
         z = self.scale * (-torch.sin(3 * u)) / 3.0 * 0.3
         return self.centre + torch.stack([x, y, z], dim=-1)
 
+    def _history(self):
+        """Obstacle histories [S, D, H, 3] (newest first; velocities (Vx, Vy, 0)) on the device."""
+        H = self.num_hist
+        if self.host_predictions:
+            ph, vh = self.host.history(self.step_idx, H=H)
+            self.h2d_bytes += ph.nbytes + vh.nbytes
+            return torch.from_numpy(ph).to(self.dev), torch.from_numpy(vh).to(self.dev)
+        t = self.step_idx * self.p.ts - 0.1 * torch.arange(H, dtype=torch.float64, device=self.dev)
+        pos = torch.stack([self._trefoil(tt) for tt in t], dim=2)
+        vel = (torch.stack([self._trefoil(tt + 1e-3) for tt in t], dim=2) - pos) / 1e-3
+        vel[..., 2] = 0.0
+        return pos.contiguous(), vel.contiguous()
+
     def predictions(self):
+        if self.predictor == "sampled":                    # dynamicPredictor on the device
+            ph, vh = self._history()
+            T = self.pparams.prediction_size + 1
+            pp = torch.empty((self.S, self.D, 4, T, 3), dtype=torch.float64, device=self.dev); ps = torch.empty_like(pp)
+            self.eng.predict_ptr(self.pparams, self.S * self.D, self.num_hist, {"pos_hist": ph.data_ptr(), "vel_hist": vh.data_ptr(), "size": self.size.data_ptr(),
+                                                                                "pred_pos": pp.data_ptr(), "pred_size": ps.data_ptr(), "intent_prob": self.prob.data_ptr()})
+            self._keep = (ph, vh)                          # alive until the stream has run the kernel
+            return pp, ps
         if self.host_predictions:                          # numpy on the host, uploaded (the e2e form)
             pp, ps = self.host.predictions(self.step_idx)
             self.h2d_bytes += pp.nbytes + ps.nbytes

@@ -84,6 +84,32 @@ def test_device_loop_with_host_predictions_counts_its_traffic():
 
 
 @pytest.mark.gpu
+def test_device_loop_with_the_sampled_predictor():
+    """SURVEY.md 8(f) row 4 wired in: predictions and intent probabilities come from mpcqp_predict_device (the reference
+    predictor's sampling, dynamicPredictor.cpp:197-541) instead of the closed-form stand-in; the candidates it leads to are
+    still solved exactly like the reference would (oracle on the identical QPs)."""
+    from intent_mpc_b200 import engine
+    from intent_mpc_b200.receding_device import DeviceIntentSweep
+    eng = engine.Engine(0)
+    try:
+        for hostp in (False, True):
+            host = receding.IntentSweep(S=24, D=4, seed0=61)
+            ds = DeviceIntentSweep(eng, host, predictor="sampled", host_predictions=hostp)
+            x_start = host.pos[:, 0].copy()
+            for step in range(5):
+                ds.step()
+            prob = ds.prob.cpu().numpy()
+            assert np.isfinite(prob).all() and (prob >= 0).all() and not np.array_equal(prob, host.prob)      # the HMM's, not the generator's
+            for mb, out in ds.batches_host():
+                _check_against_oracle(mb, out, f"sampled predictor, host histories {hostp}")
+            assert (ds.pos.cpu().numpy()[:, 0] > x_start).all()
+            if hostp:
+                assert ds.h2d_bytes == 4 * 2 * 24 * 4 * 10 * 3 * 8                                             # histories only
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
 def test_device_loop_full_size_properties():
     """65,538 candidate QPs per control step (10,923 scenarios x 6, BASELINE.json configs[2]); two control steps."""
     from intent_mpc_b200 import engine
