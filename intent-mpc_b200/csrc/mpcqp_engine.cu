@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(128) mpc_predict_kernel(const __grid_constant_
     if (intent == 0 && lane == 0) {                          // intentProb, :197-226 (+ genTransitionMatrix / Vector, :229-281)
       double P[4] = {0.25, 0.25, 0.25, 0.25};
       const double kPi = 3.14159265358979323846;
-      for (int j = 2; j < H; ++j) {
+      for (int j = 2; j < H - 1; ++j) {                        // the reference's last pass (j = H - 1) reads index -1: left out
         const double* prevPos = ph + (H - j - 1) * 3; const double* currPos = ph + (H - j - 2) * 3; const double* older = ph + (H - j) * 3;
         const double* currVel = vh + (H - j - 2) * 3;
         const double prevAngle = atan2(prevPos[1] - older[1], prevPos[0] - older[0]);

@@ -67,7 +67,10 @@ def intent_prob(c, pos_hist, vel_hist):
     """intentProb, PRED.cpp:197-226, for ONE obstacle: pos_hist / vel_hist [numHist][3], index 0 = newest."""
     P = [1.0 / 4] * 4
     nh = len(pos_hist)
-    for j in range(2, nh):
+    # The reference loops `for (j = 2; j < numHist; ++j)` and reads posHist_[i][numHist-j-2], which is index -1 on the last pass:
+    # undefined behaviour (whatever precedes the vector's storage).  That pass is left out here and in the device kernel; every
+    # defined pass is restated as written.  (Deviation recorded in DESIGN.md.)
+    for j in range(2, nh - 1):
         prevPos = pos_hist[nh - j - 1]
         currPos = pos_hist[nh - j - 2]; currVel = vel_hist[nh - j - 2]
         older = pos_hist[nh - j]
