@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
     ap.add_argument("--num-obs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep-strong", action="store_true", help="skip the strong-scaling configs[4] leg of the default workload")
+    ap.add_argument("--sweep-strong-instances", type=int, default=131072, help="total sweep instances of that leg (sharded over the ranks)")
     ap.add_argument("--workload", default="static", choices=["static", "sweep", "receding", "polytraj"],
                     help="static: configs[1], the bench line the driver reads (default).  sweep: configs[4], --instances Monte-Carlo "
                          "instances sharded by index over the ranks (strong scaling), one JSON line of the same shape.  receding: "
@@ -259,6 +261,25 @@ def run_b200(args, rank, world, local_rank):
             raise SystemExit(f"bench.py: host and device entry points disagree on {len(bad)} instances of batch {j}, e.g. {bad[:8]}: "
                              f"host {pouts[j]['iter'].numpy()[bad[:8]]} device {it_all[j][bad[:8]]}")
 
+    # ---- configs[4] as a STRONG-scaling leg on all ranks: a fixed total of sweep instances, index-sharded over the ranks --
+    sweep_strong = None
+    if not args.no_sweep_strong:
+        from intent_mpc_b200 import sharding
+        Mtot = args.sweep_strong_instances
+        lo_, hi_ = sharding.shard_bounds(Mtot, world)[rank]
+        wm_ = W.sweep_batches(lo_, min(lo_ + 2048, hi_), one_launch=True)[0]
+        eng.solve_mpc_batch(wm_[0][1])                 # warm-up of the wide kernel
+        if world > 1:
+            dist.barrier()
+        sdev, swall, sit_, shist_, _ = sweep_shard(eng, lo_, hi_, 32768)
+        t = torch.tensor([sdev, swall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sweep_strong = {"instances_total": Mtot, "value": Mtot / (float(t[0]) * 1e-3), "unit": UNIT, "kernel_ms_max_over_ranks": float(t[0]),
+                        "e2e": {"value": Mtot / (float(t[1]) * 1e-3), "unit": UNIT, "ms_max_over_ranks": float(t[1]),
+                                "note": "pinned host buffers through mpcqp_solve_mpc_batch_host, copies inside; generation untimed"},
+                        "scaling": "strong", "note": "configs[4]: the same total number of Monte-Carlo sweep instances at every N, contiguous index shards, no collective"}
+
     # ---- verification gather (NCCL over NVLink; not on the solve path, not timed into `value`) ------------
     gather_ms = None
     if world > 1:
@@ -454,6 +475,8 @@ def run_b200(args, rank, world, local_rank):
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"}},
         "cpu_baseline": cpu, "parity": parity, "clocks": sampler.summary(), "extras": extras,
     }
+    if sweep_strong is not None:
+        line["extras"]["sweep_strong_scaling"] = sweep_strong
     if gather_ms is not None:
         line["verification_gather_ms"] = gather_ms
     print(json.dumps(line), flush=True)
@@ -461,27 +484,16 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_sweep(args, rank, world, local_rank):
-    """BASELINE.json configs[4]: --instances sweep instances (intent-mpc_b200/workloads.py:sweep_batches), contiguous index
-    shards over the ranks, no collective on the solve path.  Each rank generates its shard chunk by chunk on the host
-    (untimed), solves every chunk through the host entry point (e2e: pinned-free numpy buffers, copies inside) and sums the
-    device time of its kernels (`value`); the job's time is the max over ranks."""
+def sweep_shard(eng, lo, hi, chunk):
+    """Generate (host, untimed) and solve the sweep instances [lo, hi) chunk by chunk through the host entry point with pinned
+    buffers.  Returns device ms of the kernels, wall seconds of the calls (copies inside), iterations, status histogram, launches."""
     import torch
-    import torch.distributed as dist
-    from intent_mpc_b200 import engine, workloads as W, sharding
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = engine.Engine(local_rank)
-    eng.use_history(False)                              # independent instances: slot history means nothing here
-    lo, hi = sharding.shard_bounds(args.instances, world)[rank]
-    dev_ms = 0.0; wall = 0.0; iters = 0; hist = {}; launches = 0; capped = 0
-    warm = W.sweep_batches(lo, min(lo + 2048, hi), one_launch=True)[0]
-    eng.solve_mpc_batch(warm[0][1])                    # warm-up (kernel load, buffers)
+    from intent_mpc_b200 import engine, workloads as W
+    dev_ms = 0.0; wall = 0.0; iters = 0; hist = {}; launches = 0
     st = engine.default_settings()
     names = ["x0", "xref", "obs_c", "obs_semi", "obs_yaw", "lin_pt", "warm_x"]
-    for c0 in range(lo, hi, args.chunk):
-        (idx, mb), = W.sweep_batches(c0, min(c0 + args.chunk, hi), one_launch=True)[0]
+    for c0 in range(lo, hi, chunk):
+        (idx, mb), = W.sweep_batches(c0, min(c0 + chunk, hi), one_launch=True)[0]
         B, R, n = mb.B, mb.num_obs, mb.params.n
         # pinned staging of the generated chunk (untimed, like the generation itself): the timed call then is what a caller
         # with page-locked buffers pays — host -> device copies, kernels, device -> host copies
@@ -498,6 +510,26 @@ def run_sweep(args, rank, world, local_rank):
         dev_ms += eng.last_kernel_ms; launches += eng.last_launches; iters += int(out["iter"].sum())
         for k_, v_ in _hist(out["status"]).items():
             hist[k_] = hist.get(k_, 0) + v_
+    return dev_ms, wall, iters, hist, launches
+
+
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: --instances sweep instances (intent-mpc_b200/workloads.py:sweep_batches), contiguous index
+    shards over the ranks, no collective on the solve path.  Each rank generates its shard chunk by chunk on the host
+    (untimed), solves every chunk through the host entry point (e2e: pinned host buffers, copies inside) and sums the
+    device time of its kernels (`value`); the job's time is the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from intent_mpc_b200 import engine, workloads as W, sharding
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = engine.Engine(local_rank)
+    eng.use_history(False)                              # independent instances: slot history means nothing here
+    lo, hi = sharding.shard_bounds(args.instances, world)[rank]
+    warm = W.sweep_batches(lo, min(lo + 2048, hi), one_launch=True)[0]
+    eng.solve_mpc_batch(warm[0][1])                    # warm-up (kernel load, buffers)
+    dev_ms, wall, iters, hist, launches = sweep_shard(eng, lo, hi, args.chunk)
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=torch.device("cuda", local_rank))
     agg = torch.tensor([float(iters), float(hi - lo)], dtype=torch.float64, device=torch.device("cuda", local_rank))
     if world > 1:

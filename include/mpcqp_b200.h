@@ -73,6 +73,8 @@ typedef struct {
 void mpcqp_default_mpc_params(mpcqp_mpc_params* p);
 
 /* ---- (1) engine lifecycle ------------------------------------------------------------------------- */
+/* Number of usable CUDA devices (0 when there is none: every other call then fails; there is no CPU path). */
+int mpcqp_device_count(void);
 int mpcqp_engine_create(int device, mpcqp_engine** out);
 int mpcqp_engine_destroy(mpcqp_engine* e);
 const char* mpcqp_engine_last_error(const mpcqp_engine* e);

@@ -207,6 +207,12 @@ extern "C" void mpcqp_default_mpc_params(mpcqp_mpc_params* p) {
   p->acceleration_weight = 10.0;
 }
 
+extern "C" int mpcqp_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+
 extern "C" int mpcqp_engine_create(int device, mpcqp_engine** out) {
   if (!out) return MPCQP_ERR_ARG;
   *out = nullptr;
