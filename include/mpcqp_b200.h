@@ -86,8 +86,10 @@ double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e);
 int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
 /* Which solve kernel the last batch ran: 2 = CTA kernel (one 4-warp CTA per QP, parallel-cyclic-reduction solve,
  * horizon 30, num_obs <= 8), 1 = one-warp-per-QP register-resident kernel (same shapes), 0 = generic one-warp
- * shared-memory kernel (any horizon/num_obs that fits), 4 = dense generic kernel for problems WITHOUT the mpcPlanner stage
- * structure (mpcqp_setup / mpcqp_solve only; polyTrajSolver's minimum-snap QPs).  force_generic(1) pins the generic kernel, (2) the
+ * shared-memory kernel (any horizon/num_obs that fits); for problems WITHOUT the mpcPlanner stage structure (polyTrajSolver's
+ * minimum-snap QPs): 5 = sparse generic kernel (banded L D L' of the reverse-Cuthill-McKee-ordered KKT matrix, one warp per QP;
+ * taken when the half-bandwidth is <= 31), 4 = dense generic kernel (anything else up to n + m = 4096).  force_generic(4) pins the
+ * dense kernel for unstructured problems (A/B tests).  force_generic(1) pins the generic kernel, (2) the
  * one-warp register kernel, (3) the CTA kernel without its assistant warps (launches that give a CTA an SM to itself
  * normally carry three more warps that hold the PCR matrices of levels 1..3 in registers), (0) restores the default
  * dispatch (used by the tests to cover all of them). */

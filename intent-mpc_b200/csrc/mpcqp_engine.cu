@@ -18,6 +18,8 @@
 #include "mpcqp_core.cuh"
 #include "mpcqp_kernels.cuh"
 #include "mpcqp_dense.cuh"
+#include "mpcqp_band.cuh"
+#include "mpcqp_band_host.hpp"
 
 namespace mpcqp {
 
@@ -164,7 +166,7 @@ struct DevBufScope {   // first member of the engine: opens the registry before 
 struct DevBufScopeEnd { DevBufScopeEnd() { g_devbuf_registry = nullptr; } };   // last member: closes it
 
 struct DenseDev {   // device buffers of one call of the generic (unstructured) path
-  DevBuf Pc, Pi, Px, Ac, Ai, Ax, q, l, u, wx, wy, x, y, ii, dd, ws;
+  DevBuf Pc, Pi, Px, Ac, Ai, Ax, q, l, u, wx, wy, x, y, ii, dd, ws, pat;
 };
 
 struct mpcqp_engine {
@@ -1153,6 +1155,12 @@ namespace mpcqp_dense {
 int grid_size(int B, int n, int m, int device);
 int launch(const Batch& bt, int grid, const Settings& st, cudaStream_t stream);
 }
+namespace mpcqp_band {
+void pattern_bind(Pattern* pt, int n, int m, int w, int nnzP, int nnzA, const int* dev_flat, const int* off);
+int grid_size(int B, int N, int w, int device);
+int launch(const Batch& bt, int grid, const Settings& st, cudaStream_t stream);
+}
+static_assert(sizeof(mpcqp_band::Settings) == sizeof(Settings), "the band path reads mpcqp::Settings by layout");
 static_assert(sizeof(mpcqp_dense::Settings) == sizeof(Settings), "the dense path reads mpcqp::Settings by layout");
 
 namespace {
@@ -1278,8 +1286,49 @@ int run_dense(mpcqp_engine* e, DenseDev& d, const Settings& st, int B, int n, in
               const double* wx, const double* wy, double* x, double* y, int32_t* info_i, double* info_d) {
   const size_t one = sizeof(double), nnzP = (size_t)Pc[n], nnzA = (size_t)Ac[n], mm = (size_t)(m > 0 ? m : 1);
   CK(cudaSetDevice(e->device));
+  // Sparse path first: a KKT matrix that is narrow-banded under reverse Cuthill-McKee (polyTrajSolver's is: half-bandwidth
+  // 8 .. 12) is factored and solved in band form by one warp per QP (csrc/mpcqp_band.cuh); anything else runs dense.
+  if (e->force_generic != 4) {
+    std::vector<int> flat; int off[14], w = 0;
+    if (mpcqp_band::pattern_build(n, m, Pc, Pi, Ac, Ai, &flat, off, &w)) {
+      const int bgrid = mpcqp_band::grid_size(B, n + m, w, e->device);
+      if (bgrid > 0) {
+        auto upb = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+          cudaError_t r = b.need(bytes ? bytes : 8); if (r != cudaSuccess || !bytes) return r;
+          return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
+        };
+        CK(upb(d.pat, flat.data(), flat.size() * sizeof(int)));
+        CK(upb(d.Px, Px, (size_t)B * nnzP * one)); CK(upb(d.Ax, Ax, (size_t)B * nnzA * one));
+        CK(upb(d.q, q, (size_t)B * n * one)); CK(upb(d.l, l, (size_t)B * m * one)); CK(upb(d.u, u, (size_t)B * m * one));
+        if (wx) CK(upb(d.wx, wx, (size_t)B * n * one));
+        if (wy && m > 0) CK(upb(d.wy, wy, (size_t)B * m * one));
+        CK(d.x.need((size_t)B * n * one)); CK(d.y.need((size_t)B * mm * one)); CK(d.ii.need((size_t)B * 3 * sizeof(int32_t))); CK(d.dd.need((size_t)B * 3 * one));
+        const size_t bws = mpcqp_band::ws_doubles(n, m, (int)nnzP, (int)nnzA);
+        CK(d.ws.need((size_t)bgrid * bws * one));
+        mpcqp_band::Batch bb; memset(&bb, 0, sizeof bb);
+        bb.B = B;
+        mpcqp_band::pattern_bind(&bb.pt, n, m, w, (int)nnzP, (int)nnzA, d.pat.as<int>(), off);
+        bb.Px = d.Px.as<double>(); bb.Ax = d.Ax.as<double>(); bb.q = d.q.as<double>(); bb.l = d.l.as<double>(); bb.u = d.u.as<double>();
+        bb.warm_x = wx ? d.wx.as<double>() : nullptr; bb.warm_y = (wy && m > 0) ? d.wy.as<double>() : nullptr;
+        bb.ws = d.ws.as<double>(); bb.ws_stride = (long long)bws;
+        bb.x = d.x.as<double>(); bb.y = (y && m > 0) ? d.y.as<double>() : nullptr; bb.info_i = d.ii.as<int32_t>(); bb.info_d = d.dd.as<double>();
+        mpcqp_band::Settings bs; memcpy(&bs, &st, sizeof bs);
+        e->last_launches = 0;
+        CK(cudaEventRecord(e->ev0, e->stream));
+        CK(cudaEventRecord(e->evs, e->stream));
+        const int rc = mpcqp_band::launch(bb, bgrid, bs, e->stream);
+        if (rc) { e->err = std::string("mpcqp_band_solve_kernel: ") + cudaGetErrorString((cudaError_t)rc); return MPCQP_ERR_CUDA; }
+        CK(cudaEventRecord(e->ev1, e->stream));
+        e->last_launches = 1; e->last_fast = 5;
+        CK(cudaMemcpyAsync(x, d.x.p, (size_t)B * n * one, cudaMemcpyDeviceToHost, e->stream));
+        if (y && m > 0) CK(cudaMemcpyAsync(y, d.y.p, (size_t)B * m * one, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(info_i, d.ii.p, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(info_d, d.dd.p, (size_t)B * 3 * one, cudaMemcpyDeviceToHost, e->stream));
+        return mpcqp_engine_sync(e);
+      }
+    }
+  }
   const int grid = mpcqp_dense::grid_size(B, n, m, e->device);
-  if (grid < 1) { e->err = "generic path: the kernel does not fit this device (shared memory / registers)"; cudaGetLastError(); return MPCQP_ERR_CUDA; }
   const size_t wsd = mpcqp_dense::ws_doubles(n, m);
   auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t r = b.need(bytes ? bytes : 8); if (r != cudaSuccess || !bytes) return r;

@@ -154,13 +154,14 @@ class Engine:
     @property
     def last_path(self) -> str:
         """'cta' (4-warp CTA per QP, PCR solve), 'fast' (one warp per QP, register-resident), 'generic'
-        (one warp per QP, shared-memory kernel for any stage-structured shape) or 'dense' (unstructured QP, one CTA)."""
-        return {2: "cta", 1: "fast", 4: "dense"}.get(int(self.lib.mpcqp_engine_last_path(self.h)), "generic")
+        (one warp per QP, shared-memory kernel for any stage-structured shape), 'band' (unstructured QP, banded KKT factor, one
+        warp) or 'dense' (unstructured QP, dense KKT factor, one CTA)."""
+        return {2: "cta", 1: "fast", 4: "dense", 5: "band"}.get(int(self.lib.mpcqp_engine_last_path(self.h)), "generic")
 
     def force_generic(self, on=True):
         """True / 1 / 'generic': generic kernel; 2 / 'fast': one-warp register kernel; 3 / 'cta_plain': CTA kernel without
         the assistant warps on one-per-SM launches; False / 0 / 'cta': default dispatch."""
-        names = {"generic": 1, "fast": 2, "cta": 0, "cta_plain": 3}
+        names = {"generic": 1, "fast": 2, "cta": 0, "cta_plain": 3, "dense": 4}
         code = names[on] if isinstance(on, str) else (1 if on is True else int(on))
         self._check(self.lib.mpcqp_engine_force_generic(self.h, C.c_int(code)))
 

@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libemul.so")
 SRC = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_core.cuh"),
-       os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_dense.cuh")]
+       os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_dense.cuh"), os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_band.cuh"),
+       os.path.join(ROOT, "intent-mpc_b200", "csrc", "mpcqp_band_host.hpp")]
 
 DEFAULT_D = dict(rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3, eps_prim_inf=1e-4, eps_dual_inf=1e-4,
                  adaptive_rho_tolerance=5.0)
@@ -80,7 +81,12 @@ def solve(mb, want_y=True, linsys=0, finite_inf=None, **settings):
     return out
 
 
-def solve_dense(qb, warm_y=None, **settings):
+def solve_band(qb, warm_y=None, **settings):
+    """The sparse generic-path kernel source (mpcqp_band.cuh) on the host; out["bandwidth"] = the RCM half-bandwidth."""
+    return solve_dense(qb, warm_y=warm_y, _entry="emul_band_solve", **settings)
+
+
+def solve_dense(qb, warm_y=None, _entry="emul_dense_solve", **settings):
     """The generic-path kernel source (mpcqp_dense.cuh) on the host, one QpBatch problem at a time."""
     build()
     lib = C.CDLL(SO)
@@ -99,11 +105,15 @@ def solve_dense(qb, warm_y=None, **settings):
         ii = np.zeros(3, np.int32); dd = np.zeros(3)
         wx = np.ascontiguousarray(qb.warm_x[b]) if qb.warm_x is not None else None
         wy = np.ascontiguousarray(warm_y[b]) if warm_y is not None else None
-        lib.emul_dense_solve(C.c_int(n), C.c_int(m), pat[0].ctypes.data_as(LL), pat[1].ctypes.data_as(LL),
+        rc = getattr(lib, _entry)(C.c_int(n), C.c_int(m), pat[0].ctypes.data_as(LL), pat[1].ctypes.data_as(LL),
                              dp(np.ascontiguousarray(qb.P_val[b])), pat[2].ctypes.data_as(LL), pat[3].ctypes.data_as(LL),
                              dp(np.ascontiguousarray(qb.A_val[b])), dp(np.ascontiguousarray(qb.q[b])),
                              dp(np.ascontiguousarray(qb.l[b])), dp(np.ascontiguousarray(qb.u[b])), dp(wx), dp(wy), dp(sdv),
                              siv.ctypes.data_as(I), dp(out["x"][b]), dp(out["y"][b]), ii.ctypes.data_as(I), dp(dd))
+        if _entry == "emul_band_solve":
+            if rc < 0:
+                raise RuntimeError(f"pattern not eligible for the band path (half-bandwidth {-rc})")
+            out["bandwidth"] = rc
         out["status"][b], out["iter"][b], out["rho_updates"][b] = ii
         out["obj"][b], out["pri_res"][b], out["dua_res"][b] = dd
     return out

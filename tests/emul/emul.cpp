@@ -68,3 +68,36 @@ extern "C" int emul_dense_solve(int n, int m, const long long* Pc, const long lo
   info_i[0] = ii[0]; info_i[1] = ii[1]; info_i[2] = ii[2];
   return 0;
 }
+
+// ---- sparse generic path: intent-mpc_b200/csrc/mpcqp_band.cuh with one "lane" (host pattern analysis as the library does) ----
+#include "../../intent-mpc_b200/csrc/mpcqp_band_host.hpp"
+
+// returns the half-bandwidth found (solve done), or -(bandwidth) when the pattern is not eligible for the band path
+extern "C" int emul_band_solve(int n, int m, const long long* Pc, const long long* Pi, const double* Px, const long long* Ac,
+                               const long long* Ai, const double* Ax, const double* q, const double* l,
+                               const double* u, const double* warm_x, const double* warm_y, const double* settings_d,
+                               const int* settings_i, double* x, double* y, int* info_i, double* info_d) {
+  namespace bq = mpcqp_band;
+  bq::Settings st;
+  st.rho = settings_d[0]; st.sigma = settings_d[1]; st.alpha = settings_d[2]; st.eps_abs = settings_d[3];
+  st.eps_rel = settings_d[4]; st.eps_prim_inf = settings_d[5]; st.eps_dual_inf = settings_d[6];
+  st.adaptive_rho_tolerance = settings_d[7];
+  st.max_iter = settings_i[0]; st.scaling = settings_i[1]; st.adaptive_rho = settings_i[2];
+  st.adaptive_rho_interval = settings_i[3]; st.check_termination = settings_i[4]; st.warm_start = settings_i[5];
+  std::vector<int> flat; int off[14], w = 0;
+  if (!bq::pattern_build(n, m, (const int64_t*)Pc, (const int64_t*)Pi, (const int64_t*)Ac, (const int64_t*)Ai, &flat, off, &w)) return -w;
+  bq::Batch bt; memset(&bt, 0, sizeof bt);
+  bt.B = 1;
+  bq::Pattern& pt = bt.pt;
+  pt.n = n; pt.m = m; pt.N = n + m; pt.w = w; pt.nnzP = (int)Pc[n]; pt.nnzA = (int)Ac[n];
+  const int* f = flat.data();
+  pt.Pc = f + off[0]; pt.Pi = f + off[1]; pt.Ac = f + off[2]; pt.Ai = f + off[3]; pt.Pr_ptr = f + off[4]; pt.Pr_pos = f + off[5]; pt.Pr_col = f + off[6];
+  pt.Ar_ptr = f + off[7]; pt.Ar_pos = f + off[8]; pt.Ar_col = f + off[9]; pt.slotP = f + off[10]; pt.slotA = f + off[11]; pt.perm = f + off[12]; pt.iperm = f + off[13];
+  bt.Px = Px; bt.Ax = Ax; bt.q = q; bt.l = l; bt.u = u; bt.warm_x = warm_x; bt.warm_y = warm_y; bt.x = x; bt.y = y;
+  int32_t ii[3]; bt.info_i = ii; bt.info_d = info_d;
+  std::vector<double> ws(bq::ws_doubles(n, m, pt.nnzP, pt.nnzA)), sm(bq::smem_doubles(n + m, w));
+  bq::Solver sv;
+  sv.run(bt, 0, st, ws.data(), sm.data(), 0);
+  info_i[0] = ii[0]; info_i[1] = ii[1]; info_i[2] = ii[2];
+  return w;
+}

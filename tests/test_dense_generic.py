@@ -52,7 +52,18 @@ def test_emulated_dense_kernel_matches_reference_golden(name):
     _check(name, EM.solve_dense(PA.cases()[name]), g)
 
 
-def _solve_axes(eng, qb, E, update_to=None):
+@pytest.mark.parametrize("name", NAMES)
+def test_emulated_band_kernel_matches_reference_golden(name):
+    """Kernel SOURCE of the sparse generic path (csrc/mpcqp_band.cuh, with the library's own RCM pattern analysis) compiled for the
+    host: logic check without a GPU.  polyTrajSolver's KKT matrices are narrow-banded under RCM (half-bandwidth <= 12)."""
+    from tests.emul import binding as EM
+    g = np.load(GOLD)
+    out = EM.solve_band(PA.cases()[name])
+    assert out["bandwidth"] <= 12
+    _check(name, out, g)
+
+
+def _solve_axes(eng, qb, E, update_to=None, path="band"):
     """x, y, z problems like polyTrajSolver::setUpProblem (:162-222) [+ updateProblem (:225-239)] and solve."""
     outs = []
     for b in range(3):
@@ -63,19 +74,22 @@ def _solve_axes(eng, qb, E, update_to=None):
             pr.update_bounds(update_to.l[b], update_to.u[b])
             pr.warm_start(np.zeros(qb.n), np.zeros(qb.m))     # the golden re-solve starts cold
             r = pr.solve()
-        assert eng.last_path == "dense" and eng.last_launches == 1
+        assert eng.last_path == path and eng.last_launches == 1
         pr.close()
         outs.append(r)
     return {k: np.array([o[k] for o in outs]) for k in ("x", "y", "status", "iter", "rho_updates", "obj", "pri_res", "dua_res")}
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path", ["band", "dense"])
 @pytest.mark.parametrize("name", NAMES)
-def test_dense_kernel_matches_reference_golden(name):
+def test_generic_kernels_match_reference_golden(name, path):
+    """Both generic kernels: the sparse one the dispatcher picks for these patterns, and the dense one pinned for the A/B."""
     from intent_mpc_b200 import engine as E
     g = np.load(GOLD)
     eng = E.Engine(0)
-    _check(name, _solve_axes(eng, PA.cases()[name], E), g)
+    eng.force_generic("dense" if path == "dense" else "cta")
+    _check(name, _solve_axes(eng, PA.cases()[name], E, path=path), g)
     eng.close()
 
 
@@ -133,7 +147,7 @@ def test_dense_kernel_takes_a_perturbed_mpc_problem_and_large_ones_are_refused()
     pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[0], qb.q[0], qb.A_colptr, qb.A_rowidx, qb.A_val[0], qb.l[0], qb.u[0])
     pr.warm_start(qb.warm_x[0])
     r = pr.solve(); pr.close()
-    assert eng.last_path == "dense"
+    assert eng.last_path == "dense"                          # its band (N = 1126) does not fit shared memory
     assert r["status"] == want["status"][0] and r["iter"] == want["iter"][0] and r["rho_updates"] == want["rho_updates"][0]
     assert rel_inf(r["x"][None], want["x"]).max() < TOL and abs((r["obj"] - want["obj"][0]) / want["obj"][0]) < TOL
     n = 3000; m = 1200                                       # identity P, A = first m rows of I: unstructured, too large
@@ -151,7 +165,7 @@ def test_dense_batch_entry_matches_reference_golden(name):
     g = np.load(GOLD)
     eng = E.Engine(0)
     r = E.solve_qp_batch(eng, PA.cases()[name])
-    assert eng.last_path == "dense" and eng.last_launches == 1
+    assert eng.last_path in ("band", "dense") and eng.last_launches == 1
     _check(name, r, g)
     eng.close()
 
@@ -210,7 +224,7 @@ def test_planner_qp_with_fov_half_space_rows_runs_on_the_generic_path():
             pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[b], qb.q[b], qb.A_colptr, qb.A_rowidx, qb.A_val[b], qb.l[b], qb.u[b])
             pr.warm_start(qb.warm_x[b], np.zeros(qb.m))
             r = pr.solve()
-            assert eng.last_path == "dense"
+            assert eng.last_path == "dense"                  # N = 1184: the band would not fit shared memory
             for k in got:
                 got[k].append(r[k])
             pr.close()

@@ -56,12 +56,17 @@ def test_oracle_port_matches_reference_golden(name):
     _check(name, OB.PortOsqp().solve_batch(qb, want_y=True, nthreads=os.cpu_count() or 1, **kw), np.load(GOLD))
 
 
+@pytest.mark.parametrize("kernel", ["dense", "band"])
 @pytest.mark.parametrize("name", SMALL)
-def test_emulated_dense_kernel_matches_reference_golden(name):
-    """Kernel SOURCE of the generic path (csrc/mpcqp_dense.cuh) compiled for the host: logic check without a GPU."""
+def test_emulated_generic_kernels_match_reference_golden(name, kernel):
+    """Kernel SOURCE of the generic paths (csrc/mpcqp_dense.cuh, csrc/mpcqp_band.cuh) compiled for the host: logic check without a GPU."""
     from tests.emul import binding as EM
     qb, kw = IC.cases()[name]
-    _check(name, EM.solve_dense(qb, **kw), np.load(GOLD))
+    if kernel == "band" and "rand" in name:
+        with pytest.raises(RuntimeError, match="not eligible"):      # unstructured random patterns: half-bandwidth > 31, dense kernel
+            EM.solve_band(qb, **kw)
+        return
+    _check(name, (EM.solve_dense if kernel == "dense" else EM.solve_band)(qb, **kw), np.load(GOLD))
 
 
 @pytest.mark.parametrize("horizon,linsys", [(30, 0), (30, 1), (60, 0)])
@@ -87,7 +92,7 @@ def test_single_problem_abi_reports_infeasibility_like_osqp(name):
         pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[0], qb.q[0], qb.A_colptr, qb.A_rowidx, qb.A_val[0], qb.l[0], qb.u[0],
                        settings=E.default_settings(**kw))
         r = pr.solve()
-        assert eng.last_path == "dense"
+        assert eng.last_path in ("band", "dense")            # generic kernels: the sparse one for these small patterns
         got = {k: np.asarray([r[k]]) for k in ("status", "iter", "rho_updates", "obj")}
         got["x"] = r["x"][None]; got["y"] = r["y"][None]
         _check(name, got, np.load(GOLD))
@@ -148,7 +153,7 @@ def test_structured_kernels_declare_primal_infeasibility_like_osqp(name, path):
             pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[b], qb.q[b], qb.A_colptr, qb.A_rowidx, qb.A_val[b], qb.l[b], qb.u[b])
             pr.warm_start(qb.warm_x[b], np.zeros(qb.m))
             r = pr.solve()
-            assert eng.last_path != "dense"                       # still the planner's structure: a stage kernel
+            assert eng.last_path not in ("dense", "band")         # still the planner's structure: a stage kernel
             if path:
                 assert eng.last_path == path
             for k in got:
