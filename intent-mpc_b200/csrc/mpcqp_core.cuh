@@ -130,14 +130,17 @@ MQ_HHD int iter_slots(int R) { return NV + 2 * (NBR + R) + NV + 8 + 3; }
 // slots so that the setup phase can build it in shared memory (in the not-yet-used PCR region) and copy it out once.
 MQ_HHD int cold_slots(int R) { return 2 * (NBR + R) + 2 * NV + (NBR + R) + NV + NV + 3 * R + R + iter_slots(R); }
 constexpr int kWorkSlots = 108;             // PCR factor workspace: D / D^-1, L, next L (36 slots each); r / y exchange buffers alias it
+// generic mode: slots that live in global scratch instead of shared memory (see map_memory)
+MQ_HHD int generic_global_slots(int R) { return (NBR + R) + NV + NV + 3 * R + R + 2 * (NBR + R); }
 MQ_HHD int smem_doubles(int NS, int R, int mode, bool wide = false) {
   if (mode == kModeCta) return kPcrDoubles + (kWorkSlots + (wide ? 7 * R : 0)) * NS;
-  return (hot_slots(R, mode) + (mode == kModeWarp ? 0 : iter_slots(R))) * NS + 72;
+  if (mode == kModeWarp) return hot_slots(R, mode) * NS + 72;
+  return (hot_slots(R, mode) + iter_slots(R) - generic_global_slots(R)) * NS + 72;
 }
 MQ_HHD int ws_doubles(int NS, int R, int mode) {
   const int base = 2 * (NBR + R) + 2 * NV;
   if (mode == kModeCta) return (cold_slots(R) + NV + 36 + 36 + 27 + 36 + 72 + 36 + 3 + NV + (NBR + R)) * NS;
-  return (base + (mode == kModeWarp ? iter_slots(R) : 0)) * NS;
+  return (base + (mode == kModeWarp ? iter_slots(R) : generic_global_slots(R))) * NS;
 }
 // cold block at `g` (same order wherever it lives)
 MQ_HHD double* map_cold(Mem& m, double* g, int NS, int R) {
@@ -164,11 +167,19 @@ MQ_HHD void map_memory(Mem& m, double* sm, double* ws, int NS, int R, int mode) 
   m.E = g; g += MK * NS; m.D = g; g += NV * NS; m.DY = g; g += MK * NS; m.DX = g; g += NV * NS;
   const bool fast = mode == kModeWarp;
   m.PCR = m.WK = m.RA = m.RS = m.YB = m.PD = m.PL = m.PI = m.OG = m.OX = m.OU = m.ROW = nullptr;
-  m.RH = p; p += MK * NS; m.SD = p; p += NV * NS; m.CQ = p; p += NV * NS; m.G3 = p; p += 3 * R * NS; m.LO = p; p += R * NS;
+  // generic mode: the per-row data that an iteration only streams through once (rho vector, sigma / D^2, scaled cost, obstacle
+  // gradients and bounds, the constraint iterates z and u) live in the warp's L2-resident global scratch; shared memory keeps
+  // what the serial chain and the neighbour-stage reads touch (factor, right-hand side, x): 2.4x less shared memory per QP, so
+  // that three warps instead of one share an SM at horizon 60
+  double*& r_ = fast ? p : g;
+  m.RH = r_; r_ += MK * NS; m.SD = r_; r_ += NV * NS; m.CQ = r_; r_ += NV * NS; m.G3 = r_; r_ += 3 * R * NS; m.LO = r_; r_ += R * NS;
   m.W = p; p += (fast ? 6 : NV) * NS; m.SI = p; p += 36 * NS; m.GG = p; p += 36 * NS; m.DSI = p; p += 2 * NS; m.ESD = p; p += 2 * NS;
   m.DGI = p; p += 2 * NS; m.FS = p; p += 6 * NS; m.DAI = p; p += 3 * NS; m.CV = p; p += 12 * NS; m.PK = p; p += 72;
-  double*& c = fast ? g : p;
-  m.X = c; c += NV * NS; m.Z = c; c += MK * NS; m.U = c; c += MK * NS; m.B = c; c += NV * NS; m.TD = c; c += 8 * NS; m.MA = c; c += 3 * NS;
+  if (fast) {
+    m.X = g; g += NV * NS; m.Z = g; g += MK * NS; m.U = g; g += MK * NS; m.B = g; g += NV * NS; m.TD = g; g += 8 * NS; m.MA = g; g += 3 * NS;
+  } else {
+    m.X = p; p += NV * NS; m.Z = g; g += MK * NS; m.U = g; g += MK * NS; m.B = p; p += NV * NS; m.TD = p; p += 8 * NS; m.MA = p; p += 3 * NS;
+  }
 }
 
 // Dimensions: compile-time in fast mode, runtime otherwise.
