@@ -446,7 +446,7 @@ def run_b200(args, rank, world, local_rank):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None                                   # ncu dram__bytes of one step of this workload (committed capture), if it is this workload
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if B == 1024 and R == 4:
             traffic = int(tj["bytes_per_step"])
     except Exception:
