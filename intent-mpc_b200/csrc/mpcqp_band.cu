@@ -10,7 +10,7 @@ namespace mpcqp_band {
 
 // Persistent: one warp (= one CTA of 32 threads) per QP at a time, QPs taken round-robin.  Shared memory: the band factor
 // and two N-vectors; everything else in the warp's private global workspace (L2-resident).
-__global__ void __launch_bounds__(32, 16) mpcqp_band_solve_kernel(const __grid_constant__ Batch bt, const __grid_constant__ Settings st) {
+__global__ void __launch_bounds__(32, 12) mpcqp_band_solve_kernel(const __grid_constant__ Batch bt, const __grid_constant__ Settings st) {
   extern __shared__ double bq_smem[];
   Solver sv;
   double* ws = bt.ws + (size_t)blockIdx.x * bt.ws_stride;

@@ -231,3 +231,72 @@ def test_planner_qp_with_fov_half_space_rows_runs_on_the_generic_path():
         _check_fov({k: np.asarray(v) for k, v in got.items()}, np.load(FOV_GOLD))
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_out_of_pattern_bounds_move_a_planner_qp_to_the_generic_path():
+    """osqp_setup / osqp_update_bounds accept any l <= u.  An mpcPlanner QP whose bounds leave the planner's pattern (a state box
+    that differs between stages, a finite upper bound on an obstacle row) must still be solved — on a generic kernel — and
+    give what the reference gives, both when the bounds arrive at setup and when they arrive through mpcqp_update_bounds."""
+    from intent_mpc_b200 import engine as E
+    from intent_mpc_b200 import workloads as W
+    from oracle import bindings as OB
+    from tests.helpers import to_qp_batch
+    orc = OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
+    qb = to_qp_batch(W.static_batch(1, num_obs=2, seed0=21))
+    NS, N = 30, 29
+    l2 = qb.l.copy(); u2 = qb.u.copy()
+    u2[0, 8 * NS + 8 * 12 + 1] = 1.25                       # y of stage 12 capped: the state box is no longer stage-uniform
+    u2[0, 16 * NS + 5 * N + 7] = 50.0                        # one obstacle row gets a finite upper bound
+    qb2 = dataclasses.replace(qb, l=l2, u=u2)
+    want = orc.solve_batch(qb2, want_y=False)
+    eng = E.Engine(0)
+    try:
+        # (a) at setup
+        pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[0], qb.q[0], qb.A_colptr, qb.A_rowidx, qb.A_val[0], l2[0], u2[0])
+        pr.warm_start(qb.warm_x[0], np.zeros(qb.m))
+        r = pr.solve(); pr.close()
+        assert eng.last_path in ("dense", "band")
+        assert r["status"] == want["status"][0] and r["iter"] == want["iter"][0]
+        assert rel_inf(r["x"][None], want["x"]).max() < TOL
+        # (b) through update_bounds on a problem that was set up with the planner's own bounds (stage kernel first)
+        pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[0], qb.q[0], qb.A_colptr, qb.A_rowidx, qb.A_val[0], qb.l[0], qb.u[0])
+        pr.warm_start(qb.warm_x[0], np.zeros(qb.m))
+        first = pr.solve()
+        assert eng.last_path == "cta"
+        ref1 = orc.solve_batch(qb, want_y=False)
+        assert first["status"] == ref1["status"][0] and first["iter"] == ref1["iter"][0]
+        pr.update_bounds(l2[0], u2[0])
+        pr.warm_start(qb.warm_x[0], np.zeros(qb.m))
+        r = pr.solve(); pr.close()
+        assert eng.last_path in ("dense", "band")
+        assert r["status"] == want["status"][0] and r["iter"] == want["iter"][0]
+        assert rel_inf(r["x"][None], want["x"]).max() < TOL
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_engine_outlives_destroy_while_problems_are_alive_and_warm_start_x_keeps_the_dual():
+    """mpcqp_engine_destroy with live problems only marks the engine (the last mpcqp_cleanup releases it): a Solver that
+    outlives its thread's engine stays usable.  osqp_warm_start_x replaces x only: the next solve keeps the previous dual."""
+    from intent_mpc_b200 import engine as E
+    from oracle import bindings as OB
+    orc = OB.RefOsqp() if OB.RefOsqp.available() else OB.PortOsqp()
+    qb = PA.cases()["poly_k6"]
+    eng = E.Engine(0)
+    pr = E.Problem(eng, qb.n, qb.m, qb.P_colptr, qb.P_rowidx, qb.P_val[0], qb.q[0], qb.A_colptr, qb.A_rowidx, qb.A_val[0], qb.l[0], qb.u[0])
+    r1 = pr.solve()
+    h = eng.h; eng.h = None                                  # destroy the engine under the problem
+    assert eng.lib.mpcqp_engine_destroy(h) == 0
+    # re-solve with a new primal start only: the dual start must be r1's y (what a (x, y) warm start of the oracle gives)
+    x0 = 0.5 * r1["x"]
+    pr.warm_start(x0)
+    r2 = pr.solve()
+    one = dataclasses.replace(qb, P_val=qb.P_val[:1], q=qb.q[:1], A_val=qb.A_val[:1], l=qb.l[:1], u=qb.u[:1], warm_x=x0[None])
+    want = orc.solve_batch(one, warm_y=r1["y"][None], want_y=False)
+    cold = orc.solve_batch(one, want_y=False)
+    assert r2["status"] == want["status"][0] and r2["iter"] == want["iter"][0]
+    assert rel_inf(r2["x"][None], want["x"]).max() < TOL
+    assert want["iter"][0] != cold["iter"][0] or True          # (informative: with y = 0 the oracle may take another path)
+    pr.close()                                               # the last cleanup releases the engine
