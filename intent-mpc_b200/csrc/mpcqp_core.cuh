@@ -1,28 +1,33 @@
-// mpcqp_core.cuh — one-warp-per-QP ADMM solver for the stage-structured MPC QP of
-// trajPlanner::mpcPlanner::solveTraj (reference: trajectory_planner/include/trajectory_planner/
-// mpcPlanner.cpp:375-541; QP layout mpcPlanner.cpp:932-1146), reproducing the iterate sequence of the
-// OSQP 0.6.2 solver the reference calls through OsqpEigen::Solver (constants:
+// mpcqp_core.cuh — ADMM solvers for the stage-structured MPC QP of trajPlanner::mpcPlanner::solveTraj (reference:
+// trajectory_planner/include/trajectory_planner/mpcPlanner.cpp:375-541; QP layout mpcPlanner.cpp:932-1146), reproducing the
+// iterate sequence of the OSQP 0.6.2 solver the reference calls through OsqpEigen::Solver (constants:
 // third_party/osqp/constants.h:59-118, step structure: third_party/osqp/auxil.h:21-154).
 //
-// This is NOT a port of OSQP/QDLDL.  Differences that matter:
-//   * lane = horizon stage.  All per-stage data (x_k,u_k, the 21+R constraint rows of stage k, the
-//     factor blocks of stage k) live in one shared-memory column [slot][stage], so every per-row /
-//     per-variable step of ADMM is a conflict-free lane-parallel loop and neighbour-stage coupling
-//     (dynamics rows) is a read of column k±1.
-//   * The iteration runs in UN-scaled coordinates: xh = D x, zh = E^-1 z, uh = E^-1 (y/rho).  Ruiz
-//     equilibration (scaling.h: scale_data) then only enters through Rh_i = rho_i E_i^2 and
-//     sigma/D_j^2, the constraint matrix keeps its exact constants (+-1, ts, ts^2/2, obstacle
-//     gradients) and is never stored.  This is algebraically the same iteration as OSQP's
-//     (DESIGN.md §3 derives it); only rounding differs.
-//   * The KKT solve of update_xz_tilde (auxil.h:67) is done on the reduced SPD system
-//     (c P + sigma D^-2 + A' Rh A) xt = rhs.  Slack states, accelerations and slack inputs are "leaf"
-//     variables that are eliminated in closed form, leaving a 6x6 block-tridiagonal system in
-//     (p_k, v_k) that is factored by a twisted (two-ended) block LDL' and solved by 12 lanes with
-//     warp shuffles.
+// This is NOT a port of OSQP/QDLDL.  What all kernel generations in this file share:
+//   * lane = horizon stage.  Per-stage data (x_k, u_k, the 21+R constraint rows of stage k, the factor blocks of stage k) sit
+//     in columns [slot][stage], so every per-row / per-variable step of ADMM is a conflict-free lane-parallel loop and the
+//     neighbour-stage coupling (dynamics rows) is a read of column k±1 (or a warp shuffle).
+//   * The iteration runs in UN-scaled coordinates: xh = D x, zh = E^-1 z, uh = E^-1 (y/rho).  Ruiz equilibration (scaling.h:
+//     scale_data) then only enters through Rh_i = rho_i E_i^2 and sigma/D_j^2, the constraint matrix keeps its exact constants
+//     (+-1, ts, ts^2/2, obstacle gradients) and is never stored.  Algebraically OSQP's iteration; only rounding
+//     differs.
+//   * The KKT solve of update_xz_tilde (auxil.h:67) is done on the reduced SPD system (c P + sigma D^-2 + A' Rh A) xt = rhs.
+//     Slack states, accelerations and slack inputs are "leaf" variables eliminated in closed form, leaving a 6x6
+//     block-tridiagonal system in (p_k, v_k).
+// Three ways to run it (Qp<NST, RT, QMODE, ASSIST>, see `Mem` below):
+//   * mode 2, the CTA kernels (horizon 30; the hot path): one 4-warp CTA per QP, warps 0-2 own one axis each, warp 3 the slack
+//     variables; iterates in registers from the first to the last iteration; the block-tridiagonal system is solved by block
+//     parallel cyclic reduction (pcr_factor_cta, solve_role) whose per-level 6x6 matrices fill shared memory; optional three
+//     assistant warps keep the matrices of the upper levels in registers (launches with one CTA per SM); a "wide" variant
+//     takes a run-time obstacle count per instance.
+//   * mode 1, the one-warp register kernel (horizon <= 32; first generation, kept for A/B tests): twisted two-ended block
+//     LDL' chain solved by 12 lanes with warp shuffles.
+//   * mode 0, the generic one-warp kernel (any horizon / obstacle count): the same chain with the factor, the right-hand side
+//     and x in shared memory and the streaming per-row data in L2-resident global scratch.
 //
-// The same source compiles for the host when MPCQP_HOST_EMUL is defined: lane loops become plain
-// loops over all stages.  That build exists only for tests/ (logic checks without a GPU); the
-// shipped library contains no host solve path.
+// The same source compiles for the host when MPCQP_HOST_EMUL is defined: lane loops become plain loops over all stages
+// (mode 0, and the PCR linear algebra of mode 2 around the generic iteration).  That build exists only for tests/ (logic
+// checks without a GPU); the shipped library contains no host solve path.
 #pragma once
 #include <math.h>
 #include <stdint.h>
