@@ -142,6 +142,9 @@ MQ_HHD int smem_doubles(int NS, int R, int mode, bool wide = false) {
   if (mode == kModeWarp) return hot_slots(R, mode) * NS + 72;
   return (hot_slots(R, mode) + iter_slots(R) - generic_global_slots(R)) * NS + 72;
 }
+// threads of a CTA-mode block: four solver warps; one-per-SM ("assist") blocks add three PCR assistants and, from four obstacle
+// rows per stage on (compile-time R, not the wide kernel), the row helper (Qp::kCtaThreads is the same number)
+MQ_HHD int cta_threads(int R, bool assist, bool wide) { return !assist ? 128 : ((!wide && R >= 4) ? 256 : 224); }
 MQ_HHD int ws_doubles(int NS, int R, int mode) {
   const int base = 2 * (NBR + R) + 2 * NV;
   if (mode == kModeCta) return (cold_slots(R) + NV + 36 + 36 + 27 + 36 + 72 + 36 + 3 + NV + (NBR + R)) * NS;
@@ -248,6 +251,17 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   static constexpr bool kCta = QMODE == kModeCta;
   static constexpr bool kWide = RT == kWideR;            // run-time R, obstacle rows in shared memory (CTA mode only)
   static constexpr int RC = kWide ? 0 : RT;              // compile-time R of the register-row code (none in wide mode)
+  // One-per-SM blocks with at least four obstacle rows carry an eighth warp, the row helper: the rows that would belong to the
+  // slack warp (o = 3, 7) live in shared memory (kHelpSlots values per row and stage) and the helper runs them in every iteration,
+  // so that the slack warp — four variables, the longest instruction stream between y and the next right-hand side — is not
+  // what the axis warps wait for.  Same arithmetic as the register rows (obstacle_rows): results do not depend on the variant.
+  static constexpr bool kHelp = ASSIST && !kWide && RC >= 4;
+  // up to kHelpAllMax rows per stage the helper runs ALL obstacle rows (their four chains interleave in one warp and are done
+  // before the axis warps need them), which also frees the axis warps of a row's registers and instructions
+  static constexpr int kHelpAllMax = 0;     // (measured at four rows: 1.67 us per iteration against 1.61 with the slack warp's row only)
+  static constexpr bool kHelpAll = kHelp && RC <= kHelpAllMax;
+  static constexpr int kHelpSlots = 12;
+  static constexpr int kCtaThreads = kHelp ? 256 : (ASSIST ? 224 : 128);
   static_assert(!kWide || (QMODE == kModeCta && ASSIST), "wide mode is a one-per-SM CTA kernel");
   static_assert(QMODE == kModeGeneric || NST > 0, "modes 1 and 2 need compile-time dims");
   static_assert(QMODE != kModeCta || NST == 30, "the CTA path is built for horizon 30 (5 PCR levels)");
@@ -1548,7 +1562,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   static MQ_HD double up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
   static MQ_HD double dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
   static MQ_HD double clampd(double v, double lo, double hi) { double z = v > lo ? v : lo; return z < hi ? z : hi; }
-  static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3, kBarT = 4, kBarCmd = 5, kBarH1 = 6, kBarH2 = 7, kBarA = 8;
+  static constexpr int kBarAll = 1, kBarAxis = 2, kBarY = 3, kBarT = 4, kBarCmd = 5, kBarH1 = 6, kBarRS = 7, kBarA = 8;
 
 #ifdef MPCQP_PHASE_TIMING
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // setup, leaf, pcr factor, load, iterate, info+check, park/adapt, store
@@ -1904,7 +1918,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   // single-warp array code on warp 0.
   template <bool AX> MQ_HD void solve_role(const int warp, volatile int* flag, volatile int* cmd) {
     constexpr int NVR = AX ? 3 : 4;
-    constexpr int NOW = (RC + 3) / 4;                   // obstacle rows owned per warp: row o belongs to warp o % 4
+    // obstacle row o belongs to warp o % 4: in registers (NOW rows, run by this warp), or — the rows the helper runs: the slack
+    // warp's, or everybody's (kHelpAll) — in shared memory (NHR rows; this warp only loads / parks / checks / rescales them)
+    constexpr bool kSmemRows = kHelpAll || (kHelp && !AX);
+    constexpr int NOW = kSmemRows ? 0 : (RC + 3) / 4;
+    constexpr int NHR = kSmemRows ? (RC + 3) / 4 : 0;
     constexpr bool kRows = kWide || RC > 0;             // the QP has obstacle rows
     constexpr int RW = NOW > 0 ? NOW : 1;
     const int cc = warp;
@@ -1933,7 +1951,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     auto blo = [&](int e) { if constexpr (AX) return lo[e]; else return sh.blo[e < 2 ? 6 + e : 9 + e]; };
     auto bhi = [&](int e) { if constexpr (AX) return hi[e]; else return sh.bhi[e < 2 ? 6 + e : 9 + e]; };
     double dai = 0, cv0 = 0, cv1 = 0, cv2 = 0, cv3 = 0, cv2m = 0, cv3m = 0, ogp = 0;        // AX (ogp: parked obstacle part of b_p)
-    double dsi[2], esd[2], esdn[2], dgi[2], fs[6];                                              // !AX
+    double dsi[2], esd[2], esdn[2], dgi[2], fs[6];                                              // !AX (dgi, fs: both roles in wide mode)
+    // row helper's rows: z, u, Rh, low, gradient (3), dgi and fs (3) of the row's slack type, the type itself
+    auto HR = [&](int o, int slot) -> double& { return m.ROW[(o * kHelpSlots + slot) * NS + k]; };
     unsigned slmask = 0;                                // !AX: bit o set when row o is softened by sigma_s (slack input 4)
     // owned obstacle rows (both roles): row o = 4 q + warp
     double zo[RW], uo[RW], orh[RW], og3[3 * RW], olo[RW], odg[RW], ofs[3 * RW];
@@ -1996,6 +2016,17 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         osl[q] = hasu ? SLK_(oo, k) : 0;
         odg[q] = DGI_(osl[q], k); ofs[3 * q] = FS_(3 * osl[q], k); ofs[3 * q + 1] = FS_(3 * osl[q] + 1, k); ofs[3 * q + 2] = FS_(3 * osl[q] + 2, k);
       }
+#pragma unroll
+      for (int h = 0; h < NHR; ++h) {                   // the row helper's rows: same values, in shared memory
+        const int o = 4 * h + warp;
+        if (o < R && live) {
+          const int sl = hasu ? SLK_(o, k) : 0;
+          HR(o, 0) = Z_(NBR + o, k); HR(o, 1) = U_(NBR + o, k); HR(o, 2) = RH_(NBR + o, k); HR(o, 3) = LO_(o, k);
+          HR(o, 4) = G3_(3 * o, k); HR(o, 5) = G3_(3 * o + 1, k); HR(o, 6) = G3_(3 * o + 2, k);
+          HR(o, 7) = DGI_(sl, k); HR(o, 8) = FS_(3 * sl, k); HR(o, 9) = FS_(3 * sl + 1, k); HR(o, 10) = FS_(3 * sl + 2, k);
+          HR(o, 11) = (double)sl;
+        }
+      }
     };
     // iterates (+ the deltas of the last iteration) back to the arrays the single-warp code and store() read
     auto park = [&]() {
@@ -2018,6 +2049,14 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         if constexpr (kWide) {
           for (int o = warp; o < R; o += 4) {
             const double zv = ZO[o * NS + k], uv = UO[o * NS + k], rv = ORH[o * NS + k];
+            Z_(NBR + o, k) = zv; U_(NBR + o, k) = uv; WSDY_(NBR + o, k) = rv * (uv - OU_(NBR + o, k)); if (hasu) RH_(NBR + o, k) = rv;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < NHR; ++h) {
+          const int o = 4 * h + warp;
+          if (o < R) {
+            const double zv = HR(o, 0), uv = HR(o, 1), rv = HR(o, 2);
             Z_(NBR + o, k) = zv; U_(NBR + o, k) = uv; WSDY_(NBR + o, k) = rv * (uv - OU_(NBR + o, k)); if (hasu) RH_(NBR + o, k) = rv;
           }
         }
@@ -2056,8 +2095,68 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         ps[0] = hasu ? s0 : 0.0; ps[1] = hasu ? s1 : 0.0;
       }
     };
+    // ---- owned obstacle rows (both roles) of one iteration: from the positions yp of this stage to the terms T4 / TP that the
+    // position rows and the slack warp pick up.  Needs only yp and r11 (XR).
+    auto obstacle_rows = [&](const double yp0, const double yp1, const double yp2) {
+      // (MP.cpp:1040-1071): grad . p_k - slack  >=  low.  The slack input of the row's type is re-derived from r11 (4 flops)
+      // instead of being fetched from warp 3.
+#pragma unroll
+      for (int q = 0; q < NOW; ++q) {
+        const int o = 4 * q + warp;
+        if (o < R) {
+          const double r11s = XR[osl[q] * NS + k];
+          const double sg = oex[q] ? odg[q] * (r11s - ofs[3 * q] * yp0 - ofs[3 * q + 1] * yp1 - ofs[3 * q + 2] * yp2) : 0.0;
+          const double zt = og3[3 * q] * yp0 + og3[3 * q + 1] * yp1 + og3[3 * q + 2] * yp2 - sg;
+          const double v = al * zt + om * zo[q] + uo[q];
+          const double zn = v > olo[q] ? v : olo[q];
+          zo[q] = zn; uo[q] = v - zn;
+          const double t = orh[q] * (zn - uo[q]);
+          // position rows get grad' t directly and, through the eliminated slack input of the row, fs dg t
+          const double ts_ = oex[q] ? odg[q] * t : 0.0;
+          if (live) {
+            T4[(4 * o) * NS + k] = fma(ofs[3 * q], ts_, og3[3 * q] * t); T4[(4 * o + 1) * NS + k] = fma(ofs[3 * q + 1], ts_, og3[3 * q + 1] * t);
+            T4[(4 * o + 2) * NS + k] = fma(ofs[3 * q + 2], ts_, og3[3 * q + 2] * t); T4[(4 * o + 3) * NS + k] = t;
+          }
+        }
+      }
+      if constexpr (kWide) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, as0 = 0.0, as1 = 0.0;
+        const double r11d = XR[k], r11st = XR[NS + k];
+        const double sgd = hasu ? dgi[0] * (r11d - fs[0] * yp0 - fs[1] * yp1 - fs[2] * yp2) : 0.0;     // slack inputs of this stage
+        const double sgs = hasu ? dgi[1] * (r11st - fs[3] * yp0 - fs[4] * yp1 - fs[5] * yp2) : 0.0;
+#pragma unroll 4
+        for (int o = warp; o < R; o += 4) {
+          const bool st_ = (slmask >> o) & 1u;
+          const double g0 = OG3[(3 * o) * NS + k], g1 = OG3[(3 * o + 1) * NS + k], g2 = OG3[(3 * o + 2) * NS + k];
+          const double zv = ZO[o * NS + k], uv = UO[o * NS + k], rv = ORH[o * NS + k], lv = OLO[o * NS + k];
+          const double zt = g0 * yp0 + g1 * yp1 + g2 * yp2 - (st_ ? sgs : sgd);
+          const double v = al * zt + om * zv + uv;
+          const double zn = v > lv ? v : lv;
+          const double un = v - zn;
+          if (live) { ZO[o * NS + k] = zn; UO[o * NS + k] = un; }
+          const double t = rv * (zn - un);
+          const double ts_ = hasu ? (st_ ? dgi[1] : dgi[0]) * t : 0.0;
+          a0 += fma(st_ ? fs[3] : fs[0], ts_, g0 * t); a1 += fma(st_ ? fs[4] : fs[1], ts_, g1 * t); a2 += fma(st_ ? fs[5] : fs[2], ts_, g2 * t);
+          if (st_) as1 += t; else as0 += t;
+        }
+        if (live) {
+          TP[(5 * warp) * NS + k] = a0; TP[(5 * warp + 1) * NS + k] = a1; TP[(5 * warp + 2) * NS + k] = a2;
+          TP[(5 * warp + 3) * NS + k] = as0; TP[(5 * warp + 4) * NS + k] = as1;
+        }
+      }
+    };
+    // u of the helper's rows before the last iteration of a burst (delta_y of the certificates); called behind the first barrier
+    // of the iteration: the helper's update of the previous iteration is ordered before it, the next one comes after kBarY
+    auto snapshot_helper_rows = [&](const bool lastit) {
+      if constexpr (NHR > 0) {
+        if (lastit && live) {
+#pragma unroll
+          for (int h = 0; h < NHR; ++h) { const int o = 4 * h + warp; if (o < R) OU_(NBR + o, k) = HR(o, 1); }
+        }
+      }
+    };
     auto iterate = [&](const int niter) {
-      if constexpr (!AX) { slack_forward(); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
+      if constexpr (!AX) { slack_forward(); bar_arrive(kBarRS, 128); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
       for (int it = 0; it < niter; ++it) {
         const bool lastit = it == niter - 1;
         if (lastit && live) {                       // iterate k-1 for the infeasibility certificates (delta_x, delta_y)
@@ -2082,9 +2181,13 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             r0 = (b[0] + ogp) - cv0 * ma; r1 = b[1] - cv1 * ma;
             r0 -= cv2m * mm; r1 -= cv3m * mm;             // cv2m = cv3m = 0 on stage 0
           }
+          // the slack warp's part of this stage's position row (written at the end of its previous iteration, long ago): folded
+          // in BEFORE the exchange, so that level 0 reads complete neighbour vectors
+          bar_sync(kBarRS, 128);
+          r0 += m.RS[k * 4 + cc];
           if (live) RA2[k * 3 + cc] = make_double2(r0, r1);
           bar_sync(kBarAll, 128);
-          r0 += m.RS[k * 4 + cc];
+          snapshot_helper_rows(lastit);
           // ---- PCR levels 0..2 (with assistants: level 0 only; they run levels 1, 2 and the final operator from registers)
           constexpr int kRowLevels = ASSIST ? 1 : kPcrLevels - 2;
 #pragma unroll
@@ -2094,11 +2197,6 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             const double2* ra = RA2 + cur * 3 * NS;
             double2 a0 = ra[kmm * 3], a1 = ra[kmm * 3 + 1], a2 = ra[kmm * 3 + 2];
             double2 c0 = ra[kpp * 3], c1 = ra[kpp * 3 + 1], c2 = ra[kpp * 3 + 2];
-            if (l == 0) {
-              const double2 sm0 = RS2[kmm * 2], sm1 = RS2[kmm * 2 + 1], sp0 = RS2[kpp * 2], sp1 = RS2[kpp * 2 + 1];
-              a0.x += sm0.x; a1.x += sm0.y; a2.x += sm1.x;
-              c0.x += sp0.x; c1.x += sp0.y; c2.x += sp1.x;
-            }
             double sa0 = mt[0].x * a0.x, sa1 = mt[3].x * a0.x, sg0 = mt[6].x * c0.x, sg1 = mt[9].x * c0.x;
             sa0 = fma(mt[0].y, a0.y, sa0); sa1 = fma(mt[3].y, a0.y, sa1); sg0 = fma(mt[6].y, c0.y, sg0); sg1 = fma(mt[9].y, c0.y, sg1);
             sa0 = fma(mt[1].x, a1.x, sa0); sa1 = fma(mt[4].x, a1.x, sa1); sg0 = fma(mt[7].x, c1.x, sg0); sg1 = fma(mt[10].x, c1.x, sg1);
@@ -2148,13 +2246,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             y0 = sa0 + sg0; y1 = sa1 + sg1;
             if (live) YB2[k * 3 + cc] = make_double2(y0, y1);
           }
-          bar_sync(kBarY, (ASSIST || kWide) ? 224 : 128);
+          bar_sync(kBarY, kCtaThreads);
           if constexpr (ASSIST) { const double2 yv = YB2[k * 3 + cc]; y0 = yv.x; y1 = yv.y; }
           if constexpr (kRows) { yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4]; }
           // ---- leaf backward: acceleration of this axis
           xt[0] = y0; xt[1] = y1;
           {
-            const double yn0 = dn1(y0), yn1 = dn1(y1);
+            double yn0, yn1;                              // y of stage k+1
+            if constexpr (ASSIST) { const double2 yn = YB2[kp * 3 + cc]; yn0 = yn.x; yn1 = yn.y; }   // (same values as a shuffle, one round trip fewer)
+            else { yn0 = dn1(y0); yn1 = dn1(y1); }
             const double a = dai * (b[2] - cv0 * y0 - cv1 * y1 - cv2 * yn0 - cv3 * yn1);
             xt[2] = hasu ? a : 0.0;
           }
@@ -2172,8 +2272,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           // ---- leaf forward, slack part (eliminate s_{k+1,t} then sigma_{k,t}): RS2 was written at the end of the last
           // iteration (or by the prologue); once every warp is past its obstacle rows, their part is added to r11
           bar_sync(kBarAll, 128);
+          snapshot_helper_rows(lastit);
           if (it > 0) { slack_obstacle_sums(); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
-          bar_sync(kBarY, ASSIST ? 224 : 128);
+          bar_sync(kBarY, kCtaThreads);
           yp0 = m.YB[k * 6]; yp1 = m.YB[k * 6 + 2]; yp2 = m.YB[k * 6 + 4];
           // ---- leaf backward: slack inputs, then slack states
           double xp[2];
@@ -2195,52 +2296,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             racc[t] = -td[t]; racc[2 + t] = 0.0;
           }
         }
-        // ---- owned obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low.  The slack input of the row's type is
-        // re-derived from r11 (4 flops) instead of being fetched from warp 3.
-#pragma unroll
-        for (int q = 0; q < NOW; ++q) {
-          const int o = 4 * q + warp;
-          if (o < R) {
-            const double r11s = XR[osl[q] * NS + k];
-            const double sg = oex[q] ? odg[q] * (r11s - ofs[3 * q] * yp0 - ofs[3 * q + 1] * yp1 - ofs[3 * q + 2] * yp2) : 0.0;
-            const double zt = og3[3 * q] * yp0 + og3[3 * q + 1] * yp1 + og3[3 * q + 2] * yp2 - sg;
-            const double v = al * zt + om * zo[q] + uo[q];
-            const double zn = v > olo[q] ? v : olo[q];
-            zo[q] = zn; uo[q] = v - zn;
-            const double t = orh[q] * (zn - uo[q]);
-            // position rows get grad' t directly and, through the eliminated slack input of the row, fs dg t
-            const double ts_ = oex[q] ? odg[q] * t : 0.0;
-            if (live) {
-              T4[(4 * o) * NS + k] = fma(ofs[3 * q], ts_, og3[3 * q] * t); T4[(4 * o + 1) * NS + k] = fma(ofs[3 * q + 1], ts_, og3[3 * q + 1] * t);
-              T4[(4 * o + 2) * NS + k] = fma(ofs[3 * q + 2], ts_, og3[3 * q + 2] * t); T4[(4 * o + 3) * NS + k] = t;
-            }
-          }
-        }
-        if constexpr (kWide) {
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, as0 = 0.0, as1 = 0.0;
-          const double r11d = XR[k], r11st = XR[NS + k];
-          const double sgd = hasu ? dgi[0] * (r11d - fs[0] * yp0 - fs[1] * yp1 - fs[2] * yp2) : 0.0;     // slack inputs of this stage
-          const double sgs = hasu ? dgi[1] * (r11st - fs[3] * yp0 - fs[4] * yp1 - fs[5] * yp2) : 0.0;
-#pragma unroll 4
-          for (int o = warp; o < R; o += 4) {
-            const bool st_ = (slmask >> o) & 1u;
-            const double g0 = OG3[(3 * o) * NS + k], g1 = OG3[(3 * o + 1) * NS + k], g2 = OG3[(3 * o + 2) * NS + k];
-            const double zv = ZO[o * NS + k], uv = UO[o * NS + k], rv = ORH[o * NS + k], lv = OLO[o * NS + k];
-            const double zt = g0 * yp0 + g1 * yp1 + g2 * yp2 - (st_ ? sgs : sgd);
-            const double v = al * zt + om * zv + uv;
-            const double zn = v > lv ? v : lv;
-            const double un = v - zn;
-            if (live) { ZO[o * NS + k] = zn; UO[o * NS + k] = un; }
-            const double t = rv * (zn - un);
-            const double ts_ = hasu ? (st_ ? dgi[1] : dgi[0]) * t : 0.0;
-            a0 += fma(st_ ? fs[3] : fs[0], ts_, g0 * t); a1 += fma(st_ ? fs[4] : fs[1], ts_, g1 * t); a2 += fma(st_ ? fs[5] : fs[2], ts_, g2 * t);
-            if (st_) as1 += t; else as0 += t;
-          }
-          if (live) {
-            TP[(5 * warp) * NS + k] = a0; TP[(5 * warp + 1) * NS + k] = a1; TP[(5 * warp + 2) * NS + k] = a2;
-            TP[(5 * warp + 3) * NS + k] = as0; TP[(5 * warp + 4) * NS + k] = as1;
-          }
-        }
+        if constexpr (!kSmemRows) obstacle_rows(yp0, yp1, yp2);
         // ---- box rows
 #pragma unroll
         for (int e = 0; e < NVR; ++e) {
@@ -2278,8 +2334,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             ogp = hasu ? sgo : 0.0;
           }
         } else {
-          if constexpr (kRows) bar_arrive(kBarT, 128);
+          // (with a row helper the slack warp owns no rows and the helper announces them)
+          if constexpr (kRows && !kHelp) bar_arrive(kBarT, 128);
           slack_forward();
+          if (!lastit) bar_arrive(kBarRS, 128);         // (the next burst's prologue announces its own)
         }
       }
       // burst end: all obstacle rows of the last iteration are in; the slack warp completes its rhs
@@ -2301,6 +2359,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
       for (int t = 0; t < 2; ++t) { ed_[t] = WSE_(di(t), k); oud_[t] = OU_(di(t), k); }
 #pragma unroll
       for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp, oo = o < R ? o : 0; eo_[q] = WSE_(NBR + oo, k); ouo_[q] = OU_(NBR + oo, k); }
+      double eh_[NHR > 0 ? NHR : 1], ouh_[NHR > 0 ? NHR : 1];
+#pragma unroll
+      for (int h = 0; h < NHR; ++h) { const int o = 4 * h + warp, oo = o < R ? o : 0; eh_[h] = WSE_(NBR + oo, k); ouh_[h] = OU_(NBR + oo, k); }
       // exchange: positions for the obstacle rows' A x; obstacle multipliers for the position / slack-input columns' A' y.
       // The buffers are the iteration's: wait until every warp has consumed the last iteration's obstacle terms.
       cta_sync();
@@ -2312,6 +2373,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         if (o < R && live) {
           const double yo = orh[q] * uo[q];
           T4[(4 * o) * NS + k] = og3[3 * q] * yo; T4[(4 * o + 1) * NS + k] = og3[3 * q + 1] * yo; T4[(4 * o + 2) * NS + k] = og3[3 * q + 2] * yo;
+          T4[(4 * o + 3) * NS + k] = yo;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < NHR; ++h) {
+        const int o = 4 * h + warp;
+        if (o < R && live) {
+          const double yo = HR(o, 2) * HR(o, 1);
+          T4[(4 * o) * NS + k] = HR(o, 4) * yo; T4[(4 * o + 1) * NS + k] = HR(o, 5) * yo; T4[(4 * o + 2) * NS + k] = HR(o, 6) * yo;
           T4[(4 * o + 3) * NS + k] = yo;
         }
       }
@@ -2396,6 +2466,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4], xs = XR[osl[q] * NS + k];
           row(og3[3 * q] * x0v + og3[3 * q + 1] * x1v + og3[3 * q + 2] * x2v - xs, zo[q], eo_[q]);
           cert(orh[q] * (uo[q] - ouo_[q]), eo_[q], olo[q], sh.obs_hi);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < NHR; ++h) {
+        const int o = 4 * h + warp;
+        if (o < R && hasu) {
+          const double x0v = m.RA[k * 6], x1v = m.RA[k * 6 + 2], x2v = m.RA[k * 6 + 4], xs = XR[(int)HR(o, 11) * NS + k];
+          row(HR(o, 4) * x0v + HR(o, 5) * x1v + HR(o, 6) * x2v - xs, HR(o, 0), eh_[h]);
+          cert(HR(o, 2) * (HR(o, 1) - ouh_[h]), eh_[h], HR(o, 3), sh.obs_hi);
         }
       }
       if constexpr (kWide) {
@@ -2489,7 +2568,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         if (st.adaptive_rho && st.adaptive_rho_interval) { int c2 = (iter / st.adaptive_rho_interval + 1) * st.adaptive_rho_interval; if (c2 < nb) nb = c2; }
         if constexpr (ASSIST) {                          // tell the assistants how long the burst is / to re-read the matrices
           if (warp == 0 && lane == 0) { cmd[0] = nb - iter; cmd[1] = reload ? 1 : 0; }
-          bar_sync(kBarCmd, 224);
+          bar_sync(kBarCmd, kCtaThreads);
           reload = false;
         }
         { MQ_T0(); iterate(nb - iter); MQ_T(4); }
@@ -2533,6 +2612,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           for (int t = 0; t < 2; ++t) rescale(rhd[t], ud[t], WSE_(di(t), k), bnd[t], bnd[t]);
 #pragma unroll
           for (int q = 0; q < NOW; ++q) { const int o = 4 * q + warp; if (o < R && hasu) rescale(orh[q], uo[q], WSE_(NBR + o, k), olo[q], sh.obs_hi); }
+#pragma unroll
+          for (int h = 0; h < NHR; ++h) {
+            const int o = 4 * h + warp;
+            if (o < R && hasu) {
+              double rv = HR(o, 2), uv = HR(o, 1);
+              rescale(rv, uv, WSE_(NBR + o, k), HR(o, 3), sh.obs_hi);
+              HR(o, 2) = rv; HR(o, 1) = uv;
+            }
+          }
           if constexpr (kWide) {
             if (hasu) for (int o = warp; o < R; o += 4) {
               double rv = ORH[o * NS + k], uv = UO[o * NS + k];
@@ -2624,7 +2712,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 #pragma unroll
     for (int h = 0; h < 24; ++h) wt[h] = make_double2(0.0, 0.0);
     for (;;) {
-      bar_sync(kBarCmd, 224);
+      bar_sync(kBarCmd, kCtaThreads);
       const int n = cmd[0], rl = cmd[1];
       if (n < 0) break;
       if (rl) {
@@ -2675,8 +2763,67 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
             sa0 = fma(w[2].y, a2.y, sa0); sa1 = fma(w[5].y, a2.y, sa1); sg0 = fma(w[8].y, c2.y, sg0); sg1 = fma(w[11].y, c2.y, sg1);
           }
           if (live) YB2[k * 3 + a] = make_double2(sa0 + sg0, sa1 + sg1);
-          bar_arrive(kBarY, 224);
+          bar_arrive(kBarY, kCtaThreads);
         }
+      }
+    }
+  }
+
+  // Row helper (threads 224..255 of a kHelp block): the obstacle rows o = 3, 7 — or all of them (kHelpAll) — of every iteration,
+  // on the values their owners left in shared memory (solve_role: load), exactly as obstacle_rows() runs a register row.  It
+  // waits for y like everyone else, announces the rows' terms at kBarT and follows the same burst commands as the assistants.
+  MQ_HD void helper_role(volatile int* cmd) {
+    constexpr int NROW = kHelpAll ? RC : (kHelp ? RC / 4 : 0), NR_ = NROW > 0 ? NROW : 1;
+    const int k = lane < NS ? lane : NS - 1;
+    const bool live = lane < NS, hasu = lane < N;
+    const double al = st.alpha, om = 1.0 - st.alpha;
+    double* const XR = m.YB + 6 * NS;
+    double* const T4 = XR + 2 * NS;
+    auto HR = [&](int o, int slot) -> double& { return m.ROW[(o * kHelpSlots + slot) * NS + k]; };
+    for (;;) {
+      bar_sync(kBarCmd, kCtaThreads);
+      const int n = cmd[0];
+      if (n < 0) break;
+      for (int it = 0; it < n; ++it) {
+        // everything but y and r11 is fetched before the barrier
+        double zo[NR_], uo[NR_], orh[NR_], olo[NR_], og3[3 * NR_], odg[NR_], ofs[3 * NR_];
+        int osl[NR_];
+#pragma unroll
+        for (int h = 0; h < NROW; ++h) {
+          const int o = kHelpAll ? h : 4 * h + 3;
+          zo[h] = HR(o, 0); uo[h] = HR(o, 1); orh[h] = HR(o, 2); olo[h] = HR(o, 3);
+          og3[3 * h] = HR(o, 4); og3[3 * h + 1] = HR(o, 5); og3[3 * h + 2] = HR(o, 6);
+          odg[h] = HR(o, 7); ofs[3 * h] = HR(o, 8); ofs[3 * h + 1] = HR(o, 9); ofs[3 * h + 2] = HR(o, 10);
+          osl[h] = (int)HR(o, 11);
+        }
+        bar_sync(kBarY, kCtaThreads);
+        const double yp0 = m.YB[k * 6], yp1 = m.YB[k * 6 + 2], yp2 = m.YB[k * 6 + 4];
+        // loads, arithmetic and stores in separate passes: the rows' chains then interleave (a store between two rows would
+        // order the next row's loads behind it)
+        double r11s[NR_], w0[NR_], w1[NR_], w2[NR_], w3[NR_];
+#pragma unroll
+        for (int h = 0; h < NROW; ++h) r11s[h] = XR[osl[h] * NS + k];
+#pragma unroll
+        for (int h = 0; h < NROW; ++h) {
+          const double sg = hasu ? odg[h] * (r11s[h] - ofs[3 * h] * yp0 - ofs[3 * h + 1] * yp1 - ofs[3 * h + 2] * yp2) : 0.0;
+          const double zt = og3[3 * h] * yp0 + og3[3 * h + 1] * yp1 + og3[3 * h + 2] * yp2 - sg;
+          const double v = al * zt + om * zo[h] + uo[h];
+          const double zn = v > olo[h] ? v : olo[h];
+          zo[h] = zn; uo[h] = v - zn;
+          const double t = orh[h] * (zn - uo[h]);
+          const double ts_ = hasu ? odg[h] * t : 0.0;
+          w0[h] = fma(ofs[3 * h], ts_, og3[3 * h] * t); w1[h] = fma(ofs[3 * h + 1], ts_, og3[3 * h + 1] * t);
+          w2[h] = fma(ofs[3 * h + 2], ts_, og3[3 * h + 2] * t); w3[h] = t;
+        }
+        if (live) {
+#pragma unroll
+          for (int h = 0; h < NROW; ++h) {
+            const int o = kHelpAll ? h : 4 * h + 3;
+            HR(o, 0) = zo[h]; HR(o, 1) = uo[h];
+            T4[(4 * o) * NS + k] = w0[h]; T4[(4 * o + 1) * NS + k] = w1[h]; T4[(4 * o + 2) * NS + k] = w2[h]; T4[(4 * o + 3) * NS + k] = w3[h];
+          }
+        }
+        bar_arrive(kBarT, 128);
       }
     }
   }

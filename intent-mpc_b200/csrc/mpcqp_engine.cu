@@ -377,7 +377,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     // one-per-SM launches use the variant with PCR assistant warps (224 threads, matrices of levels 1..3 in registers)
     int mode_a = 0;
     SolveKernel kern_solo = e->no_assist ? kern : pick_kernel(sh.NS, sh.R, want, &mode_a, true);
-    const int threads_solo = e->no_assist ? threads : 224;
+    const int threads_solo = e->no_assist ? threads : cta_threads(sh.R, true, false);
     CK(cudaFuncSetAttribute(kern_solo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
     if (bt.B <= e->num_sms || !bt.order) {
       const bool solo = bt.B <= e->num_sms;

@@ -39,16 +39,21 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
 }
 
 // CTA kernel: persistent, one 4-warp CTA per QP at a time (mode 2 of mpcqp_core.cuh), two CTAs per SM.  ASSIST: the
-// block has the SM to itself and carries three more warps that keep the PCR matrices of levels 1..3 in registers.
+// block has the SM to itself and carries three more warps that keep the PCR matrices of levels 1..3 in registers, and — with
+// four or more obstacle rows per stage — an eighth warp that runs the slack warp's obstacle rows (Qp::helper_role).
 template <int RT, bool ASSIST>
-__global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+__global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
                                                                                         const __grid_constant__ Batch bt, int ws_stride, int* counter) {
   extern __shared__ double smem[];
   __shared__ int s_next, s_flag, s_cmd[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Qp<30, RT, kModeCta, ASSIST> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
   if constexpr (ASSIST) {
-    if (warp >= 4) { qp.assist_role(warp - 4, s_cmd); return; }
+    if (warp >= 4) {
+      if (warp < 7) qp.assist_role(warp - 4, s_cmd);
+      else if constexpr (Qp<30, RT, kModeCta, ASSIST>::kHelp) qp.helper_role(s_cmd);
+      return;
+    }
   }
   // queue 0: all instances in natural order.  queue 1: the hard list only.  queue 2: everything not flagged hard, then
   // whatever is left of the hard list (so an over-long hard list does not serialise on the one-per-SM launch).
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(ASSIST ? 224 : 128, ASSIST ? 1 : 2) mpcqp_solv
   }
   if constexpr (ASSIST) {                                  // release the assistants
     if (threadIdx.x == 0) s_cmd[0] = -1;
-    asm volatile("bar.sync 5, 224;" ::: "memory");
+    Qp<30, RT, kModeCta, ASSIST>::bar_sync(5, Qp<30, RT, kModeCta, ASSIST>::kCtaThreads);
   }
 }
 

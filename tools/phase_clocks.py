@@ -1,7 +1,7 @@
 import sys, ctypes as C; sys.path.insert(0, ".")
 import numpy as np
 from intent_mpc_b200 import engine, workloads as W
-engine.LIB_PATH = "build/libmpcqp_timing.so"
+engine.LIB_PATH = "devlibs/libmpcqp_timing.so"
 eng = engine.Engine(0)
 names = ["setup", "leaf+rhs(warp0)", "pcr_factor", "load", "iterate", "info+check", "park+adapt", "store", "pcr:init", "pcr:invert", "pcr:products", "pcr:final", "setup:ruiz", "-", "-", "-"]
 for B in (1, 1024, 16384):
