@@ -2157,8 +2157,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     };
     auto iterate = [&](const int niter) {
       if constexpr (!AX) { slack_forward(); bar_arrive(kBarRS, 128); r11[0] -= ps[0]; r11[1] -= ps[1]; if (live) { XR[k] = r11[0]; XR[NS + k] = r11[1]; } }
-      for (int it = 0; it < niter; ++it) {
-        const bool lastit = it == niter - 1;
+      for (int left = niter; left > 0; --left) {
+        const bool lastit = left == 1;
+        const int it = niter - left;
         if (lastit && live) {                       // iterate k-1 for the infeasibility certificates (delta_x, delta_y)
 #pragma unroll
           for (int e = 0; e < NVR; ++e) { const int j = vj(e); OX_(j, k) = x[e]; OU_(8 + j, k) = ub[e]; }

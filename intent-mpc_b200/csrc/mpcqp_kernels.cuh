@@ -46,7 +46,11 @@ __global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASS
                                                                                         const __grid_constant__ Batch bt, int ws_stride, int* counter) {
   extern __shared__ double smem[];
   __shared__ int s_next, s_flag, s_cmd[2];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // one-per-SM blocks: opaque to the compiler, which would otherwise re-derive the lane (S2R + mask + compare, ~40 dependent
+  // cycles) at every use of a lane predicate in the iteration loop instead of keeping it in a register (two-per-SM blocks are
+  // better off with the register: 16k batch 445k -> 408k QPs/s with it)
+  if constexpr (ASSIST) asm volatile("" : "+r"(lane), "+r"(warp));
   Qp<30, RT, kModeCta, ASSIST> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
   if constexpr (ASSIST) {
     if (warp >= 4) {
