@@ -218,6 +218,20 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0, 128;" :::
 #define MQ_SYNC() ((void)0)
 #endif
 
+#if MQ_DEV
+// One bulk asynchronous copy (cp.async.bulk: the TMA engine moves the bytes, SASS UBLKCP) of `bytes` (a multiple of 16, both
+// addresses 16-byte aligned) from shared to global memory, issued and awaited by the calling thread.  The block's writes to `src`
+// must be ordered before the call by a barrier; the copy has landed when the call returns.
+__device__ __forceinline__ void bulk_store_shared_to_global(double* dst, const double* src, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(src);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes to src -> visible to the async proxy
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async.global;" ::: "memory");               // the block reads dst with ordinary loads afterwards
+}
+#endif
+
 MQ_HD double limit_scaling(double v) { v = v < kMinScaling ? 1.0 : v; return v > kMaxScaling ? kMaxScaling : v; }
 // 1/sqrt(v) of scaling.h's scale_data (sqrt then reciprocal, as OSQP computes it)
 #if MQ_DEV
@@ -2663,8 +2677,9 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     m.YB = smem0 + cold_slots(R) * NS;
     load_and_scale<4>(bt, b, warp);
     double* dst = bt.susp_cold + (size_t)slot * bt.susp_stride;
-    for (int i = threadIdx.x; i < cold_slots(R) * NS; i += 128) dst[i] = smem0[i];
     if (threadIdx.x == 0) {
+      // the cold block (55 KB at four obstacle rows) leaves shared memory as ONE bulk copy
+      bulk_store_shared_to_global(dst, smem0, (unsigned)(cold_slots(R) * NS * sizeof(double)));
       double* sc = bt.susp_scal + (size_t)slot * 8;
       sc[0] = c; sc[1] = cinv; sc[2] = rho; sc[3] = nq; sc[4] = nq_s; sc[5] = 0.0; sc[6] = 1.0; sc[7] = 0.0;
       bt.susp_list[slot] = b;
@@ -2844,7 +2859,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
       map_cold(m, keep.PCR, NS, R);
       load_and_scale<4>(bt, b, warp);           // all four warps; every thread ends with the same c, rho, |q| norms
       m = keep;
-      for (int i = threadIdx.x; i < cold_slots(R) * NS; i += 128) m.E[i] = m.PCR[i];
+      if (threadIdx.x == 0) bulk_store_shared_to_global(m.E, m.PCR, (unsigned)(cold_slots(R) * NS * sizeof(double)));   // one bulk copy
       cta_sync();
       MQ_T(0);
     }

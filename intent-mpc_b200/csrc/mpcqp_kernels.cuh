@@ -26,7 +26,7 @@ SolveKernel mpcqp_kernel_generic();
 template <int NST, int RT>
 __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
                                                          const __grid_constant__ Batch bt, int ws_stride, int* counter) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   Qp<NST, RT> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
   for (;;) {
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
 template <int RT, bool ASSIST>
 __global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
                                                                                         const __grid_constant__ Batch bt, int ws_stride, int* counter) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ int s_next, s_flag, s_cmd[2];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // one-per-SM blocks: opaque to the compiler, which would otherwise re-derive the lane (S2R + mask + compare, ~40 dependent
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASS
 template <int RT>
 __global__ void __launch_bounds__(128, 3) mpcqp_setup_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
                                                              const __grid_constant__ Batch bt, int ws_stride, int* counter) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ int s_next, s_slot;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Qp<30, RT, kModeCta, false> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
