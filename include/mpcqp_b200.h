@@ -85,7 +85,8 @@ double mpcqp_engine_last_kernel_ms(const mpcqp_engine* e);
 double mpcqp_engine_last_solve_kernel_ms(const mpcqp_engine* e);
 int64_t mpcqp_engine_last_launches(const mpcqp_engine* e);
 /* Which solve kernel the last batch ran: 2 = CTA kernel (one 4-warp CTA per QP, parallel-cyclic-reduction solve,
- * horizon 30, num_obs <= 8), 1 = one-warp-per-QP register-resident kernel (same shapes), 0 = generic one-warp
+ * horizon 30, num_obs <= 8; horizons 20 and 25 without the assistant variant), 1 = one-warp-per-QP register-resident kernel
+ * (horizon 30), 0 = generic one-warp
  * shared-memory kernel (any horizon/num_obs that fits); for problems WITHOUT the mpcPlanner stage structure (polyTrajSolver's
  * minimum-snap QPs): 5 = sparse generic kernel (banded L D L' of the reverse-Cuthill-McKee-ordered KKT matrix, one warp per QP;
  * taken when the half-bandwidth is <= 31), 4 = dense generic kernel (anything else up to n + m = 4096).  force_generic(4) pins the

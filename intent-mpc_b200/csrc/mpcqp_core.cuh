@@ -15,7 +15,7 @@
 //     Slack states, accelerations and slack inputs are "leaf" variables eliminated in closed form, leaving a 6x6
 //     block-tridiagonal system in (p_k, v_k).
 // Three ways to run it (Qp<NST, RT, QMODE, ASSIST>, see `Mem` below):
-//   * mode 2, the CTA kernels (horizon 30; the hot path): one 4-warp CTA per QP, warps 0-2 own one axis each, warp 3 the slack
+//   * mode 2, the CTA kernels (horizon 30: the hot path; also built for horizons 20 and 25): one 4-warp CTA per QP, warps 0-2 own one axis each, warp 3 the slack
 //     variables; iterates in registers from the first to the last iteration; the block-tridiagonal system is solved by block
 //     parallel cyclic reduction (pcr_factor_cta, solve_role) whose per-level 6x6 matrices fill shared memory; optional three
 //     assistant warps keep the matrices of the upper levels in registers (launches with one CTA per SM); a "wide" variant
@@ -113,7 +113,7 @@ struct Batch {              // device pointers
 //           side live in REGISTERS during a burst of iterations and are parked in the per-warp global scratch
 //           between bursts; shared memory holds the read-only scaled data, the twisted factor and the 6-vector
 //           exchange buffer.
-//   mode 2, CTA (horizon == 30): one 4-warp CTA per QP; the block-tridiagonal solve is a parallel cyclic reduction
+//   mode 2, CTA (horizons 17..30, lane = stage): one 4-warp CTA per QP; the block-tridiagonal solve is a parallel cyclic reduction
 //           whose per-level 6x6 matrices fill shared memory (86 KB); iterates live in registers split by axis
 //           across the warps; everything cold (factor workspace, parked iterates) is in the per-CTA global scratch.
 constexpr int kModeGeneric = 0, kModeWarp = 1, kModeCta = 2;
@@ -223,6 +223,7 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0, 128;" :::
 // addresses 16-byte aligned) from shared to global memory, issued and awaited by the calling thread.  The block's writes to `src`
 // must be ordered before the call by a barrier; the copy has landed when the call returns.
 __device__ __forceinline__ void bulk_store_shared_to_global(double* dst, const double* src, unsigned bytes) {
+  if (bytes & 8u) { bytes -= 8u; dst[bytes / 8] = src[bytes / 8]; }       // an odd number of doubles (odd horizon x odd slot count): the last one by hand
   const unsigned s = (unsigned)__cvta_generic_to_shared(src);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes to src -> visible to the async proxy
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s), "r"(bytes) : "memory");
@@ -278,7 +279,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   static constexpr int kCtaThreads = kHelp ? 256 : (ASSIST ? 224 : 128);
   static_assert(!kWide || (QMODE == kModeCta && ASSIST), "wide mode is a one-per-SM CTA kernel");
   static_assert(QMODE == kModeGeneric || NST > 0, "modes 1 and 2 need compile-time dims");
-  static_assert(QMODE != kModeCta || NST == 30, "the CTA path is built for horizon 30 (5 PCR levels)");
+  static_assert(QMODE != kModeCta || (NST >= 17 && NST <= 30), "the CTA path is built for horizons 17..30 (lane = stage, 5 PCR levels, matrices sized for 30 stages)");
   static constexpr int kWS = 6;    // fast mode: W holds one 6-vector per stage, stage-major (16-byte aligned rows)
   // Fast mode stores the per-stage chain data (G, W) in CHAIN order so that both chains of the twisted
   // recursion walk upward in memory: stages 0..mid-1 -> slots 0..mid-1, mid -> slot mid, stages N..mid+1 ->
@@ -2258,7 +2259,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
           if constexpr (!ASSIST) {
             const double2* const rb = RA2 + 3 * NS;
             const int c0 = k & 7;
-            const int t0 = c0, t1 = c0 + 8, t2 = c0 + 16, t3 = c0 + 24 <= N ? c0 + 24 : c0;       // (W_3 = 0 where the chain has three stages)
+            const int t0 = c0, t1 = c0 + 8, t2 = c0 + 16 <= N ? c0 + 16 : c0, t3 = c0 + 24 <= N ? c0 + 24 : c0;   // (W_p = 0 where the chain is shorter)
             double2 a0 = rb[t0 * 3], a1 = rb[t0 * 3 + 1], a2 = rb[t0 * 3 + 2];
             double2 c0_ = rb[t1 * 3], c1 = rb[t1 * 3 + 1], c2 = rb[t1 * 3 + 2];
             const double2* mn = M + (kPcrLevels - 1) * (kPcrLevelDoubles / 2);
@@ -2740,7 +2741,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
     double2* const YB2 = reinterpret_cast<double2*>(m.YB);
     const double2* const M = reinterpret_cast<const double2*>(m.PCR) + (a * 12) * NS + k;
     const int c0 = k & 7;
-    const int t0 = c0, t1 = c0 + 8, t2 = c0 + 16, t3 = c0 + 24 <= N ? c0 + 24 : c0;     // the stage's stride-8 chain (W_3 = 0 if it has three stages)
+    const int t0 = c0, t1 = c0 + 8, t2 = c0 + 16 <= N ? c0 + 16 : c0, t3 = c0 + 24 <= N ? c0 + 24 : c0;     // the stage's stride-8 chain (W_p = 0 where it is shorter)
     double2 mt[2][12], wt[24];
 #pragma unroll
     for (int l = 0; l < 2; ++l)

@@ -94,9 +94,21 @@ __global__ void mpc_order_kernel(int B, const int* hard, int* order, int* cnt) {
   }
 }
 
+// CTA kernels for horizons other than 30, registered by their translation units at load time (mpcqp_kernels.cuh)
+static SolveKernel g_alt_kernels[kAltNsMax + 1][kAltRMax + 1];
+AltKernelRegistration::AltKernelRegistration(int ns, int r, SolveKernel k) {
+  if (ns >= 0 && ns <= kAltNsMax && r >= 0 && r <= kAltRMax) g_alt_kernels[ns][r] = k;
+}
+SolveKernel mpcqp_kernel_cta_alt(int ns, int r) {
+  return (ns >= 0 && ns <= kAltNsMax && r >= 0 && r <= kAltRMax) ? g_alt_kernels[ns][r] : nullptr;
+}
+
 // want: 2 = CTA kernel if available, 1 = warp-fast kernel if available, 0 = generic.  *mode returns what was picked.
 static SolveKernel pick_kernel(int NS, int R, int want, int* mode, bool assist = false, bool* wide = nullptr, bool force_wide = false) {
   if (wide) *wide = false;
+  if (NS != 30 && want == kModeCta) {                      // other horizons: the plain 4-warp CTA kernel where it was built
+    if (SolveKernel k = mpcqp_kernel_cta_alt(NS, R)) { *mode = kModeCta; return k; }
+  }
   if (NS == 30 && want == kModeCta && wide && (R > 8 || (force_wide && R > 0)) && R <= kWideMax) {   // run-time obstacle count, rows in shared memory
     *mode = kModeCta; *wide = true;
     return mpcqp_kernel_cta_wide();
@@ -351,7 +363,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   if (occ < 1) { e->err = "solve kernel cannot be resident"; return MPCQP_ERR_CUDA; }
   long long grid = (long long)e->num_sms * occ;
   if (grid > bt.B) grid = bt.B;
-  const int wsd = ws_doubles(sh.NS, sh.R, mode);
+  const int wsd = (ws_doubles(sh.NS, sh.R, mode) + 1) & ~1;     // even: every block's scratch starts 16-byte aligned (bulk copies)
   CK(e->counter.need(4 * sizeof(int)));
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
   e->last_fast = mode;
@@ -376,8 +388,9 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     const size_t smem_solo = (size_t)e->max_smem_optin - 2048;   // more than half an SM: nothing else fits beside it
     // one-per-SM launches use the variant with PCR assistant warps (224 threads, matrices of levels 1..3 in registers)
     int mode_a = 0;
-    SolveKernel kern_solo = e->no_assist ? kern : pick_kernel(sh.NS, sh.R, want, &mode_a, true);
-    const int threads_solo = e->no_assist ? threads : cta_threads(sh.R, true, false);
+    const bool plain_solo = e->no_assist || sh.NS != 30;        // (the assistant / helper variants exist for horizon 30 only)
+    SolveKernel kern_solo = plain_solo ? kern : pick_kernel(sh.NS, sh.R, want, &mode_a, true);
+    const int threads_solo = plain_solo ? threads : cta_threads(sh.R, true, false);
     CK(cudaFuncSetAttribute(kern_solo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
     if (bt.B <= e->num_sms || !bt.order) {
       const bool solo = bt.B <= e->num_sms;
@@ -418,7 +431,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       if (e->hist_active) bt.suspend_at = 0;
       // Large batch: every SM stays busy with two CTAs to the end anyway, and a one-per-SM launch would only halve the
       // occupancy of the SMs it takes.  One launch, two CTAs per SM, the hard list first.
-      SolveKernel kset = e->split_setup ? pick_setup_kernel(sh.R) : nullptr;
+      SolveKernel kset = (e->split_setup && sh.NS == 30) ? pick_setup_kernel(sh.R) : nullptr;
       if (kset) {
         // Setup (Ruiz scaling, rho vector, warm start) in its own kernel, three CTAs per SM with only the cold block in shared
         // memory; it leaves every instance parked at iteration 0 and the solve launch resumes them all (hard list first).

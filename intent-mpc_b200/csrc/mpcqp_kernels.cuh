@@ -18,6 +18,13 @@ MPCQP_FAST_R_LIST
 #undef X
 SolveKernel mpcqp_kernel_cta_wide();
 SolveKernel mpcqp_kernel_generic();
+// CTA kernel (two-per-SM variant, also used alone on an SM) for horizons other than 30 — 20 is the code default of
+// mpcPlanner::initParam (mpcPlanner.cpp:19-173), 25 the case where 8 * horizon % 5 != 0 (castMPCToQPHessian's index quirk).  Every
+// (horizon, obstacle count) pair is a translation unit of its own (mpcqp_kernels.cu, -DMPCQP_GROUP_ALT_NS / _R) that registers its
+// kernel here when the library is loaded; the lookup returns nullptr for pairs that were not built.
+constexpr int kAltNsMax = 30, kAltRMax = 8;
+struct AltKernelRegistration { AltKernelRegistration(int ns, int r, SolveKernel k); };
+SolveKernel mpcqp_kernel_cta_alt(int ns, int r);
 
 #ifdef MPCQP_KERNEL_BODIES
 // ------------------------------------------------------------------------------------------------
@@ -41,8 +48,8 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
 // CTA kernel: persistent, one 4-warp CTA per QP at a time (mode 2 of mpcqp_core.cuh), two CTAs per SM.  ASSIST: the
 // block has the SM to itself and carries three more warps that keep the PCR matrices of levels 1..3 in registers, and — with
 // four or more obstacle rows per stage — an eighth warp that runs the slack warp's obstacle rows (Qp::helper_role).
-template <int RT, bool ASSIST>
-__global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
+template <int RT, bool ASSIST, int NST = 30>
+__global__ void __launch_bounds__(Qp<NST, RT, kModeCta, ASSIST>::kCtaThreads, ASSIST ? 1 : 2) mpcqp_solve_cta_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Settings st,
                                                                                         const __grid_constant__ Batch bt, int ws_stride, int* counter) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next, s_flag, s_cmd[2];
@@ -51,11 +58,12 @@ __global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASS
   // cycles) at every use of a lane predicate in the iteration loop instead of keeping it in a register (two-per-SM blocks are
   // better off with the register: 16k batch 445k -> 408k QPs/s with it)
   if constexpr (ASSIST) asm volatile("" : "+r"(lane), "+r"(warp));
-  Qp<30, RT, kModeCta, ASSIST> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  using Q = Qp<NST, RT, kModeCta, ASSIST>;
+  Q qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
   if constexpr (ASSIST) {
     if (warp >= 4) {
       if (warp < 7) qp.assist_role(warp - 4, s_cmd);
-      else if constexpr (Qp<30, RT, kModeCta, ASSIST>::kHelp) qp.helper_role(s_cmd);
+      else if constexpr (Q::kHelp) qp.helper_role(s_cmd);
       return;
     }
   }
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(Qp<30, RT, kModeCta, ASSIST>::kCtaThreads, ASS
   }
   if constexpr (ASSIST) {                                  // release the assistants
     if (threadIdx.x == 0) s_cmd[0] = -1;
-    Qp<30, RT, kModeCta, ASSIST>::bar_sync(5, Qp<30, RT, kModeCta, ASSIST>::kCtaThreads);
+    Q::bar_sync(5, Q::kCtaThreads);
   }
 }
 

@@ -190,11 +190,38 @@ def test_shapes_weights_and_hessian_quirk(eng, horizon, num_obs, kw):
     p = W.MpcParams(horizon=horizon, **kw)
     mb = W.static_batch(24, num_obs=num_obs, params=p, seed0=4000 + horizon)
     out = eng.solve_mpc_batch(mb)
+    assert eng.last_path == ("cta" if horizon <= 30 else "generic")      # horizons 20, 25, 30 have CTA kernels
     ref = _oracle().solve_batch(to_qp_batch(mb), want_y=False)
     assert (out["status"] == ref["status"]).all() and (out["iter"] == ref["iter"]).all()
     assert (out["rho_updates"] == ref["rho_updates"]).all()
     assert rel_inf(out["x"], ref["x"]).max() < TOL
     assert np.abs((out["obj"] - ref["obj"]) / ref["obj"]).max() < TOL
+
+
+@pytest.mark.parametrize("horizon", [20, 25])
+def test_other_horizons_on_the_cta_kernel_with_migration(eng, horizon):
+    """Horizons 20 (the code default of mpcPlanner::initParam) and 25 run the 4-warp CTA / PCR kernel built for that stage count
+    (chains of the composed final operator are shorter; no assistant variant): a batch large enough for the two-launch regime
+    (hard list, two per SM, parked instances resumed one per SM) against the oracle and against the generic kernel."""
+    p = W.MpcParams(horizon=horizon)
+    mb = W.static_batch(400, num_obs=4, params=p, seed0=9000 + horizon)
+    eng.use_history(False)
+    try:
+        out = eng.solve_mpc_batch(mb, want_y=True)
+        assert eng.last_path == "cta"
+        again = eng.solve_mpc_batch(mb, want_y=True)
+        eng.force_generic("generic")
+        gen = eng.solve_mpc_batch(mb)
+        assert eng.last_path == "generic"
+    finally:
+        eng.force_generic("cta"); eng.use_history(True)
+    for k in ("x", "y", "iter", "status", "obj"):
+        assert np.array_equal(out[k], again[k]), k
+    ref = _oracle().solve_batch(to_qp_batch(mb), want_y=True)
+    assert (out["status"] == ref["status"]).all() and (out["iter"] == ref["iter"]).all() and (out["rho_updates"] == ref["rho_updates"]).all()
+    assert (gen["status"] == ref["status"]).all() and (gen["iter"] == ref["iter"]).all()
+    assert rel_inf(out["x"], ref["x"]).max() < TOL and np.abs((out["obj"] - ref["obj"]) / ref["obj"]).max() < TOL
+    assert out["iter"].max() > 100                      # something was parked and resumed
 
 
 def test_ragged_batches_and_mixed_rows(eng):
