@@ -211,7 +211,7 @@ template <> struct DimsT<0, 0> {
 #define MQ_FOR_STAGES(k) for (int k = lane; k < NS; k += 32)
 #define MQ_SYNC() __syncwarp()
 // Barrier of the four solver warps of a CTA-mode block (threads 0..127).  The block may carry three more warps (PCR
-// assistants, threads 128..223) that never take part in it.
+// assistants, threads 128..223) and a row helper (threads 224..255) that never take part in it.
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
 #else
 #define MQ_FOR_STAGES(k) for (int k = 0; k < NS; ++k)
@@ -1589,9 +1589,10 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
   // ================================================================================================
   // mode 2: one 4-warp CTA per QP.  lane = stage in every warp; warps 0..2 own one axis each (variables p, v, a of
   // that axis, their two dynamics rows and three box rows, and rows 2w, 2w+1 of the PCR solve); warp 3 owns the
-  // slack states / slack inputs, their rows and the obstacle rows.  All iterates live in registers during a burst;
-  // the warps exchange the reduced right-hand side, the PCR intermediate vectors and the solution through small
-  // shared-memory buffers with named barriers (6 per iteration).
+  // slack states / slack inputs and their rows; obstacle row o belongs to warp o % 4.  All iterates live in registers during
+  // a burst; the warps exchange the reduced right-hand side, the PCR intermediate vectors and the solution through small
+  // shared-memory buffers with named barriers (kBarRS, kBarAll, [kBarAxis | kBarH1, kBarA], kBarY, kBarT per iteration).
+  // One-per-SM blocks add three PCR assistants (assist_role) and a row helper (helper_role).
   // ================================================================================================
   static MQ_HD void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
   static MQ_HD void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }

@@ -386,7 +386,8 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     // the instances flagged hard (they run to max_iter and would otherwise form the tail of the batch) one per SM on
     // the main stream, everything else two per SM on the side stream, on whatever SMs the first launch leaves free.
     const size_t smem_solo = (size_t)e->max_smem_optin - 2048;   // more than half an SM: nothing else fits beside it
-    // one-per-SM launches use the variant with PCR assistant warps (224 threads, matrices of levels 1..3 in registers)
+    // one-per-SM launches use the variant with PCR assistant warps (224 threads, matrices of levels 1..3 in registers) and, from
+    // four obstacle rows per stage on, the row helper (256 threads)
     int mode_a = 0;
     const bool plain_solo = e->no_assist || sh.NS != 30;        // (the assistant / helper variants exist for horizon 30 only)
     SolveKernel kern_solo = plain_solo ? kern : pick_kernel(sh.NS, sh.R, want, &mode_a, true);
