@@ -470,7 +470,7 @@ def run_b200(args, rank, world, local_rank):
         "status_hist": _hist(status),
         "roofline": {"bound": "fp64_fma", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                      "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per step (both solve launches), ncu capture in profiles/; algorithmic: %d" % int(algorithmic_bytes(N, R) * B),
-                     "kernel": "mpcqp_solve_cta_kernel (hard-queue launch with PCR assistants + two-per-SM launch)", "kernel_ms": solve_avg_ms,
+                     "kernel": "mpcqp_solve_cta_kernel (two-per-SM launch + one-per-SM launches of the hard list and of the parked instances: 4 solver warps, 3 PCR assistants, row helper)", "kernel_ms": solve_avg_ms,
                      "peak_source": "fp64 DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "algorithmic_flops_per_launch": flops,
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
