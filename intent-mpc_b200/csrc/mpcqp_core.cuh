@@ -99,6 +99,10 @@ struct Batch {              // device pointers
   // (queue 4) resumes it, bit-identically, where it stopped
   int suspend_at, susp_cap, susp_stride;
   double* susp_cold; double* susp_scal; int* susp_list; int* susp_count;
+  // order in which the parked instances are resumed: susp_key[slot] = primal residual when the instance was parked (a large
+  // one after a few dozen iterations marks the instances that run long), susp_order = slots by decreasing key (or nullptr:
+  // slot order)
+  double* susp_key; const int* susp_order;
   const double* limits;         // [B][2] per-instance (max_vel, max_acc) replacing the batch-uniform box on v and a (CTA kernels), or nullptr
   const int* nobs;              // [B] obstacle rows per stage of each instance (wide CTA kernel only; R is then the stride of
                                 // g / low / slack and m the stride of y), or nullptr
@@ -2898,6 +2902,7 @@ template <int NST, int RT, int QMODE = (NST > 0 ? kModeWarp : kModeGeneric), boo
         sc[0] = c; sc[1] = cinv; sc[2] = rho; sc[3] = nq; sc[4] = nq_s; sc[5] = (double)rho_updates; sc[6] = susp_refactor_ ? 1.0 : 0.0;
         sc[7] = (double)susp_K_;
         bt.susp_list[susp_slot_] = b;
+        if (bt.susp_key) bt.susp_key[susp_slot_] = pri_res == pri_res ? pri_res : 1e300;
       }
       cta_sync();
     } else {

@@ -87,6 +87,18 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
   }
 }
 
+// Parked instances by decreasing key (rank sort: one thread per slot counts the slots ahead of it; n is a few hundred to a few
+// thousand).  Ties and equal keys keep slot order.
+__global__ void mpc_rank_parked_kernel(const int* count, int cap, const double* key, int* order) {
+  int n = *count; if (n > cap) n = cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double ki = key[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) { const double kj = key[j]; r += (kj > ki || (kj == ki && j < i)) ? 1 : 0; }
+    order[r] = i;
+  }
+}
+
 // Compacts the indices of the instances flagged `hard` into order[0 .. cnt[0]).
 __global__ void mpc_order_kernel(int B, const int* hard, int* order, int* cnt) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
@@ -190,10 +202,10 @@ struct mpcqp_engine {
   cudaEvent_t evf = nullptr, evj = nullptr;                  // fork / join of the side stream
   std::string err;
   int live_problems = 0; bool destroy_pending = false;       // mpcqp_problem handles keep their engine alive (see mpcqp_engine_destroy)
-  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int split_setup = 1; int migrate = 1, suspend_at = 300, suspend_at_small = 100, hist_active = 0;
+  double last_ms = 0.0, last_solve_ms = 0.0; long long last_launches = 0; int last_fast = 0; int force_generic = 0; int no_assist = 0; int dyn_per_instance = 0; int large_batch_factor = 0; int split_setup = 1; int migrate = 1, suspend_at = 300, suspend_at_small = 25, hist_active = 0;
   const int32_t* nobs_host = nullptr; const double* limits_host = nullptr;
   // structured-problem buffers (device)
-  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_ctr, cand_tab;
+  DevBuf pd, slack, q, x0s, g, low, ws, counter, hard, order, hist, dbg, nobs, limits, susp_cold, susp_scal, susp_list, susp_key, susp_order, susp_ctr, cand_tab;
   int hist_B = 0, hist_R = -1, use_history = 1;       // iteration counts of the previous batch call (same B, R) as a scheduling hint
   // staging for the *_host entry point
   DevBuf in_x0, in_xref, in_c, in_semi, in_yaw, in_lin, in_warm, out_x, out_y, out_i, out_d;
@@ -407,9 +419,13 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     // Migration of long-running instances: whoever is still iterating after suspend_at iterations in a two-per-SM launch
     // parks its state; a follow-up launch resumes these instances (bit-identically) — on SMs of their own for small
     // batches, evenly spread for large ones — so that an instance nobody could predict to be long does not form the tail.
-    // (a small batch waits for its longest instance anyway: the sooner the long ones get an SM — and its assistant warps — of
-    // their own the better; measured on 1,024 QPs: 100 iterations 6.42 ms, 300 iterations 6.53 ms per step)
-    const int suspend_at = bt.B <= 14 * (long long)e->num_sms ? e->suspend_at_small : e->suspend_at;
+    // In the two-launch regime (below) the two-per-SM launch is a probe: setup, factorisation and ONE check interval, then
+    // everybody still running is parked and the one-per-SM launch resumes them by decreasing primal residual — a step waits
+    // for its longest instance anyway, and the residual after 25 iterations tells which ones those are (measured, parked
+    // after 25 / 100 / 300 iterations: 1,024 QPs 5.97 / 6.38 / 6.53 ms, 2,048 QPs 6.56 / 7.68 / 7.85 ms, 4,096 QPs 10.5 / 11.4 /
+    // 10.6 ms).  Large batches without the setup kernel keep 300.
+    const int lb_factor = e->large_batch_factor > 0 ? e->large_batch_factor : (e->hist_active ? 13 : (e->split_setup ? 26 : 40));
+    const int suspend_at = bt.B < (long long)lb_factor * grid ? e->suspend_at_small : e->suspend_at;
     const bool migrate = e->migrate && suspend_at > 0 && suspend_at < st.max_iter;
     if (migrate) {
       const int cap = bt.B < 8192 ? bt.B : 8192;
@@ -422,10 +438,13 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
       bt.suspend_at = suspend_at; bt.susp_cap = cap; bt.susp_stride = stride;
       bt.susp_cold = e->susp_cold.as<double>(); bt.susp_scal = e->susp_scal.as<double>();
       bt.susp_list = e->susp_list.as<int>(); bt.susp_count = e->susp_ctr.as<int>();
+      CK(e->susp_key.need((size_t)cap * sizeof(double)));
+      CK(e->susp_order.need((size_t)cap * sizeof(int)));
+      bt.susp_key = e->susp_key.as<double>();
     }
     // measured crossovers (configs[1]-shaped batches): with a history the single launch (setup split off into its own kernel)
-    // wins from ~13 x 296 instances, without one (nothing known about the instances) the two launches + migration win up to ~20 x 296
-    const int lb_factor = e->large_batch_factor > 0 ? e->large_batch_factor : (e->hist_active ? 13 : (e->split_setup ? 20 : 40));
+    // wins from ~13 x 296 instances, without one (nothing known about the instances) the probe + ordered resume win up to ~26 x 296
+    // (6,144 QPs: 16.0 against 17.0 ms; 8,192: 21.5 either way)
     if (bt.B >= (long long)lb_factor * grid) {
       // (migration: the follow-up launch only starts when this one has drained, so it pays only where nothing is known
       // about the instances — no iteration history — and the batch is long enough to amortise the second launch)
@@ -491,7 +510,12 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     kern<<<(unsigned)grid, threads, smem, e->stream2>>>(sh, st, bn, wsd, e->counter.as<int>());
     CK(cudaGetLastError());
     if (migrate) {                                         // the parked instances, one per SM (with assistants), behind the second launch
+      // ... those with the largest primal residual first: after a few dozen iterations it separates the instances that run to
+      // max_iter from the rest almost perfectly (8,192 configs[1] instances: all long ones among the first 148 of every 1,024)
+      mpc_rank_parked_kernel<<<8, 256, 0, e->stream2>>>(bt.susp_count, bt.susp_cap, bt.susp_key, e->susp_order.as<int>());
+      CK(cudaGetLastError());
       Batch br = bt; br.queue = 4; br.suspend_at = 0; br.ws = e->ws.as<double>() + (size_t)(gh + grid) * wsd;
+      br.susp_order = e->susp_order.as<int>();
       kern_solo<<<(unsigned)gh, threads_solo, smem_solo, e->stream2>>>(sh, st, br, wsd, e->counter.as<int>());
       CK(cudaGetLastError());
       e->last_launches += 1;

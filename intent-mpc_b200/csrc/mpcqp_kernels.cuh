@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(Qp<NST, RT, kModeCta, ASSIST>::kCtaThreads, AS
       const int slot = s_next;
       cta_sync();
       if (slot >= n) break;
-      qp.run_cta_resume(bt, slot, warp, &s_flag, s_cmd);
+      qp.run_cta_resume(bt, bt.susp_order ? bt.susp_order[slot] : slot, warp, &s_flag, s_cmd);
     }
   } else {
   bool natural = bt.queue != 1 && bt.queue != 3;
