@@ -460,7 +460,7 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(B, R), "batch_per_gpu": B, "num_obs": R, "horizon": p.horizon,
                    "pins": "adaptive_rho_interval=25,time_limit=0", "l2": "flushed between steps (256 MiB write)",
-                   "schedule": "independent batches: the engine's hint from the previous call is OFF; instances whose fixed start violates a stage-0 obstacle row start first; anything still running after 100 iterations is parked and resumed bit-identically on an SM of its own (4 solver warps + 3 PCR assistants + a row helper) by a follow-up launch; results never depend on scheduling (extras.headline_same_batch_with_history = the receding-horizon case)",
+                   "schedule": "independent batches: the engine's hint from the previous call is OFF; instances whose fixed start violates a stage-0 obstacle row start first; the two-per-SM launch is a probe (setup, factorisation, 25 iterations); anything still running is parked and resumed bit-identically on an SM of its own (4 solver warps + 3 PCR assistants + a row helper) by a follow-up launch, largest primal residual first; results never depend on scheduling (extras.headline_same_batch_with_history = the receding-horizon case)",
                    "kernel_path": eng.last_path, "iterations_total": iters_timed, "iterations_max": int(max(int(v.max()) for v in it_all))},
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / K},
@@ -469,7 +469,7 @@ def run_b200(args, rank, world, local_rank):
         "batch_step_ms_p50": float(np.median(step_ms)),
         "status_hist": _hist(status),
         "roofline": {"bound": "fp64_fma", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                     "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per step (both solve launches), ncu capture in profiles/; algorithmic: %d" % int(algorithmic_bytes(N, R) * B),
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per step (all solve launches; ncu flushes the caches between launches, so the parked cold blocks count), ncu capture in profiles/; algorithmic: %d" % int(algorithmic_bytes(N, R) * B),
                      "kernel": "mpcqp_solve_cta_kernel (two-per-SM launch + one-per-SM launches of the hard list and of the parked instances: 4 solver warps, 3 PCR assistants, row helper)", "kernel_ms": solve_avg_ms,
                      "peak_source": "fp64 DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "algorithmic_flops_per_launch": flops,

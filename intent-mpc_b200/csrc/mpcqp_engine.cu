@@ -90,13 +90,20 @@ __global__ void mpc_assemble_kernel(const __grid_constant__ AsmArgs a) {
 // Parked instances by decreasing key (rank sort: one thread per slot counts the slots ahead of it; n is a few hundred to a few
 // thousand).  Ties and equal keys keep slot order.
 __global__ void mpc_rank_parked_kernel(const int* count, int cap, const double* key, int* order) {
+  __shared__ double tile[1024];
   int n = *count; if (n > cap) n = cap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double ki = key[i];
-    int r = 0;
-    for (int j = 0; j < n; ++j) { const double kj = key[j]; r += (kj > ki || (kj == ki && j < i)) ? 1 : 0; }
-    order[r] = i;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double ki = i < n ? key[i] : 0.0;
+  int r = 0;
+  for (int j0 = 0; j0 < n; j0 += 1024) {                   // every block walks all keys, 1,024 at a time through shared memory
+    const int m = n - j0 < 1024 ? n - j0 : 1024;
+    __syncthreads();
+    for (int t = threadIdx.x; t < m; t += blockDim.x) tile[t] = key[j0 + t];
+    __syncthreads();
+#pragma unroll 8
+    for (int t = 0; t < m; ++t) { const double kj = tile[t]; r += (kj > ki || (kj == ki && j0 + t < i)) ? 1 : 0; }
   }
+  if (i < n) order[r] = i;
 }
 
 // Compacts the indices of the instances flagged `hard` into order[0 .. cnt[0]).
@@ -512,7 +519,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
     if (migrate) {                                         // the parked instances, one per SM (with assistants), behind the second launch
       // ... those with the largest primal residual first: after a few dozen iterations it separates the instances that run to
       // max_iter from the rest almost perfectly (8,192 configs[1] instances: all long ones among the first 148 of every 1,024)
-      mpc_rank_parked_kernel<<<8, 256, 0, e->stream2>>>(bt.susp_count, bt.susp_cap, bt.susp_key, e->susp_order.as<int>());
+      mpc_rank_parked_kernel<<<(unsigned)((bt.susp_cap + 127) / 128), 128, 0, e->stream2>>>(bt.susp_count, bt.susp_cap, bt.susp_key, e->susp_order.as<int>());
       CK(cudaGetLastError());
       Batch br = bt; br.queue = 4; br.suspend_at = 0; br.ws = e->ws.as<double>() + (size_t)(gh + grid) * wsd;
       br.susp_order = e->susp_order.as<int>();
