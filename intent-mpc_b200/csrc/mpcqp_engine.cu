@@ -387,7 +387,7 @@ static int launch_solve(mpcqp_engine* e, const Shape& sh, const Settings& st, Ba
   CK(cudaMemsetAsync(e->counter.p, 0, sizeof(int), e->stream));
   e->last_fast = mode;
   bt.queue = 0; bt.nhard = nullptr;
-  if (mode != kModeCta) { bt.order = nullptr; bt.hard = nullptr; }
+  if (mode != kModeCta) { if (bt.order) bt.nhard = e->counter.as<int>() + 1; }      // one-warp kernels: hard list first, then the rest
   if (mode == kModeCta && wide) {
     // one CTA (4 solver warps + 3 PCR assistants) per SM; instances flagged hard first, then the rest
     CK(e->ws.need((size_t)grid * wsd * sizeof(double)));

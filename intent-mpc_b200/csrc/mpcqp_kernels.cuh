@@ -36,11 +36,20 @@ __global__ void __launch_bounds__(32) mpcqp_solve_kernel(const __grid_constant__
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   Qp<NST, RT> qp(smem, sh, st, bt, bt.ws + (size_t)blockIdx.x * ws_stride, lane);
+  // queue 3 (bt.order given): the instances flagged hard first, then the others in natural order; otherwise natural order
+  bool hardq = bt.order != nullptr;
   for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(counter, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= bt.B) break;
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(counter + (hardq || !bt.order ? 0 : 3), 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    int b = idx;
+    if (hardq) {
+      if (idx >= *bt.nhard) { hardq = false; continue; }
+      b = bt.order[idx];
+    } else {
+      if (idx >= bt.B) break;
+      if (bt.order && bt.hard[idx]) continue;
+    }
     qp.run(bt, b);
   }
 }
